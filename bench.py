@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- columns/s for all-sky-with-aerosols `update_fluxes!` (ncol = 1e5 per GPU, nlay = 64, Float32).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--ncol C]
+
+One process per GPU (torchrun for N > 1; RANK / LOCAL_RANK / WORLD_SIZE from the env).  A "step" is one
+full `update_fluxes!` (prepare_atmosphere! + LW two-stream + SW two-stream + net flux, clouds with McICA,
+15-species aerosols) over one batch of synthetic columns (seeded generator).  Columns shard
+across ranks (weak scaling: `--ncol` columns PER GPU); for N > 1 the step ends with the NCCL all-gather of
+the eight (nlev, ncol) flux views (north star).
+
+Rank 0 prints ONE JSON line.  `value` = whole-job columns/s with inputs resident in HBM; `e2e` = the same
+step driven from pinned HOST buffers (H2D of every input + D2H of every flux inside the timed region);
+`roofline` = algorithmic HBM bytes of the dominant kernel / its CUDA-event time vs the measured HBM peak
+(this path is FP32/LUT-gather bound, not HBM bound -- see DESIGN.md; the FP32 view is in `roofline_fp32`);
+`cpu_baseline` = the restated reference (oracle/, OpenMP, all host cores) on a bounded column sample.
+`--impl reference` times that CPU restatement alone (the reference itself is Julia and cannot run here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "columns/sec for all-sky update_fluxes! (ncol=1e5, nlay=64) at 1/2/4/8 B200"
+PARAMS = dict(grav=9.80665, molmass_dryair=0.028964, molmass_water=0.018016)
+ALGO_FLOPS_PER_COL = 6.8e6      # SURVEY.md §8d (+-30 %)
+FP32_PEAK_TFLOPS = 74.4         # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
+
+
+def workload_name(ncol, nlay):
+    return (f"all_sky_with_aerosols: ncol={ncol}/GPU nlay={nlay} Float32, 256 LW + 224 SW g-points, two-stream LW+SW, "
+            "cld_frac=1 (McICA), 15-species aerosols, cos_zenith=0.86, synthetic LUT pack seed 7")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_state(ncol, nlay, rank):
+    import rrtmgp_b200 as R
+    return R.synthetic.make_atmosphere(ncol, nlay, seed=20260101 + rank, cld_frac=1.0, cos_zenith=0.86)
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the restated reference CPU path (oracle/), all host threads, bounded sample."""
+    if rank != 0:
+        return
+    import rrtmgp_b200 as R
+    from oracle import Oracle
+    ncol_s = min(args.ncol, args.cpu_sample)
+    pack = R.synthetic.make_lut_pack(seed=7)
+    st = make_state(ncol_s, args.nlay, 0)
+    o = Oracle(pack, np.float32)
+    for _ in range(args.warmup):
+        o.update_fluxes(st, seed=1, params=PARAMS)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.update_fluxes(st, seed=1, params=PARAMS)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = ncol_s / dt
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "columns/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.ncol, args.nlay)},
+            "cpu_baseline": {"value": v, "unit": "columns/s", "cores": cores, "kind": "port",
+                             "sample": f"{ncol_s} of {args.ncol} columns per step (cost is linear in ncol); "
+                                       "C++ restatement of the Julia reference, OpenMP over columns"},
+            "e2e": {"value": v, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--ncol", type=int, default=100000, help="columns per GPU")
+    ap.add_argument("--nlay", type=int, default=64)
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="columns of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import rrtmgp_b200 as R
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ncol, nlay, nlev = args.ncol, args.nlay, args.nlay + 1
+    pack = R.synthetic.make_lut_pack(seed=7)
+    st = make_state(ncol, nlay, rank)
+    gp = R.RRTMGPGridParams(FT=np.float32, domain_nlay=nlay, ncol=ncol, device=local_rank)
+    rm = R.AllSkyRadiation(aerosol_radiation=True, reset_rng_seed=True)
+    s = R.RRTMGPSolver(gp, rm, R.default_parameters(**PARAMS), pack, col_offset=rank * ncol)
+    s.set_state(st)
+    R.compute_relative_humidity(s)
+
+    flux_keys = ("lw_flux_up", "lw_flux_dn", "lw_flux_net", "sw_flux_up", "sw_flux_dn", "sw_flux_net",
+                 "sw_flux_dn_dir", "net_flux")
+    gathered = None
+    if world > 1:   # (nlev, ncol) views are contiguous per shard: one all-gather per array, grouped
+        gathered = {k: torch.empty(world * ncol, nlev, dtype=torch.float32, device=dev) for k in flux_keys}
+
+    def step(seed):
+        R.update_fluxes(s, seed)
+        if world > 1:
+            works = [dist.all_gather_into_tensor(gathered[k], s.buffers[k], async_op=True) for k in flux_keys]
+            for w in works:
+                w.wait()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step(100 + i)
+            launches += s.last_launch_count
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * ncol / (ms * 1e-3)
+
+    # --- dominant kernel: per-kernel CUDA-event timing on the launching stream ---
+    def time_call(fn, n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    k_steps = max(2, min(args.steps, 5))
+    ms_prep = time_call(lambda i: R.prepare_atmosphere(s), k_steps)
+    ms_lw = time_call(lambda i: R.update_lw_fluxes(s, 200 + i), k_steps)
+    ms_sw = time_call(lambda i: R.update_sw_fluxes(s, 200 + i), k_steps)
+    esz = 4
+    in_common = (nlay * 4 + nlay * 2 + nlay * 5 + 2 * nlay * 15) * esz    # layerdata, h2o+o3, cloud, aerosols
+    lw_bytes = in_common + (nlev + 1 + 16) * esz + 3 * nlev * esz           # + t_lev, t_sfc, emis; out up/dn/net
+    sw_bytes = in_common + (2 + 2 * 14) * esz + (4 + 1) * nlev * esz + nlev * esz  # + mu0, toa, albedos; out 4 + net (+ lw_net read)
+    dom = "LW" if ms_lw >= ms_sw else "SW"
+    dom_ms, dom_bytes = (ms_lw, lw_bytes) if dom == "LW" else (ms_sw, sw_bytes)
+    hbm_peak, peak_src = peaks()
+    achieved = ncol * dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": f"solve_kernel<float,{'LW_2STREAM' if dom == 'LW' else 'SW_2STREAM'}>",
+                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": ncol * dom_bytes, "peak_source": peak_src,
+                "note": "fused path is FP32/LUT-gather bound by construction (SURVEY.md §8d): the HBM fraction is "
+                        "<< 1; see roofline_fp32"}
+    cols_per_s_gpu = ncol / ((ms_prep + ms_lw + ms_sw) * 1e-3)
+    roofline_fp32 = {"bound": "fp32", "achieved": cols_per_s_gpu * ALGO_FLOPS_PER_COL / 1e12, "peak": FP32_PEAK_TFLOPS,
+                     "unit": "TFLOP/s", "frac": cols_per_s_gpu * ALGO_FLOPS_PER_COL / 1e12 / FP32_PEAK_TFLOPS,
+                     "peak_source": "nominal 148 SM x 128 x 2 x 1.965 GHz", "algorithmic_flops_per_column": ALGO_FLOPS_PER_COL}
+
+    # --- e2e: host buffers, H2D of every input + D2H of every flux inside the timed region ---
+    e2e = None
+    if not args.no_e2e:
+        in_keys = [k for k in ("layerdata", "p_lev", "t_lev", "t_sfc", "vmr_h2o", "vmr_o3", "vmr", "cld_r_eff_liq",
+                               "cld_r_eff_ice", "cld_path_liq", "cld_path_ice", "cld_frac", "aero_mass", "aero_size",
+                               "sfc_emis", "cos_zenith", "toa_flux", "sfc_alb_direct", "sfc_alb_diffuse")
+                   if s.buffers.get(k) is not None]
+        host_in = {k: s.buffers[k].cpu().pin_memory() for k in in_keys}
+        out_keys = list(flux_keys) + ["cld_cover_lw", "cld_cover_sw", "aod_sw_ext", "aod_sw_sca"]
+        host_out = {k: torch.empty_like(s.buffers[k], device="cpu").pin_memory() for k in out_keys}
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+        def e2e_step(seed):
+            for k in in_keys:
+                s.buffers[k].copy_(host_in[k], non_blocking=True)
+            R.update_fluxes(s, seed)
+            for k in out_keys:
+                host_out[k].copy_(s.buffers[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for i in range(n_e2e):
+            e2e_step(300 + i)
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ncol / float(dt.item()), "unit": "columns/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": float(dt.item()) * 1e3}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import Oracle
+        ncs = min(ncol, args.cpu_sample)
+        sub = {k: (v[:ncs] if (v.ndim >= 1 and v.shape[0] == ncol) else v) for k, v in st.items()}
+        o = Oracle(pack, np.float32)
+        o.update_fluxes(sub, seed=1, params=PARAMS)
+        t0 = time.perf_counter()
+        o.update_fluxes(sub, seed=1, params=PARAMS)
+        dtc = time.perf_counter() - t0
+        cpu_baseline = {"value": ncs / dtc, "unit": "columns/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"first {ncs} of {ncol} columns, one update_fluxes (cost is linear in ncol); C++ "
+                                  "restatement of the Julia reference CPU path, OpenMP over columns, Float32"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(ncol, nlay), "global_columns": world * ncol,
+                           "parallelism": f"column shards x{world}" + (", NCCL all-gather of 8 flux views" if world > 1 else ""),
+                           "l2_policy": f"inputs {ncol * (in_common + 400) / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "roofline_fp32": roofline_fp32, "cpu_baseline": cpu_baseline,
+                "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,164 @@
+/* rrtmgp_b200.h -- C ABI of the B200-native column-radiation engine.
+ *
+ * Drop-in boundary for the `update_fluxes!` hot path of CliMA/RRTMGP.jl (reference v1.0.0;
+ * citations are file:line in the reference tree).  The reference reaches its device code
+ * through Julia multiple dispatch, not a plugin ABI; the seam this library replaces is the
+ * set of methods `ext/RRTMGPCUDAExt.jl:33-45` specialises on the CUDA device
+ * (`rte_lw_2stream_solve!`, `rte_sw_2stream_solve!`, `rte_lw_noscat_solve!`,
+ * `compute_col_gas!`) plus the Layer-2 orchestration around them
+ * (`src/api/update_fluxes.jl:223-281`).  A Julia host `ccall`s these entry points with the
+ * `CuPtr`s of the arrays its `RRTMGPSolver` already owns; in this
+ * repository the same ABI is driven through ctypes + torch device tensors.
+ *
+ * Conventions
+ *   - every function returns an `rrtmgp_b200_status` (0 = ok); nothing throws, nothing
+ *     allocates after `create`/`load_luts`, nothing synchronises the device (contract of
+ *     src/api/update_fluxes.jl:215-218);
+ *   - all array pointers are DEVICE pointers owned by the caller, element type `float` or
+ *     `double` per `config.dtype`;
+ *   - layouts are the reference's: Julia `(vertical, ncol)` column-major == C `[ncol][vertical]`
+ *     (SURVEY.md Appendix B); level/layer 1 is the surface (src/rte/longwave_2stream.jl:262-267);
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ */
+#ifndef RRTMGP_B200_H
+#define RRTMGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRTMGP_B200_ABI_VERSION 1
+
+typedef enum {
+    RRTMGP_B200_OK = 0,
+    RRTMGP_B200_ERR_INVALID_ARG = 1,   /* bad config / null pointer / unsupported combination */
+    RRTMGP_B200_ERR_BAD_LUT_PACK = 2,  /* magic/version/size mismatch or missing table */
+    RRTMGP_B200_ERR_NOT_READY = 3,     /* update called before load_luts / bind */
+    RRTMGP_B200_ERR_CUDA = 4,          /* a CUDA runtime call failed (see rrtmgp_b200_last_cuda_error) */
+    RRTMGP_B200_ERR_UNSUPPORTED = 5    /* e.g. nlay too large for the kernel's register tiling */
+} rrtmgp_b200_status;
+
+/* radiation_methods.jl:19,30,49,67 (GrayRadiation has no g-point axis and stays on the host) */
+enum { RRTMGP_B200_CLEAR_SKY = 0, RRTMGP_B200_ALL_SKY = 1, RRTMGP_B200_ALL_SKY_WITH_CLEAR = 2 };
+/* optical_props.jl:13,48 */
+enum { RRTMGP_B200_TWO_STREAM = 0, RRTMGP_B200_ONE_SCALAR = 1 };
+/* VolumeMixingRatios.jl:34-43 (VmrGM) and :75-78 (Vmr) */
+enum { RRTMGP_B200_VMR_GM = 0, RRTMGP_B200_VMR_FULL = 1 };
+
+/* Mirrors what `RRTMGPSolver(grid_params, radiation_method, params, ...; op_lw, n_gauss_angles,
+ * spectral_fluxes, deep_atmosphere_inverse_scaling)` fixes at construction
+ * (src/api/solver.jl:136-331, src/api/grid_params.jl:38-54, src/Parameters.jl:6-14). */
+typedef struct {
+    int32_t abi_version;        /* RRTMGP_B200_ABI_VERSION */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t dtype;              /* 0 = Float32, 1 = Float64 */
+    int32_t ncol;
+    int32_t nlay;               /* layers incl. the isothermal boundary layer, if any */
+    int32_t ngas;               /* length of the gas axis of `vmr` */
+    int32_t vmr_kind;           /* RRTMGP_B200_VMR_* */
+    int32_t method;             /* RRTMGP_B200_CLEAR_SKY / ALL_SKY / ALL_SKY_WITH_CLEAR */
+    int32_t aerosol_radiation;  /* 0/1 */
+    int32_t op_lw;              /* TWO_STREAM or ONE_SCALAR (no-scattering LW) */
+    int32_t n_gauss_angles;     /* 1..4, ONE_SCALAR only (solver.jl:159-171) */
+    int32_t ice_rgh;            /* 1..3 (AtmosphericStates.jl:236-248) */
+    int32_t spectral_fluxes;    /* 0/1: also fill per-band fluxes (Fluxes.jl:170-215) */
+    int32_t isothermal_boundary_layer; /* 0/1: top layer is filled by prepare (grid_adaptation.jl:135-150) */
+    int64_t col_offset;         /* global index of column 0 of this handle (column shards; keys McICA) */
+    double grav, molmass_dryair, molmass_water, avogad; /* Parameters.jl:6-14 */
+} rrtmgp_b200_config_t;
+
+/* Device pointers of the arrays the reference's solver owns (src/api/solver.jl:216-272).
+ * Optional pointers may be NULL.  nlev = nlay + 1. */
+typedef struct {
+    /* --- AtmosphericState (AtmosphericStates.jl:70-81), mutated in place by prepare --- */
+    void* layerdata;      /* [ncol][nlay][4] (col_dry, p_lay, t_lay, rel_hum) */
+    void* p_lev;          /* [ncol][nlev] */
+    void* t_lev;          /* [ncol][nlev] */
+    void* t_sfc;          /* [ncol] */
+    void* vmr_h2o;        /* [ncol][nlay]            (VMR_GM) */
+    void* vmr_o3;         /* [ncol][nlay]            (VMR_GM) */
+    void* vmr;            /* VMR_GM: [ngas]; VMR_FULL: [ncol][nlay][ngas] */
+    void* lat;            /* [ncol] degrees or NULL (gas_optics.jl:29-33) */
+    /* CloudState (AtmosphericStates.jl:236-248); all NULL when there is no cloud state */
+    void* cld_r_eff_liq;  /* [ncol][nlay] */
+    void* cld_r_eff_ice;
+    void* cld_path_liq;
+    void* cld_path_ice;
+    void* cld_frac;
+    void* cld_cover_lw;   /* [ncol] out, optional */
+    void* cld_cover_sw;   /* [ncol] out, optional */
+    /* AerosolState (AtmosphericStates.jl:292-298); NULL when there is no aerosol state */
+    void* aero_mass;      /* [ncol][nlay][15] */
+    void* aero_size;      /* [ncol][nlay][15] */
+    void* aod_sw_ext;     /* [ncol] out, optional */
+    void* aod_sw_sca;     /* [ncol] out, optional */
+    /* --- boundary conditions (BCs.jl:17-23,40-47) --- */
+    void* sfc_emis;       /* [ncol][n_bnd_lw] */
+    void* inc_flux_lw;    /* [n_gpt_lw][ncol] or NULL */
+    void* cos_zenith;     /* [ncol] */
+    void* toa_flux;       /* [ncol] */
+    void* sfc_alb_direct; /* [ncol][n_bnd_sw] */
+    void* sfc_alb_diffuse;/* [ncol][n_bnd_sw] */
+    void* metric_scaling; /* [ncol][nlev] deep_atmosphere_inverse_scaling or NULL (Fluxes.jl:295-304) */
+    /* --- outputs: the (nlev, ncol) presentation arrays the getters expose (Fluxes.jl:355-374) --- */
+    void* lw_flux_up;  void* lw_flux_dn;  void* lw_flux_net;                      /* [ncol][nlev] */
+    void* sw_flux_up;  void* sw_flux_dn;  void* sw_flux_net;  void* sw_flux_dn_dir;
+    void* net_flux;                                                               /* lw_net + sw_net */
+    /* clear-sky snapshots, ALL_SKY_WITH_CLEAR only (update_fluxes.jl:39-65,101-128) */
+    void* clear_lw_flux_up; void* clear_lw_flux_dn; void* clear_lw_flux_net;
+    void* clear_sw_flux_up; void* clear_sw_flux_dn; void* clear_sw_flux_net; void* clear_sw_flux_dn_dir;
+    void* clear_net_flux;
+    /* per-band fluxes, spectral_fluxes only: Julia (nlev, ncol, n_bnd) == C [n_bnd][ncol][nlev] */
+    void* lw_band_flux_up; void* lw_band_flux_dn; void* lw_band_flux_net;
+    void* sw_band_flux_up; void* sw_band_flux_dn; void* sw_band_flux_net;
+} rrtmgp_b200_buffers_t;
+
+/* Table dimensions and the scalars a host needs before allocating (LookUpTables.jl:130-143,185-201). */
+typedef struct {
+    int32_t n_gpt_lw, n_bnd_lw, n_gpt_sw, n_bnd_sw, ngas, iband_550nm;
+    double p_ref_min, t_ref_min, t_ref_max, solar_src_tot;
+} rrtmgp_b200_lut_info_t;
+
+typedef struct rrtmgp_b200_handle rrtmgp_b200_handle_t;
+
+/* RRTMGPSolver(...) construction: validates the option combination (solver.jl:159-193) and
+ * sizes every internal workspace.  One handle per GPU / per column shard. */
+int rrtmgp_b200_create(const rrtmgp_b200_config_t* cfg, rrtmgp_b200_handle_t** out);
+void rrtmgp_b200_destroy(rrtmgp_b200_handle_t* h);
+
+/* lookup_tables(grid_params, method) (ext/RRTMGPNCDatasetsExt.jl:93-133): `pack` is a HOST
+ * pointer to a flat LUT pack (rrtmgp.jl_b200/lutpack.py); tables are converted to `dtype`,
+ * re-laid out g-point-fastest and uploaded. */
+int rrtmgp_b200_load_luts(rrtmgp_b200_handle_t* h, const void* pack, size_t nbytes);
+int rrtmgp_b200_lut_info(const rrtmgp_b200_handle_t* h, rrtmgp_b200_lut_info_t* out);
+
+/* Registers the caller-owned device arrays (the struct is copied). */
+int rrtmgp_b200_bind(rrtmgp_b200_handle_t* h, const rrtmgp_b200_buffers_t* bufs);
+
+/* prepare_atmosphere!(s) (update_fluxes.jl:252-281): boundary layer fill, clip!, col_dry; in place. */
+int rrtmgp_b200_prepare_atmosphere(rrtmgp_b200_handle_t* h, void* stream);
+/* update_lw_fluxes!(s) / update_sw_fluxes!(s) / update_net_fluxes!(s) (update_fluxes.jl:12-16,74-78,165-194).
+ * `have_seed == 0` mirrors `seedval = nothing`: an internal per-call counter keys the McICA draws. */
+int rrtmgp_b200_update_lw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream);
+int rrtmgp_b200_update_sw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream);
+int rrtmgp_b200_update_net_fluxes(rrtmgp_b200_handle_t* h, void* stream);
+/* update_fluxes!(s, seedval) (update_fluxes.jl:223-233) = prepare + lw + sw + net, async on `stream`. */
+int rrtmgp_b200_update_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream);
+
+/* compute_relative_humidity!(...) (src/optics/column_amounts.jl:52-76, gas_optics.jl:58-80): a host
+ * duty in the reference (grid_adaptation.jl:267-270); writes layerdata[..][3]. */
+int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream);
+
+/* Diagnostics: kernels launched by the last update_* call; last CUDA error string. */
+int rrtmgp_b200_last_launch_count(const rrtmgp_b200_handle_t* h);
+const char* rrtmgp_b200_last_cuda_error(const rrtmgp_b200_handle_t* h);
+const char* rrtmgp_b200_strerror(int status);
+int rrtmgp_b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTMGP_B200_H */

@@ -1,0 +1,464 @@
+// C ABI (include/rrtmgp_b200.h): handle lifetime, argument validation, and the Layer-2
+// orchestration of src/api/update_fluxes.jl on a CUDA stream.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/rrtmgp_b200.h"
+#include "lut.cuh"
+#include "solver.cuh"
+
+using namespace rb;
+
+struct rrtmgp_b200_handle {
+    rrtmgp_b200_config_t cfg;
+    rrtmgp_b200_buffers_t buf;
+    bool bound = false;
+    LutStore luts;
+    int max_smem_optin = 0;
+    int sm_count = 0;
+    unsigned long long call_counter = 0;
+    int last_launches = 0;
+    char cuda_err[256] = {0};
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// small elementwise kernels of prepare_atmosphere! and update_net_fluxes!
+// ------------------------------------------------------------------------------------
+// add_isothermal_boundary_layer! (grid_adaptation.jl:135-150,176-214); one thread per column
+template <typename FT>
+__global__ void boundary_layer_kernel(rrtmgp_b200_buffers_t B, int ncol, int nlay, int ngas, int vmr_kind, FT p_min) {
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    const int nlev = nlay + 1, top = nlay - 1;
+    FT* ld = (FT*)B.layerdata + (size_t)col * nlay * 4;
+    FT* p_lev = (FT*)B.p_lev + (size_t)col * nlev;
+    FT* t_lev = (FT*)B.t_lev + (size_t)col * nlev;
+    ld[4 * top + 1] = (p_lev[nlev - 2] + p_min) / FT(2);
+    p_lev[nlev - 1] = p_min;
+    ld[4 * top + 2] = t_lev[nlev - 2];
+    t_lev[nlev - 1] = t_lev[nlev - 2];
+    ld[4 * top + 3] = ld[4 * (top - 1) + 3];
+    size_t k = (size_t)col * nlay + top;
+    if (vmr_kind == RRTMGP_B200_VMR_GM) {
+        ((FT*)B.vmr_h2o)[k] = ((FT*)B.vmr_h2o)[k - 1];
+        ((FT*)B.vmr_o3)[k] = ((FT*)B.vmr_o3)[k - 1];
+    } else {
+        FT* v = (FT*)B.vmr;
+        for (int g = 0; g < ngas; ++g) v[k * ngas + g] = v[(k - 1) * ngas + g];
+    }
+    if (B.cld_frac) {
+        FT* arrs[5] = {(FT*)B.cld_r_eff_liq, (FT*)B.cld_r_eff_ice, (FT*)B.cld_path_liq, (FT*)B.cld_path_ice, (FT*)B.cld_frac};
+        for (int a = 0; a < 5; ++a) arrs[a][k] = arrs[a][k - 1];
+    }
+    if (B.aero_mass) {
+        FT* am = (FT*)B.aero_mass; FT* as = (FT*)B.aero_size;
+        for (int i = 0; i < 15; ++i) { am[k * 15 + i] = am[(k - 1) * 15 + i]; as[k * 15 + i] = as[(k - 1) * 15 + i]; }
+    }
+}
+
+// clip! (grid_adaptation.jl:232-258) + compute_col_gas_kernel! (gas_optics.jl:16-41); thread per (col, level)
+template <typename FT>
+__global__ void prepare_kernel(rrtmgp_b200_buffers_t B, int ncol, int nlay, int ngas, int vmr_kind, int idx_h2o, FT p_min,
+                               FT t_min, FT t_max, FT grav, FT m_dry, FT m_h2o, FT avogad) {
+    const int nlev = nlay + 1;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)ncol * nlev) return;
+    const int col = (int)(idx / nlev), lev = (int)(idx - (long long)col * nlev);
+    FT* p_lev = (FT*)B.p_lev + (size_t)col * nlev;
+    FT* t_lev = (FT*)B.t_lev + (size_t)col * nlev;
+    const FT p_here = rmax(p_lev[lev], p_min);
+    FT p_above = FT(0);
+    if (lev < nlay) p_above = rmax(p_lev[lev + 1], p_min);
+    p_lev[lev] = p_here;
+    t_lev[lev] = rmin(rmax(t_lev[lev], t_min), t_max);
+    if (lev < nlay) {
+        size_t k = (size_t)col * nlay + lev;
+        FT* ld = (FT*)B.layerdata + k * 4;
+        FT* h2o = vmr_kind == RRTMGP_B200_VMR_GM ? (FT*)B.vmr_h2o + k : (FT*)B.vmr + k * ngas + (idx_h2o - 1);
+        FT v = rmax(*h2o, FT(0));
+        *h2o = v;
+        ld[1] = rmax(ld[1], p_min);
+        ld[2] = rmin(rmax(ld[2], t_min), t_max);
+        const FT helmert2 = FT(0.02586), m2_to_cm2 = FT(100 * 100);
+        FT g0 = grav;
+        if (B.lat) g0 = grav - helmert2 * rcos(FT(2) * Num<FT>::pi() * ((const FT*)B.lat)[col] / FT(180));
+        FT dp = p_here - p_above;
+        FT m_air = m_dry + m_h2o * v;
+        ld[0] = dp * avogad / (m2_to_cm2 * m_air * g0);
+    }
+}
+
+// compute_relative_humidity_kernel! (gas_optics.jl:58-80)
+template <typename FT>
+__global__ void rel_hum_kernel(rrtmgp_b200_buffers_t B, int ncol, int nlay, int ngas, int vmr_kind, int idx_h2o, FT mwd) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (long long)ncol * nlay) return;
+    FT* ld = (FT*)B.layerdata + (size_t)k * 4;
+    FT vmr = vmr_kind == RRTMGP_B200_VMR_GM ? ((const FT*)B.vmr_h2o)[k] : ((const FT*)B.vmr)[(size_t)k * ngas + (idx_h2o - 1)];
+    FT mmr = vmr * mwd;
+    FT q = mmr / (FT(1) + mmr);
+    FT q_tmp = rmax(FT(1e-7), q);
+    FT t = ld[2];
+    FT es = rexp((FT(17.67) * (t - FT(273.16))) / (t - FT(29.65)));
+    ld[3] = rmax(FT(0.01) * (FT(0.263) * ld[1] * q_tmp) / es, FT(0));
+}
+
+// transpose_sum_into! without the transpose (Fluxes.jl:423-435)
+template <typename FT> __global__ void add_kernel(const FT* a, const FT* b, FT* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+
+int fail_cuda(rrtmgp_b200_handle* h, cudaError_t e) {
+    std::snprintf(h->cuda_err, sizeof(h->cuda_err), "%s", cudaGetErrorString(e));
+    return RRTMGP_B200_ERR_CUDA;
+}
+
+template <typename FT> const Luts<FT>& luts_of(const rrtmgp_b200_handle* h);
+template <> const Luts<float>& luts_of<float>(const rrtmgp_b200_handle* h) { return h->luts.f32; }
+template <> const Luts<double>& luts_of<double>(const rrtmgp_b200_handle* h) { return h->luts.f64; }
+
+template <typename FT>
+void fill_io(const rrtmgp_b200_handle* h, ColumnIO<FT>& io) {
+    const rrtmgp_b200_buffers_t& B = h->buf;
+    std::memset(&io, 0, sizeof(io));
+    io.layerdata = (const FT*)B.layerdata; io.p_lev = (const FT*)B.p_lev; io.t_lev = (const FT*)B.t_lev;
+    io.t_sfc = (const FT*)B.t_sfc; io.vmr_h2o = (const FT*)B.vmr_h2o; io.vmr_o3 = (const FT*)B.vmr_o3;
+    io.vmr = (const FT*)B.vmr;
+    io.cld_r_eff_liq = (const FT*)B.cld_r_eff_liq; io.cld_r_eff_ice = (const FT*)B.cld_r_eff_ice;
+    io.cld_path_liq = (const FT*)B.cld_path_liq; io.cld_path_ice = (const FT*)B.cld_path_ice;
+    io.cld_frac = (const FT*)B.cld_frac;
+    io.aero_mass = (const FT*)B.aero_mass; io.aero_size = (const FT*)B.aero_size;
+    io.sfc_emis = (const FT*)B.sfc_emis; io.inc_flux_lw = (const FT*)B.inc_flux_lw;
+    io.cos_zenith = (const FT*)B.cos_zenith; io.toa_flux = (const FT*)B.toa_flux;
+    io.sfc_alb_direct = (const FT*)B.sfc_alb_direct; io.sfc_alb_diffuse = (const FT*)B.sfc_alb_diffuse;
+    io.metric_scaling = (const FT*)B.metric_scaling;
+}
+
+// src/optics/AngularDiscretizations.jl:34-63
+template <typename FT> void gauss_angles(int n, FT* Ds, FT* wts) {
+    static const double mu[4][4] = {{0.6096748751, 0, 0, 0},
+                                    {0.2509907356, 0.7908473988, 0, 0},
+                                    {0.1024922169, 0.4417960320, 0.8633751621, 0},
+                                    {0.0454586727, 0.2322334416, 0.5740198775, 0.9030775973}};
+    static const double w[4][4] = {{1, 0, 0, 0},
+                                   {0.2300253764, 0.7699746236, 0, 0},
+                                   {0.0437820218, 0.3875796738, 0.5686383044, 0},
+                                   {0.0092068785, 0.1285704278, 0.4323381850, 0.4298845087}};
+    for (int i = 0; i < 4; ++i) { Ds[i] = FT(0); wts[i] = FT(0); }
+    for (int i = 0; i < n; ++i) { Ds[i] = (FT)(1.0 / mu[n - 1][i]); wts[i] = (FT)w[n - 1][i]; }
+}
+
+template <typename FT>
+void base_params(const rrtmgp_b200_handle* h, SolveParams<FT>& P, bool sw, bool clouds, unsigned long long seed) {
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const Luts<FT>& L = luts_of<FT>(h);
+    std::memset(&P, 0, sizeof(P));
+    fill_io(h, P.io);
+    P.lut = sw ? L.sw : L.lw;
+    P.cld = sw ? L.cld_sw : L.cld_lw;
+    P.aero = sw ? L.aero_sw : L.aero_lw;
+    P.ncol = c.ncol; P.nlay = c.nlay; P.ngas = c.ngas; P.vmr_kind = c.vmr_kind; P.ice_rgh = c.ice_rgh;
+    P.use_cloud = clouds && h->buf.cld_frac != nullptr;
+    P.use_aero = c.aerosol_radiation && h->buf.aero_mass != nullptr;
+    P.n_mu = c.op_lw == RRTMGP_B200_ONE_SCALAR ? c.n_gauss_angles : 1;
+    P.col_offset = c.col_offset;
+    P.seed = seed;
+    gauss_angles<FT>(P.n_mu, P.Ds, P.wts);
+}
+
+unsigned long long effective_seed(rrtmgp_b200_handle* h, uint64_t seed, int have_seed) {
+    // `seedval = nothing` (update_fluxes.jl:150-156): the RNG stream simply continues; here a
+    // per-call counter keys the draws so successive unseeded calls sample differently.
+    return have_seed ? (unsigned long long)seed : 0xA5A5F00DULL + (++h->call_counter) * 0x632BE59BD9B4E019ULL;
+}
+
+template <typename FT>
+int solve_lw_t(rrtmgp_b200_handle* h, unsigned long long seed, cudaStream_t s) {
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const rrtmgp_b200_buffers_t& B = h->buf;
+    const int mode = c.op_lw == RRTMGP_B200_ONE_SCALAR ? MODE_LW_NOSCAT : MODE_LW_2STREAM;
+    const size_t nb = (size_t)h->luts.n_bnd_lw * c.ncol * (c.nlay + 1) * sizeof(FT);
+    SolveParams<FT> P;
+    if (c.method == RRTMGP_B200_ALL_SKY_WITH_CLEAR) {   // update_fluxes.jl:39-65
+        base_params<FT>(h, P, false, false, seed);
+        P.io.out_up = (FT*)B.clear_lw_flux_up; P.io.out_dn = (FT*)B.clear_lw_flux_dn; P.io.out_net = (FT*)B.clear_lw_flux_net;
+        int e = launch_solve<FT>(mode, P, h->max_smem_optin, s);
+        if (e) return fail_cuda(h, (cudaError_t)e);
+        ++h->last_launches;
+    }
+    base_params<FT>(h, P, false, c.method >= RRTMGP_B200_ALL_SKY, seed);
+    P.io.out_up = (FT*)B.lw_flux_up; P.io.out_dn = (FT*)B.lw_flux_dn; P.io.out_net = (FT*)B.lw_flux_net;
+    P.io.cld_cover = (FT*)B.cld_cover_lw;
+    if (c.spectral_fluxes && mode == MODE_LW_2STREAM) {
+        P.io.band_up = (FT*)B.lw_band_flux_up; P.io.band_dn = (FT*)B.lw_band_flux_dn; P.io.band_net = (FT*)B.lw_band_flux_net;
+        cudaError_t e = cudaMemsetAsync(B.lw_band_flux_up, 0, nb, s);   // set_band_flux_to_zero! (Fluxes.jl:191-197)
+        if (e == cudaSuccess) e = cudaMemsetAsync(B.lw_band_flux_dn, 0, nb, s);
+        if (e != cudaSuccess) return fail_cuda(h, e);
+    }
+    int e = launch_solve<FT>(mode, P, h->max_smem_optin, s);
+    if (e) return fail_cuda(h, (cudaError_t)e);
+    ++h->last_launches;
+    return RRTMGP_B200_OK;
+}
+
+template <typename FT>
+int solve_sw_t(rrtmgp_b200_handle* h, unsigned long long seed, bool fuse_net, cudaStream_t s) {
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const rrtmgp_b200_buffers_t& B = h->buf;
+    const size_t nb = (size_t)h->luts.n_bnd_sw * c.ncol * (c.nlay + 1) * sizeof(FT);
+    SolveParams<FT> P;
+    if (c.method == RRTMGP_B200_ALL_SKY_WITH_CLEAR) {   // update_fluxes.jl:101-128
+        base_params<FT>(h, P, true, false, seed);
+        P.io.out_up = (FT*)B.clear_sw_flux_up; P.io.out_dn = (FT*)B.clear_sw_flux_dn; P.io.out_net = (FT*)B.clear_sw_flux_net;
+        P.io.out_dir = (FT*)B.clear_sw_flux_dn_dir;
+        P.io.aod_ext = (FT*)B.aod_sw_ext; P.io.aod_sca = (FT*)B.aod_sw_sca;
+        if (fuse_net && B.clear_net_flux) { P.io.add_net = (const FT*)B.clear_lw_flux_net; P.io.out_total_net = (FT*)B.clear_net_flux; }
+        int e = launch_solve<FT>(MODE_SW_2STREAM, P, h->max_smem_optin, s);
+        if (e) return fail_cuda(h, (cudaError_t)e);
+        ++h->last_launches;
+    }
+    base_params<FT>(h, P, true, c.method >= RRTMGP_B200_ALL_SKY, seed);
+    P.io.out_up = (FT*)B.sw_flux_up; P.io.out_dn = (FT*)B.sw_flux_dn; P.io.out_net = (FT*)B.sw_flux_net;
+    P.io.out_dir = (FT*)B.sw_flux_dn_dir;
+    P.io.cld_cover = (FT*)B.cld_cover_sw;
+    P.io.aod_ext = (FT*)B.aod_sw_ext; P.io.aod_sca = (FT*)B.aod_sw_sca;
+    if (fuse_net && B.net_flux) { P.io.add_net = (const FT*)B.lw_flux_net; P.io.out_total_net = (FT*)B.net_flux; }
+    if (c.spectral_fluxes) {
+        P.io.band_up = (FT*)B.sw_band_flux_up; P.io.band_dn = (FT*)B.sw_band_flux_dn; P.io.band_net = (FT*)B.sw_band_flux_net;
+        cudaError_t e = cudaMemsetAsync(B.sw_band_flux_up, 0, nb, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(B.sw_band_flux_dn, 0, nb, s);
+        if (e != cudaSuccess) return fail_cuda(h, e);
+    }
+    int e = launch_solve<FT>(MODE_SW_2STREAM, P, h->max_smem_optin, s);
+    if (e) return fail_cuda(h, (cudaError_t)e);
+    ++h->last_launches;
+    return RRTMGP_B200_OK;
+}
+
+template <typename FT> int prepare_t(rrtmgp_b200_handle* h, cudaStream_t s) {
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const LutStore& L = h->luts;
+    const int idx_h2o = luts_of<FT>(h).lw.idx_h2o;
+    if (c.isothermal_boundary_layer) {
+        boundary_layer_kernel<FT><<<(c.ncol + 127) / 128, 128, 0, s>>>(h->buf, c.ncol, c.nlay, c.ngas, c.vmr_kind, (FT)L.p_ref_min);
+        ++h->last_launches;
+    }
+    const long long n = (long long)c.ncol * (c.nlay + 1);
+    prepare_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->buf, c.ncol, c.nlay, c.ngas, c.vmr_kind, idx_h2o,
+                                                                  luts_of<FT>(h).lw.p_ref_min, luts_of<FT>(h).lw.t_ref_min,
+                                                                  luts_of<FT>(h).lw.t_ref_max, (FT)c.grav, (FT)c.molmass_dryair,
+                                                                  (FT)c.molmass_water, (FT)c.avogad);
+    ++h->last_launches;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RRTMGP_B200_OK : fail_cuda(h, e);
+}
+
+template <typename FT> int net_t(rrtmgp_b200_handle* h, cudaStream_t s) {
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const rrtmgp_b200_buffers_t& B = h->buf;
+    const long long n = (long long)c.ncol * (c.nlay + 1);
+    if (B.net_flux) {
+        add_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const FT*)B.lw_flux_net, (const FT*)B.sw_flux_net, (FT*)B.net_flux, n);
+        ++h->last_launches;
+    }
+    if (c.method == RRTMGP_B200_ALL_SKY_WITH_CLEAR && B.clear_net_flux) {
+        add_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const FT*)B.clear_lw_flux_net, (const FT*)B.clear_sw_flux_net,
+                                                                  (FT*)B.clear_net_flux, n);
+        ++h->last_launches;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RRTMGP_B200_OK : fail_cuda(h, e);
+}
+
+int ready(const rrtmgp_b200_handle* h) {
+    if (!h) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (!h->luts.loaded || !h->bound) return RRTMGP_B200_ERR_NOT_READY;
+    return RRTMGP_B200_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int rrtmgp_b200_abi_version(void) { return RRTMGP_B200_ABI_VERSION; }
+
+const char* rrtmgp_b200_strerror(int status) {
+    switch (status) {
+        case RRTMGP_B200_OK: return "ok";
+        case RRTMGP_B200_ERR_INVALID_ARG: return "invalid argument or unsupported option combination";
+        case RRTMGP_B200_ERR_BAD_LUT_PACK: return "malformed or incomplete LUT pack";
+        case RRTMGP_B200_ERR_NOT_READY: return "lookup tables not loaded or buffers not bound";
+        case RRTMGP_B200_ERR_CUDA: return "CUDA runtime error";
+        case RRTMGP_B200_ERR_UNSUPPORTED: return "configuration not supported by this build";
+    }
+    return "unknown status";
+}
+
+int rrtmgp_b200_create(const rrtmgp_b200_config_t* cfg, rrtmgp_b200_handle_t** out) {
+    if (!cfg || !out) return RRTMGP_B200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->abi_version != RRTMGP_B200_ABI_VERSION) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->dtype != 0 && cfg->dtype != 1) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->ncol <= 0 || cfg->nlay < 2 || cfg->ngas <= 0) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->method < 0 || cfg->method > 2) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->vmr_kind != RRTMGP_B200_VMR_GM && cfg->vmr_kind != RRTMGP_B200_VMR_FULL) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->op_lw != RRTMGP_B200_TWO_STREAM && cfg->op_lw != RRTMGP_B200_ONE_SCALAR) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->n_gauss_angles < 1 || cfg->n_gauss_angles > 4) return RRTMGP_B200_ERR_INVALID_ARG;   // AngularDiscretizations.jl:40
+    // solver.jl:159-171: n_gauss_angles only applies to the non-scattering longwave solver
+    if (cfg->n_gauss_angles != 1 && cfg->op_lw != RRTMGP_B200_ONE_SCALAR) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->ice_rgh < 1 || cfg->ice_rgh > 3) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (cfg->nlay + 1 > 32 * kMaxLevPerLane) return RRTMGP_B200_ERR_UNSUPPORTED;
+    if (!(cfg->grav > 0) || !(cfg->molmass_dryair > 0) || !(cfg->avogad > 0)) return RRTMGP_B200_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return RRTMGP_B200_ERR_CUDA;
+    rrtmgp_b200_handle* h = new (std::nothrow) rrtmgp_b200_handle();
+    if (!h) return RRTMGP_B200_ERR_INVALID_ARG;
+    h->cfg = *cfg;
+    std::memset(&h->buf, 0, sizeof(h->buf));
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+    *out = h;
+    return RRTMGP_B200_OK;
+}
+
+void rrtmgp_b200_destroy(rrtmgp_b200_handle_t* h) {
+    if (!h) return;
+    DeviceGuard g(h->cfg.device);
+    free_lut_store(h->luts);
+    delete h;
+}
+
+int rrtmgp_b200_load_luts(rrtmgp_b200_handle_t* h, const void* pack, size_t nbytes) {
+    if (!h || !pack) return RRTMGP_B200_ERR_INVALID_ARG;
+    DeviceGuard g(h->cfg.device);
+    const char* err = nullptr;
+    int st = load_lut_pack(h->luts, pack, nbytes, h->cfg.dtype == 1, &err);
+    if (st == RRTMGP_B200_ERR_CUDA && err) std::snprintf(h->cuda_err, sizeof(h->cuda_err), "%s", err);
+    if (st != RRTMGP_B200_OK) return st;
+    if (h->luts.ngas > h->cfg.ngas) return RRTMGP_B200_ERR_INVALID_ARG;   // vmr gas axis shorter than the tables'
+    if (h->luts.f32.lw.n_eta > 16 || h->luts.f64.lw.n_eta > 16) return RRTMGP_B200_ERR_UNSUPPORTED;
+    return RRTMGP_B200_OK;
+}
+
+int rrtmgp_b200_lut_info(const rrtmgp_b200_handle_t* h, rrtmgp_b200_lut_info_t* o) {
+    if (!h || !o) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (!h->luts.loaded) return RRTMGP_B200_ERR_NOT_READY;
+    const LutStore& L = h->luts;
+    o->n_gpt_lw = L.n_gpt_lw; o->n_bnd_lw = L.n_bnd_lw; o->n_gpt_sw = L.n_gpt_sw; o->n_bnd_sw = L.n_bnd_sw;
+    o->ngas = L.ngas; o->iband_550nm = L.iband_550nm;
+    o->p_ref_min = L.p_ref_min; o->t_ref_min = L.t_ref_min; o->t_ref_max = L.t_ref_max; o->solar_src_tot = L.solar_src_tot;
+    return RRTMGP_B200_OK;
+}
+
+int rrtmgp_b200_bind(rrtmgp_b200_handle_t* h, const rrtmgp_b200_buffers_t* b) {
+    if (!h || !b) return RRTMGP_B200_ERR_INVALID_ARG;
+    const rrtmgp_b200_config_t& c = h->cfg;
+    if (!b->layerdata || !b->p_lev || !b->t_lev || !b->t_sfc || !b->vmr) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (c.vmr_kind == RRTMGP_B200_VMR_GM && (!b->vmr_h2o || !b->vmr_o3)) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (!b->sfc_emis || !b->cos_zenith || !b->toa_flux || !b->sfc_alb_direct || !b->sfc_alb_diffuse) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (!b->lw_flux_up || !b->lw_flux_dn || !b->lw_flux_net) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (!b->sw_flux_up || !b->sw_flux_dn || !b->sw_flux_net || !b->sw_flux_dn_dir) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (c.method >= RRTMGP_B200_ALL_SKY &&
+        (!b->cld_frac || !b->cld_r_eff_liq || !b->cld_r_eff_ice || !b->cld_path_liq || !b->cld_path_ice))
+        return RRTMGP_B200_ERR_INVALID_ARG;
+    if (c.aerosol_radiation && (!b->aero_mass || !b->aero_size)) return RRTMGP_B200_ERR_INVALID_ARG;
+    if ((b->aod_sw_ext == nullptr) != (b->aod_sw_sca == nullptr)) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (c.method == RRTMGP_B200_ALL_SKY_WITH_CLEAR &&
+        (!b->clear_lw_flux_up || !b->clear_lw_flux_dn || !b->clear_lw_flux_net || !b->clear_sw_flux_up ||
+         !b->clear_sw_flux_dn || !b->clear_sw_flux_net || !b->clear_sw_flux_dn_dir))
+        return RRTMGP_B200_ERR_INVALID_ARG;
+    if (c.spectral_fluxes && (!b->lw_band_flux_up || !b->lw_band_flux_dn || !b->lw_band_flux_net || !b->sw_band_flux_up ||
+                              !b->sw_band_flux_dn || !b->sw_band_flux_net))
+        return RRTMGP_B200_ERR_INVALID_ARG;
+    h->buf = *b;
+    h->bound = true;
+    return RRTMGP_B200_OK;
+}
+
+#define RB_DISPATCH(h, call) ((h)->cfg.dtype == 1 ? call<double> : call<float>)
+
+int rrtmgp_b200_prepare_atmosphere(rrtmgp_b200_handle_t* h, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 0;
+    return h->cfg.dtype == 1 ? prepare_t<double>(h, (cudaStream_t)stream) : prepare_t<float>(h, (cudaStream_t)stream);
+}
+
+int rrtmgp_b200_update_lw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 0;
+    unsigned long long s = effective_seed(h, seed, have_seed);
+    return h->cfg.dtype == 1 ? solve_lw_t<double>(h, s, (cudaStream_t)stream) : solve_lw_t<float>(h, s, (cudaStream_t)stream);
+}
+
+int rrtmgp_b200_update_sw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 0;
+    unsigned long long s = effective_seed(h, seed, have_seed);
+    return h->cfg.dtype == 1 ? solve_sw_t<double>(h, s, false, (cudaStream_t)stream)
+                             : solve_sw_t<float>(h, s, false, (cudaStream_t)stream);
+}
+
+int rrtmgp_b200_update_net_fluxes(rrtmgp_b200_handle_t* h, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 0;
+    return h->cfg.dtype == 1 ? net_t<double>(h, (cudaStream_t)stream) : net_t<float>(h, (cudaStream_t)stream);
+}
+
+int rrtmgp_b200_update_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long sd = effective_seed(h, seed, have_seed);
+    const bool f64 = h->cfg.dtype == 1;
+    st = f64 ? prepare_t<double>(h, s) : prepare_t<float>(h, s);
+    if (st) return st;
+    st = f64 ? solve_lw_t<double>(h, sd, s) : solve_lw_t<float>(h, sd, s);
+    if (st) return st;
+    // net = lw_net + sw_net is folded into the shortwave epilogue (update_fluxes.jl:165-194)
+    return f64 ? solve_sw_t<double>(h, sd, true, s) : solve_sw_t<float>(h, sd, true, s);
+}
+
+int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 1;
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const long long n = (long long)c.ncol * c.nlay;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (c.dtype == 1)
+        rel_hum_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(h->buf, c.ncol, c.nlay, c.ngas, c.vmr_kind, h->luts.f64.lw.idx_h2o,
+                                                                       c.molmass_water / c.molmass_dryair);
+    else
+        rel_hum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(h->buf, c.ncol, c.nlay, c.ngas, c.vmr_kind, h->luts.f32.lw.idx_h2o,
+                                                                      (float)c.molmass_water / (float)c.molmass_dryair);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RRTMGP_B200_OK : fail_cuda(h, e);
+}
+
+int rrtmgp_b200_last_launch_count(const rrtmgp_b200_handle_t* h) { return h ? h->last_launches : 0; }
+const char* rrtmgp_b200_last_cuda_error(const rrtmgp_b200_handle_t* h) { return h ? h->cuda_err : ""; }
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// Scalar building blocks of the hot path, shared by every kernel.  Each function names the
+// reference routine it computes (file:line in CliMA/RRTMGP.jl v1.0.0).  IEEE division /
+// sqrt / full-precision exp, expm1, log are kept (no --use_fast_math): the reference's
+// numerics notes (docs/src/precision.md:36-72) depend on the exact guard constants below.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+namespace rb {
+
+// ---- precision traits: src/Numerics.jl:24,37,49,63 ----
+template <typename FT> struct Num;
+template <> struct Num<float> {
+    static __device__ __forceinline__ float eps() { return FLT_EPSILON; }
+    static __device__ __forceinline__ float k_min() { return 3.4526698300e-04f; }       // sqrt(eps)
+    static __device__ __forceinline__ float tau_thresh() { return 1.8581361171e-02f; }  // eps^(1/4)
+    static __device__ __forceinline__ float pi() { return 3.14159274101257324f; }
+};
+template <> struct Num<double> {
+    static __device__ __forceinline__ double eps() { return DBL_EPSILON; }
+    static __device__ __forceinline__ double k_min() { return 1.4901161193847656e-08; }
+    static __device__ __forceinline__ double tau_thresh() { return 1.220703125e-04; }
+    static __device__ __forceinline__ double pi() { return 3.141592653589793; }
+};
+
+__device__ __forceinline__ float rexp(float x) { return expf(x); }
+__device__ __forceinline__ double rexp(double x) { return exp(x); }
+__device__ __forceinline__ float rexpm1(float x) { return expm1f(x); }
+__device__ __forceinline__ double rexpm1(double x) { return expm1(x); }
+__device__ __forceinline__ float rlog(float x) { return logf(x); }
+__device__ __forceinline__ double rlog(double x) { return log(x); }
+__device__ __forceinline__ float rsqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ double rsqrt_(double x) { return sqrt(x); }
+__device__ __forceinline__ float rcos(float x) { return cosf(x); }
+__device__ __forceinline__ double rcos(double x) { return cos(x); }
+template <typename FT> __device__ __forceinline__ FT rmax(FT a, FT b) { return a > b ? a : b; }
+template <typename FT> __device__ __forceinline__ FT rmin(FT a, FT b) { return a < b ? a : b; }
+template <typename FT> __device__ __forceinline__ FT rabs(FT a) { return a < FT(0) ? -a : a; }
+
+// ---- optics_utils.jl:189-202 ----
+template <typename FT>
+__device__ __forceinline__ void increment_2stream(FT& t1, FT& s1, FT& g1, FT t2, FT s2, FT g2) {
+    FT tau = t1 + t2;
+    FT ssa = t1 * s1 + t2 * s2;
+    FT ssag = (t1 * s1 * g1 + t2 * s2 * g2) / rmax(Num<FT>::eps(), ssa);
+    ssa /= rmax(Num<FT>::eps(), tau);
+    t1 = tau; s1 = ssa; g1 = ssag;
+}
+// ---- optics_utils.jl:208-223 ----
+template <typename FT> __device__ __forceinline__ void delta_scale(FT& tau, FT& ssa, FT& g) {
+    FT ssa_one_minus_g2 = ssa * (FT(1) - g) * (FT(1) + g);
+    FT one_minus_wf = (FT(1) - ssa) + ssa_one_minus_g2;
+    FT tau_s = one_minus_wf * tau;
+    FT ssa_s = ssa_one_minus_g2 / rmax(Num<FT>::eps(), one_minus_wf);
+    FT g_s = g / rmax(Num<FT>::eps(), FT(1) + g);
+    tau = tau_s; ssa = ssa_s; g = g_s;
+}
+// ---- optics_utils.jl:7-14 (equispaced) ----
+template <typename FT> __device__ __forceinline__ int loc_lower_eq(FT xi, FT dx, int n, const FT* __restrict__ x) {
+    if (xi <= __ldg(x)) return 1;
+    if (xi >= __ldg(x + n - 1)) return n - 1;
+    int j = (int)((xi - __ldg(x)) / dx) + 1;
+    return j < n - 1 ? j : n - 1;
+}
+// ---- optics_utils.jl:34-44 ----
+template <typename FT>
+__device__ __forceinline__ FT interp1d_equispaced(FT xi, const FT* __restrict__ x, const FT* __restrict__ y, int n) {
+    if (xi < __ldg(x)) return __ldg(y);
+    if (xi > __ldg(x + n - 1)) return __ldg(y + n - 1);
+    FT dx = __ldg(x + 1) - __ldg(x);
+    int loc = loc_lower_eq(xi, dx, n, x);
+    FT factor = (xi - __ldg(x + loc - 1)) / dx;
+    return __ldg(y + loc - 1) * (FT(1) - factor) + __ldg(y + loc) * factor;
+}
+// ---- optics_utils.jl:51-62 + :21-27 (non-uniform x) ----
+template <typename FT>
+__device__ __forceinline__ void interp1d_loc_factor(FT xi, const FT* __restrict__ x, int n, int& loc, FT& factor) {
+    if (xi < __ldg(x)) { loc = 1; factor = FT(0); return; }
+    if (xi > __ldg(x + n - 1)) { loc = n - 1; factor = FT(1); return; }
+    loc = n - 1;
+    if (xi <= __ldg(x)) loc = 1;
+    else
+        for (int i = 1; i <= n; ++i)
+            if (xi < __ldg(x + i - 1)) { loc = i - 1; break; }
+    factor = (xi - __ldg(x + loc - 1)) / (__ldg(x + loc) - __ldg(x + loc - 1));
+}
+
+// ---- longwave_2stream.jl:149-222 ----
+template <typename FT>
+__device__ __forceinline__ void lw_2stream_coeffs(FT tau, FT ssa, FT g, FT lev_src_bot, FT lev_src_top, FT& Rdif,
+                                                  FT& Tdif, FT& src_up, FT& src_dn) {
+    const FT lw_diff_sec = FT(1.66);
+    FT g1 = lw_diff_sec * (FT(1) - FT(0.5) * ssa * (FT(1) + g));
+    FT g2 = lw_diff_sec * FT(0.5) * ssa * (FT(1) - g);
+    FT k = rsqrt_(rmax(lw_diff_sec * (FT(1) - ssa) * (g1 + g2), Num<FT>::k_min()));
+    FT e1 = rexp(-tau * k);
+    FT om1 = -rexpm1(-tau * k);
+    FT coeff = e1 * e1;
+    FT one_minus_e2kt = om1 * (FT(1) + e1);
+    FT RT_term = FT(1) / (k * (FT(1) + coeff) + g1 * one_minus_e2kt);
+    Rdif = RT_term * g2 * one_minus_e2kt;
+    Tdif = RT_term * FT(2) * k * e1;
+    if (tau > FT(0)) {
+        FT dB = lev_src_bot - lev_src_top;
+        FT g_sum = g1 + g2;
+        FT one_p_e1 = FT(1) + e1;
+        FT emis_fac = om1 * (k * om1 + lw_diff_sec * (FT(1) - ssa) * one_p_e1) * RT_term;
+        FT dBz = dB * (om1 / tau) * (k * om1 + g_sum * one_p_e1) * RT_term / rmax(g_sum, Num<FT>::eps());
+        src_up = Num<FT>::pi() * (lev_src_top * emis_fac - Tdif * dB + dBz);
+        src_dn = Num<FT>::pi() * (lev_src_bot * emis_fac + Tdif * dB - dBz);
+    } else {
+        src_up = FT(0); src_dn = FT(0);
+    }
+}
+
+// ---- shortwave_2stream.jl:189-279 ----
+template <typename FT>
+__device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, FT& Rdir, FT& Tdir, FT& Rdif,
+                                                  FT& Tdif) {
+    FT g1 = (FT(8) - ssa * (FT(5) + FT(3) * g)) * FT(0.25);
+    FT g2 = FT(3) * (ssa * (FT(1) - g)) * FT(0.25);
+    FT g3 = (FT(2) - (FT(3) * mu0) * g) * FT(0.25);
+    FT g4 = FT(1) - g3;
+    FT a1 = g1 * g4 + g2 * g3;
+    FT a2 = g1 * g3 + g2 * g4;
+    FT k = rsqrt_(rmax(FT(2) * (FT(1) - ssa) * (g1 + g2), Num<FT>::k_min()));
+    FT e = rexp(-tau * k);
+    FT e2 = e * e;
+    FT om1 = -rexpm1(-tau * k);
+    FT one_minus_e2kt = om1 * (FT(1) + e);
+    FT RT_term = FT(1) / (k * (FT(1) + e2) + g1 * one_minus_e2kt);
+    Rdif = RT_term * g2 * one_minus_e2kt;
+    Tdif = RT_term * FT(2) * k * e;
+    FT T0 = rexp(-tau / rmax(mu0, Num<FT>::eps()));   // mu0_min = eps (Numerics.jl:63)
+    FT k_mu = k * mu0;
+    FT k_mu2 = k_mu * k_mu;
+    FT diff = FT(1) - k_mu2;
+    const FT win = Num<FT>::k_min();                   // resonance_window = sqrt(eps) (Numerics.jl:49)
+    if (rabs(diff) < win) {
+        k_mu2 = diff >= FT(0) ? FT(1) - win : FT(1) + win;
+        k_mu = rsqrt_(k_mu2);
+    }
+    FT k_g3 = k * g3, k_g4 = k * g4;
+    RT_term = ssa * RT_term / (FT(1) - k_mu2);
+    FT Rdir_u = RT_term * ((FT(1) - k_mu) * (a2 + k_g3) - (FT(1) + k_mu) * (a2 - k_g3) * e2 -
+                           FT(2) * (k_g3 - a2 * k_mu) * e * T0);
+    FT Tdir_u = -RT_term * ((FT(1) + k_mu) * (a1 + k_g4) * T0 - (FT(1) - k_mu) * (a1 - k_g4) * e2 * T0 -
+                            FT(2) * (k_g4 + a1 * k_mu) * e);
+    Rdir = rmax(FT(0), Rdir_u);
+    Tdir = rmax(FT(0), Tdir_u);
+    FT av_energy = rmax(FT(0), FT(1) - T0);
+    FT tot_dir = Rdir + Tdir;
+    if (tot_dir > av_energy) {
+        FT scale = av_energy / rmax(Num<FT>::eps(), tot_dir);
+        Rdir *= scale; Tdir *= scale;
+    }
+}
+
+// ---- longwave_noscat.jl:171-205 ----
+template <typename FT> __device__ __forceinline__ FT lw_noscat_source(FT lev_source, FT lay_source, FT tau_loc, FT trans) {
+    FT fact = (tau_loc > Num<FT>::tau_thresh())
+                  ? ((FT(1) - trans) / tau_loc - trans)
+                  : tau_loc * (FT(0.5) + tau_loc * (-FT(1.0 / 3.0) + tau_loc * FT(0.125)));
+    return (FT(1) - trans) * lev_source + FT(2) * fact * (lay_source - lev_source);
+}
+
+// ---- counter-based McICA uniforms shared bit-for-bit with the CPU oracle ----
+// (the reference draws Random.rand(), cloud_optics.jl:253-262,283,293; see DESIGN.md "McICA")
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t mcica_col_key(uint64_t seed, uint64_t gcol0) {
+    return splitmix64(splitmix64(seed) ^ (gcol0 * 0xD1B54A32D192ED03ULL));
+}
+__host__ __device__ __forceinline__ double mcica_rand(uint64_t col_key, int sw, int igpt, int ilay) {
+    uint64_t h = splitmix64(col_key ^ ((uint64_t)sw << 40) ^ ((uint64_t)igpt << 16) ^ (uint64_t)ilay);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace rb

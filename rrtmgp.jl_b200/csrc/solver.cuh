@@ -1,0 +1,661 @@
+// Fused column-radiation kernels: one warp owns one column, the 32 lanes are 32 consecutive
+// g-points (two 16-g-point bands of the real tables), and the warp walks the column's
+// vertical recurrences with the per-level state of its 32 (column, g-point) problems in
+// shared memory.  Replaces the reference's one-thread-per-column kernels
+// (ext/cuda/rte_longwave_2stream.jl:86-141, rte_shortwave_2stream.jl:96-157,
+// rte_longwave_noscat.jl:91-146), which round-trip tau/ssa/g, sources and per-g-point fluxes
+// through global scratch for every g-point (src/rte/RTE.jl:121-128).
+//
+// Per column and per block of 32 g-points:
+//   phase 1 (lanes = layers x bands)  everything that depends on (layer, band) only:
+//            eta interpolation fractions, minor-gas scalings, Planck functions, LUT cloud
+//            optics, MERRA aerosol optics            -> shared "band records"
+//   McICA    (lanes = g-points)       max-random cloud mask, one bit per layer  -> registers
+//   phase 2  (lanes = g-points)       LUT gathers (64 B per band per corner), tau/ssa/g,
+//            two-stream coefficients, adding recurrences; 4-5 values per level per lane in
+//            the shared "level store"
+//   reduce   (lanes = levels)         g-point sum by a rotated (bank-conflict-free) transposed
+//            read of the level store into per-lane broadband accumulators
+// and once per column: clip-free state prefetch (phase 0) and the (nlev, ncol) epilogue with
+// net flux, metric scaling, night zeroing, cloud cover and AOD diagnostics folded in.
+#pragma once
+#include "device_math.cuh"
+#include "lut.cuh"
+
+namespace rb {
+
+enum SolveMode { MODE_LW_2STREAM = 0, MODE_LW_NOSCAT = 1, MODE_SW_2STREAM = 2 };
+
+constexpr int kMaxLevPerLane = 3;   // nlev <= 96
+
+template <typename FT>
+struct ColumnIO {
+    const FT* layerdata; const FT* p_lev; const FT* t_lev; const FT* t_sfc;
+    const FT* vmr_h2o; const FT* vmr_o3; const FT* vmr;
+    const FT *cld_r_eff_liq, *cld_r_eff_ice, *cld_path_liq, *cld_path_ice, *cld_frac;
+    const FT *aero_mass, *aero_size;
+    const FT *sfc_emis, *inc_flux_lw, *cos_zenith, *toa_flux, *sfc_alb_direct, *sfc_alb_diffuse, *metric_scaling;
+    FT *out_up, *out_dn, *out_net, *out_dir;   // [ncol][nlev]
+    const FT* add_net;                         // lw net to add (SW pass) or null
+    FT* out_total_net;                         // net_flux = lw_net + sw_net or null
+    FT* cld_cover;                             // [ncol] or null
+    FT *aod_ext, *aod_sca;                     // [ncol] or null (SW)
+    FT *band_up, *band_dn, *band_net;          // [n_bnd][ncol][nlev] or null
+};
+
+template <typename FT>
+struct SolveParams {
+    ColumnIO<FT> io;
+    GasLut<FT> lut;
+    CldLut<FT> cld;
+    AeroLut<FT> aero;
+    int ncol, nlay, ngas, vmr_kind, ice_rgh;
+    int use_cloud, use_aero, n_mu;
+    long long col_offset;
+    unsigned long long seed;
+    FT Ds[4], wts[4];
+    // per-warp shared-memory layout, in bytes from the warp's base
+    int off_colj, off_colp, off_recj, off_rec, off_plk, off_store, warp_bytes;
+    int rec_words;   // FT words per band record
+};
+
+// ---------------------------------------------------------------------------------------------
+// VolumeMixingRatios.jl:91-129; ig 1-based gas index (0 = dry air)
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+__device__ __forceinline__ FT get_vmr(const SolveParams<FT>& P, int ig, int lay, long long col) {
+    if (ig == 0) return FT(1);
+    size_t k = (size_t)col * P.nlay + lay;
+    if (P.vmr_kind == 0) {
+        if (ig == 1) return __ldg(P.io.vmr_h2o + k);
+        if (ig == 3) return __ldg(P.io.vmr_o3 + k);
+        return __ldg(P.io.vmr + ig - 1);
+    }
+    return __ldg(P.io.vmr + k * P.ngas + ig - 1);
+}
+
+// cloud_optics.jl:154-192 / :207-244
+template <typename FT>
+__device__ __forceinline__ void cld_props(int nsize, FT lwr, FT upr, const FT* __restrict__ tbl, FT re, FT path,
+                                          FT& tau, FT& tau_ssa, FT& tau_ssag) {
+    tau = tau_ssa = tau_ssag = FT(0);
+    if (path > Num<FT>::eps()) {
+        FT dr = (upr - lwr) / FT(nsize - 1);
+        re = rmax(rmin(re, upr), lwr);
+        int loc = (int)((re - lwr) / dr) + 1;
+        loc = loc < nsize - 1 ? loc : nsize - 1;
+        loc = loc > 1 ? loc : 1;
+        FT fac = (re - lwr - (loc - 1) * dr) / dr;
+        FT fc1 = FT(1) - fac;
+        tau = rmax((fc1 * __ldg(tbl + loc - 1) + fac * __ldg(tbl + loc)) * path, FT(0));
+        tau_ssa = (fc1 * __ldg(tbl + nsize + loc - 1) + fac * __ldg(tbl + nsize + loc)) * tau;
+        tau_ssag = (fc1 * __ldg(tbl + 2 * nsize + loc - 1) + fac * __ldg(tbl + 2 * nsize + loc)) * tau_ssa;
+    }
+}
+
+// aerosol_optics.jl:438-451
+template <typename FT> __device__ __forceinline__ int merra_size_bin(const FT* __restrict__ lims, int nbins, FT size) {
+    int bin = 1;
+    for (int ib = 1; ib <= nbins; ++ib) {
+        if (__ldg(lims + 2 * (ib - 1)) <= size && size <= __ldg(lims + 2 * (ib - 1) + 1)) { bin = ib; break; }
+        bin = nbins;
+    }
+    return bin;
+}
+
+// aerosol_optics.jl:141-235 (+ species functions :243-431); ibnd 0-based
+template <typename FT>
+__device__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, const FT* __restrict__ mass, const FT* __restrict__ size,
+                               FT rh, FT& tc, FT& tsc, FT& tsgc) {
+    tc = tsc = tsgc = FT(0);
+    const int nrh = A.nrh, nbin = A.nbin;
+    int loc = 0; FT f = FT(0); bool have_rh = false;
+    auto rh_species = [&](const FT* __restrict__ t3, FT m) {   // t3 -> (3, nrh) slice
+        if (!have_rh) { interp1d_loc_factor(rh, A.rh_levels, nrh, loc, f); have_rh = true; }
+        FT t = m * (__ldg(t3 + 3 * (loc - 1)) * (FT(1) - f) + __ldg(t3 + 3 * loc) * f);
+        FT ts = t * (__ldg(t3 + 3 * (loc - 1) + 1) * (FT(1) - f) + __ldg(t3 + 3 * loc + 1) * f);
+        FT tsg = ts * (__ldg(t3 + 3 * (loc - 1) + 2) * (FT(1) - f) + __ldg(t3 + 3 * loc + 2) * f);
+        tc += t; tsc += ts; tsgc += tsg;
+    };
+    auto dry_species = [&](const FT* __restrict__ t3, FT m) {
+        FT t = m * __ldg(t3); FT ts = t * __ldg(t3 + 1); FT tsg = ts * __ldg(t3 + 2);
+        tc += t; tsc += ts; tsgc += tsg;
+    };
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {   // dust: species 1, 8..11
+        int i = k == 0 ? 0 : 6 + k;
+        FT m = __ldg(mass + i);
+        if (m > FT(0)) {
+            int bin = merra_size_bin(A.size_bin_limits, nbin, __ldg(size + i));
+            dry_species(A.dust + 3 * ((bin - 1) + (size_t)nbin * ibnd), m);
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {   // sea salt: species 2, 12..15
+        int i = k == 0 ? 1 : 10 + k;
+        FT m = __ldg(mass + i);
+        if (m > FT(0)) {
+            int bin = merra_size_bin(A.size_bin_limits, nbin, __ldg(size + i));
+            rh_species(A.sea_salt + (size_t)3 * nrh * ((bin - 1) + (size_t)nbin * ibnd), m);
+        }
+    }
+    FT m;
+    m = __ldg(mass + 2); if (m > FT(0)) rh_species(A.sulfate + (size_t)3 * nrh * ibnd, m);
+    m = __ldg(mass + 3); if (m > FT(0)) rh_species(A.black_carbon_rh + (size_t)3 * nrh * ibnd, m);
+    m = __ldg(mass + 4); if (m > FT(0)) dry_species(A.black_carbon + 3 * ibnd, m);
+    m = __ldg(mass + 5); if (m > FT(0)) rh_species(A.organic_carbon_rh + (size_t)3 * nrh * ibnd, m);
+    m = __ldg(mass + 6); if (m > FT(0)) dry_species(A.organic_carbon + 3 * ibnd, m);
+}
+
+// optics_utils.jl:85-98 on the g-point-fastest layout; tbl points at [t=0][eta=0][gpt]
+template <typename FT>
+__device__ __forceinline__ FT interp2d_g(const FT* __restrict__ tbl, int n_eta, int n_gpt, int je1, int je2, FT fe1,
+                                         FT fe2, int jt, FT ft) {
+    const size_t st = (size_t)n_eta * n_gpt;
+    const FT* r0 = tbl + (size_t)(jt - 1) * st;
+    const FT* r1 = r0 + st;
+    FT c11 = __ldg(r0 + (size_t)(je1 - 1) * n_gpt), c21 = __ldg(r0 + (size_t)je1 * n_gpt);
+    FT c12 = __ldg(r1 + (size_t)(je2 - 1) * n_gpt), c22 = __ldg(r1 + (size_t)je2 * n_gpt);
+    return (FT(1) - fe1) * (FT(1) - ft) * c11 + fe1 * (FT(1) - ft) * c21 + (FT(1) - fe2) * ft * c12 + fe2 * ft * c22;
+}
+// optics_utils.jl:136-181; tbl points at [p=0][t=0][eta=0][gpt]
+template <typename FT>
+__device__ __forceinline__ FT interp3d_g(const FT* __restrict__ tbl, int n_t, int n_eta, int n_gpt, int je1, int je2,
+                                         FT fe1, FT fe2, int jt, FT ft, int jp, FT fp, FT s1, FT s2) {
+    const size_t st = (size_t)n_eta * n_gpt, sp = st * n_t;
+    const FT* a0 = tbl + (size_t)(jp - 2) * sp + (size_t)(jt - 1) * st;   // (jp-1, jt)
+    const FT* a1 = a0 + sp;                                               // (jp,   jt)
+    const FT* b0 = a0 + st;                                               // (jp-1, jt+1)
+    const FT* b1 = a1 + st;                                               // (jp,   jt+1)
+    const size_t e1 = (size_t)(je1 - 1) * n_gpt, e2 = (size_t)(je2 - 1) * n_gpt;
+    FT c000 = __ldg(a0 + e1), c100 = __ldg(a0 + e1 + n_gpt), c010 = __ldg(a1 + e1), c110 = __ldg(a1 + e1 + n_gpt);
+    FT c001 = __ldg(b0 + e2), c101 = __ldg(b0 + e2 + n_gpt), c011 = __ldg(b1 + e2), c111 = __ldg(b1 + e2 + n_gpt);
+    FT omft = FT(1) - ft, omfp = FT(1) - fp, omfe1 = FT(1) - fe1, omfe2 = FT(1) - fe2;
+    return s1 * (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
+           s2 * (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <typename FT, int MODE>
+__global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const long long col = (long long)blockIdx.x * wpc + warp;
+    if (col >= P.ncol) return;   // warp-uniform; no block-level barriers are used below
+
+    constexpr bool LW = MODE != MODE_SW_2STREAM;
+    constexpr bool NOSCAT = MODE == MODE_LW_NOSCAT;
+    constexpr int NV = MODE == MODE_LW_2STREAM ? 4 : 5;   // level-store values per level
+
+    const GasLut<FT>& L = P.lut;
+    const int nlay = P.nlay, nlev = nlay + 1;
+    const int n_gpt = L.n_gpt, n_eta = L.n_eta, n_t = L.n_t;
+
+    unsigned char* wbase = smem_raw + (size_t)warp * P.warp_bytes;
+    int* colj = reinterpret_cast<int*>(wbase + P.off_colj);   // [nlay] jt | jp<<8 | tropo<<16 | aero<<17
+    FT* colp = reinterpret_cast<FT*>(wbase + P.off_colp);     // [nlay][4] ft, fp, col_dry, vmr_h2o+1
+    int* recj = reinterpret_cast<int*>(wbase + P.off_recj);   // [nlay][maxb] je1 | je2<<4 | nminor<<8
+    FT* rec = reinterpret_cast<FT*>(wbase + P.off_rec);       // [nlay][maxb][rec_words]
+    FT* plk = reinterpret_cast<FT*>(wbase + P.off_plk);       // LW: [maxb][2*nlev] B(t_lev), B(t_lay)/B(t_sfc)
+    FT* store = reinterpret_cast<FT*>(wbase + P.off_store);   // [nlev][NV][32]
+    const int RW = P.rec_words, maxb = L.maxb;
+
+    const FT* ld = P.io.layerdata + (size_t)col * nlay * 4;
+    const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
+
+    // ---------------- phase 0: per-(column, layer) quantities (gas_optics.jl:87-115,188) ----------------
+    for (int k = lane; k < nlay; k += 32) {
+        FT col_dry = __ldg(ld + 4 * k + 0), p_lay = __ldg(ld + 4 * k + 1), t_lay = __ldg(ld + 4 * k + 2);
+        int tropo = p_lay > L.p_ref_tropo ? 1 : 2;
+        FT dT = __ldg(L.t_ref + 1) - __ldg(L.t_ref);
+        int jt = loc_lower_eq(t_lay, dT, n_t, L.t_ref);
+        FT ft = (t_lay - __ldg(L.t_ref + jt - 1)) / dT;
+        FT dlnp = __ldg(L.ln_p_ref) - __ldg(L.ln_p_ref + 1);
+        FT lp = rlog(p_lay);
+        int jpress = (int)((__ldg(L.ln_p_ref) - lp) / dlnp) + 1;
+        jpress = jpress > 1 ? jpress : 1;
+        jpress = (jpress < L.n_p_ref - 1 ? jpress : L.n_p_ref - 1) + 1;
+        FT fp = (__ldg(L.ln_p_ref + jpress - 2) - lp) / dlnp;
+        int jp = jpress + tropo - 1;
+        int aero_on = 0;
+        if (use_aero) {   // aerosol_optics.jl:464-483
+            const FT* am = P.io.aero_mass + ((size_t)col * nlay + k) * 15;
+            for (int i = 0; i < 15; ++i) aero_on |= (__ldg(am + i) > FT(0)) ? 1 : 0;
+        }
+        colj[k] = jt | (jp << 8) | ((tropo - 1) << 16) | (aero_on << 17);
+        colp[4 * k + 0] = ft; colp[4 * k + 1] = fp; colp[4 * k + 2] = col_dry;
+        colp[4 * k + 3] = get_vmr(P, L.idx_h2o, k, col) + FT(1);
+    }
+    __syncwarp();
+
+    // McICA column key; cloudy span (cloud_optics.jl:271-275,309-321)
+    const uint64_t col_key = mcica_col_key(P.seed, (uint64_t)(P.col_offset + col));
+    int cld_start = 0, cld_finish = 0;   // 1-based, 0 = no cloud
+    if (use_cloud) {
+        const FT* cf = P.io.cld_frac + (size_t)col * nlay;
+        unsigned lo = 0xffffffffu, hi = 0;
+        for (int k = lane; k < nlay; k += 32)
+            if (__ldg(cf + k) > FT(0)) { lo = lo < (unsigned)(k + 1) ? lo : (unsigned)(k + 1); hi = hi > (unsigned)(k + 1) ? hi : (unsigned)(k + 1); }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (hi > 0) { cld_start = (int)lo; cld_finish = (int)hi; }
+    }
+
+    const FT mu0 = LW ? FT(1) : __ldg(P.io.cos_zenith + col);
+    const bool day = LW || mu0 > FT(0);
+    const FT toa = LW ? FT(0) : __ldg(P.io.toa_flux + col);
+
+    FT acc_up[kMaxLevPerLane], acc_dn[kMaxLevPerLane], acc_dir[kMaxLevPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxLevPerLane; ++i) acc_up[i] = acc_dn[i] = acc_dir[i] = FT(0);
+    int n_cloudy = 0;
+
+    // =====================================================================================
+    for (int g0 = 0; g0 < n_gpt; g0 += 32) {
+        const bool lane_on = g0 + lane < n_gpt;
+        const int gpt = lane_on ? g0 + lane : n_gpt - 1;
+        const int b_first = __ldg(L.gpt2bnd + g0);
+        const int b_last = __ldg(L.gpt2bnd + (g0 + 31 < n_gpt ? g0 + 31 : n_gpt - 1));
+        const int nb = b_last - b_first + 1;
+        const int ibnd = __ldg(L.gpt2bnd + gpt);
+        const int bl = ibnd - b_first;
+        __syncwarp();
+
+        // ---------------- phase 1: band records ----------------
+        for (int item = lane; item < nb * nlay; item += 32) {
+            const int b = item / nlay, k = item - b * nlay;
+            const int ib = b_first + b;
+            const int cj = colj[k];
+            const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
+            const FT col_dry = colp[4 * k + 2];
+            const FT vmr_h2o = get_vmr(P, L.idx_h2o, k, col);
+            FT* r = rec + ((size_t)k * maxb + b) * RW;
+            // gas_optics.jl:129-170
+            const int ig1 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib));
+            const int ig2 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib) + 1);
+            const FT vmr1 = get_vmr(P, ig1, k, col), vmr2 = get_vmr(P, ig2, k, col);
+            int je[2]; FT fe[2], cm[2];
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const FT* vr = L.vmr_ref + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
+                FT eta_half = __ldg(vr + 2 * ig1) / __ldg(vr + 2 * ig2);
+                FT col_mix = vmr1 + eta_half * vmr2;
+                FT eta = vmr1 * (FT(1) / col_mix);
+                if (col_mix <= FT(0)) eta = FT(0.5);
+                FT loc_eta = eta * FT(n_eta - 1);
+                int j = (int)loc_eta + 1;
+                j = j < n_eta - 1 ? j : n_eta - 1;
+                je[it] = j; fe[it] = loc_eta - FT(j - 1); cm[it] = col_mix;
+            }
+            r[0] = fe[0]; r[1] = fe[1]; r[2] = cm[0]; r[3] = cm[1];
+            // gas_optics.jl:344-412: per-absorber scalings
+            const int* bst = L.minor_bnd_st[tropo - 1];
+            const int m0 = __ldg(bst + ib), nmin = __ldg(bst + ib + 1) - m0;
+            {
+                const FT p_lay = __ldg(ld + 4 * k + 1), t_lay = __ldg(ld + 4 * k + 2);
+                const FT dry_fact = FT(1) / (FT(1) + vmr_h2o);
+                const FT density_fact = FT(0.01) * p_lay / t_lay;
+                for (int i = 0; i < nmin; ++i) {
+                    const int* gd = L.minor_gasdata[tropo - 1] + 4 * (m0 + i);
+                    const int idx_gas = __ldg(gd), idx_sc = __ldg(gd + 1), swd = __ldg(gd + 2), sbc = __ldg(gd + 3);
+                    FT vmr_i = get_vmr(P, idx_gas, k, col);
+                    FT scaling = FT(0);
+                    if (vmr_i > FT(0)) {
+                        scaling = vmr_i * col_dry;
+                        if (swd == 1) {
+                            scaling *= density_fact;
+                            if (idx_sc > 0) {
+                                if (sbc == 1) scaling *= (FT(1) - get_vmr(P, idx_sc, k, col) * dry_fact);
+                                else scaling *= get_vmr(P, idx_sc, k, col) * dry_fact;
+                            }
+                        }
+                    }
+                    r[4 + i] = scaling;
+                }
+            }
+            recj[k * maxb + b] = je[0] | (je[1] << 4) | (nmin << 8);
+            FT* rc = r + 4 + L.nminor_max;   // cloud (3) then aerosol (3)
+            // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
+            if (use_cloud) {
+                FT tc = FT(0), sc = FT(0), gc = FT(0);
+                size_t kk = (size_t)col * nlay + k;
+                if (__ldg(P.io.cld_frac + kk) > FT(0)) {
+                    const CldLut<FT>& C = P.cld;
+                    const FT* liq = C.liqdata + (size_t)3 * C.nsize_liq * ib;
+                    const FT* ice = C.icedata + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
+                    FT tl, tls, tlsg, ti, tis, tisg;
+                    cld_props(C.nsize_liq, C.radliq_lwr, C.radliq_upr, liq, __ldg(P.io.cld_r_eff_liq + kk),
+                              __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
+                    cld_props(C.nsize_ice, C.radice_lwr, C.radice_upr, ice, __ldg(P.io.cld_r_eff_ice + kk),
+                              __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
+                    if (NOSCAT) {
+                        tc = (tl - tls) + (ti - tis);
+                    } else {
+                        tc = tl + ti;
+                        sc = tls + tis;
+                        gc = (tlsg + tisg) / rmax(Num<FT>::eps(), sc);
+                        sc /= rmax(Num<FT>::eps(), tc);
+                        if (!LW) delta_scale(tc, sc, gc);
+                    }
+                }
+                rc[0] = tc; rc[1] = sc; rc[2] = gc;
+            }
+            // aerosol_optics.jl:80-133 (2-stream) / :18-61 (1-scalar)
+            if (use_aero) {
+                FT ta = FT(0), sa = FT(0), ga = FT(0), t_ext = FT(0), t_sca = FT(0);
+                if ((cj >> 17) & 1) {
+                    size_t kk = ((size_t)col * nlay + k) * 15;
+                    FT tsa, tsga;
+                    lookup_aerosol(P.aero, ib, P.io.aero_mass + kk, P.io.aero_size + kk, __ldg(ld + 4 * k + 3), ta, tsa, tsga);
+                    t_ext = ta; t_sca = tsa;
+                    if (NOSCAT) {
+                        ta = ta - tsa;
+                    } else {
+                        ga = tsga / rmax(Num<FT>::eps(), tsa);
+                        sa = tsa / rmax(Num<FT>::eps(), ta);
+                        if (!LW) delta_scale(ta, sa, ga);
+                    }
+                }
+                rc[3] = ta; rc[4] = sa; rc[5] = ga;
+                if (!LW && ib + 1 == P.aero.iband_550nm) { rc[6] = t_ext; rc[7] = t_sca; }
+            }
+            // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
+            if (LW) {
+                const FT* totplnk = L.tot_planck + (size_t)L.n_t_plnk * ib;
+                FT* pb = plk + (size_t)b * 2 * nlev;
+                const FT* tl = P.io.t_lev + (size_t)col * nlev;
+                pb[k + 1] = interp1d_equispaced(__ldg(tl + k + 1), L.t_planck, totplnk, L.n_t_plnk);
+                if (k == 0) {
+                    pb[0] = interp1d_equispaced(__ldg(tl), L.t_planck, totplnk, L.n_t_plnk);
+                    pb[nlev + nlay] = interp1d_equispaced(__ldg(P.io.t_sfc + col), L.t_planck, totplnk, L.n_t_plnk);
+                }
+                if (NOSCAT) pb[nlev + k] = interp1d_equispaced(__ldg(ld + 4 * k + 2), L.t_planck, totplnk, L.n_t_plnk);
+            }
+        }
+        __syncwarp();
+
+        // AOD diagnostic at 550 nm (aerosol_optics.jl:96-116): sequential layer sum of the band's records
+        if (!LW && use_aero && P.io.aod_ext != nullptr && P.aero.iband_550nm >= b_first + 1 &&
+            P.aero.iband_550nm <= b_last + 1 && lane == 0) {
+            const int b = P.aero.iband_550nm - 1 - b_first;
+            FT e = FT(0), s = FT(0);
+            for (int k = 0; k < nlay; ++k)
+                if ((colj[k] >> 17) & 1) {
+                    const FT* rc = rec + ((size_t)k * maxb + b) * RW + 4 + L.nminor_max;
+                    e += rc[6]; s += rc[7];
+                }
+            P.io.aod_ext[col] = e; P.io.aod_sca[col] = s;
+        }
+
+        // ---------------- McICA mask for this lane's g-point (cloud_optics.jl:264-307) ----------------
+        unsigned mask[kMaxLevPerLane] = {0u, 0u, 0u};
+        if (use_cloud && cld_finish > 0) {
+            const FT* cf = P.io.cld_frac + (size_t)col * nlay;
+            const int swflag = LW ? 0 : 1;
+            FT cf_p1 = __ldg(cf + cld_finish - 1);
+            double r_p1 = mcica_rand(col_key, swflag, gpt + 1, cld_finish);
+            bool m_p1 = r_p1 >= (double)(FT(1) - cf_p1);
+            if (m_p1) mask[(cld_finish - 1) >> 5] |= 1u << ((cld_finish - 1) & 31);
+            for (int ilay = cld_finish - 1; ilay >= cld_start; --ilay) {
+                FT cfk = __ldg(cf + ilay - 1);
+                bool m = false;
+                if (cfk > FT(0)) {
+                    double r = m_p1 ? r_p1 : mcica_rand(col_key, swflag, gpt + 1, ilay) * (double)(FT(1) - cf_p1);
+                    m = r >= (double)(FT(1) - cfk);
+                    r_p1 = r;
+                }
+                if (m) mask[(ilay - 1) >> 5] |= 1u << ((ilay - 1) & 31);
+                cf_p1 = cfk; m_p1 = m;
+            }
+            bool any = lane_on && ((mask[0] | mask[1] | mask[2]) != 0u);
+            n_cloudy += __popc(__ballot_sync(0xffffffffu, any));
+        }
+        auto mask_bit = [&](int k) -> bool {
+            unsigned w = k < 32 ? mask[0] : (k < 64 ? mask[1] : mask[2]);
+            return (w >> (k & 31)) & 1u;
+        };
+
+        if (!day) continue;   // night: masks/AOD only (shortwave_2stream.jl:66-102)
+
+        // ---------------- phase 2 ----------------
+        // gas + cloud + aerosol optics of layer k for this lane's g-point
+        auto optics = [&](int k, FT& tau, FT& ssa, FT& g, FT& pfrac) {
+            const int cj = colj[k];
+            const int jt = cj & 0xff, jp = (cj >> 8) & 0xff, tr = (cj >> 16) & 1;
+            const FT ft = colp[4 * k + 0], fp = colp[4 * k + 1], col_dry = colp[4 * k + 2];
+            const int rj = recj[k * maxb + bl];
+            const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf, nmin = rj >> 8;
+            const FT* r = rec + ((size_t)k * maxb + bl) * RW;
+            const FT fe1 = r[0], fe2 = r[1];
+            FT tau_major = interp3d_g(L.kmajor + gpt, n_t, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft, jp, fp, r[2], r[3]) * col_dry;
+            FT tau_minor = FT(0);
+            const FT* km = L.kminor[tr] + gpt;
+            for (int i = 0; i < nmin; ++i)
+                tau_minor += interp2d_g(km + (size_t)i * n_t * n_eta * n_gpt, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft) * r[4 + i];
+            if (LW) {
+                pfrac = interp3d_g(L.pfrac + gpt, n_t, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft, jp, fp, FT(1), FT(1));
+                tau = rmax(tau_major + tau_minor, FT(0));
+                ssa = FT(0); g = FT(0);
+            } else {
+                FT tau_ray = interp2d_g(L.rayl + (size_t)tr * n_t * n_eta * n_gpt + gpt, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft) *
+                             colp[4 * k + 3] * col_dry;
+                tau = rmax(tau_major + tau_minor + tau_ray, FT(0));
+                ssa = tau_ray * (FT(1) / tau);
+                if (tau <= FT(0)) ssa = FT(0);
+                g = FT(0); pfrac = FT(0);
+            }
+            const FT* rc = r + 4 + L.nminor_max;
+            if (use_cloud && mask_bit(k)) {
+                if (NOSCAT) tau += rc[0];
+                else increment_2stream(tau, ssa, g, rc[0], rc[1], rc[2]);
+            }
+            if (use_aero && ((cj >> 17) & 1)) {
+                if (NOSCAT) tau += rc[3];
+                else increment_2stream(tau, ssa, g, rc[3], rc[4], rc[5]);
+            }
+        };
+        auto S = [&](int lev, int v) -> FT& { return store[((size_t)lev * NV + v) * 32 + lane]; };
+
+        if (MODE == MODE_LW_2STREAM) {
+            // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding
+            const FT* pb = plk + (size_t)bl * 2 * nlev;
+            const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
+            const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : FT(0);
+            FT tau, ssa, g, pf;
+            optics(0, tau, ssa, g, pf);
+            FT lev_bot = pb[0] * pf;
+            FT albedo = FT(1) - emis;
+            FT src = Num<FT>::pi() * emis * (pb[nlev + nlay] * pf);
+            for (int k = 0; k < nlay; ++k) {
+                FT tau_n = FT(0), ssa_n = FT(0), g_n = FT(0), pf_n = FT(0), lev_top;
+                FT inc_k = pb[k + 1] * pf;                       // lev_src_inc of layer k
+                if (k + 1 < nlay) {
+                    optics(k + 1, tau_n, ssa_n, g_n, pf_n);
+                    lev_top = rsqrt_(inc_k * (pb[k + 1] * pf_n));   // sqrt(inc_prev * dec)
+                } else {
+                    lev_top = inc_k;
+                }
+                FT Rdif, Tdif, su, sd;
+                lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
+                FT denom = FT(1) / (FT(1) - Rdif * albedo);
+                // level k (bottom of layer k): what the downward sweep needs
+                S(k, 0) = Tdif * denom;                           // A_k
+                S(k, 1) = (Rdif * src + sd) * denom;              // B_k
+                S(k, 2) = albedo;
+                S(k, 3) = src;
+                FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
+                src = su + Tdif * denom * (src + albedo * sd);
+                albedo = albedo_n;
+                lev_bot = lev_top; tau = tau_n; ssa = ssa_n; g = g_n; pf = pf_n;
+            }
+            // top of domain, then downward sweep: F_dn(k) = A_k F_dn(k+1) + B_k ; F_up(k) = alb_k F_dn(k) + src_k
+            FT dn = inc;
+            FT up = dn * albedo + src;
+            S(nlay, 0) = lane_on ? up : FT(0);
+            S(nlay, 1) = lane_on ? dn : FT(0);
+            for (int k = nlay - 1; k >= 0; --k) {
+                dn = S(k, 0) * dn + S(k, 1);
+                up = dn * S(k, 2) + S(k, 3);
+                S(k, 0) = lane_on ? up : FT(0);
+                S(k, 1) = lane_on ? dn : FT(0);
+            }
+        } else if (MODE == MODE_SW_2STREAM) {
+            // shortwave_2stream.jl:300-392
+            const FT alb_dir = __ldg(P.io.sfc_alb_direct + (size_t)col * L.n_bnd + ibnd);
+            const FT alb_dif = __ldg(P.io.sfc_alb_diffuse + (size_t)col * L.n_bnd + ibnd);
+            const FT dir_top = toa * __ldg(L.solar_src_scaled + gpt) * mu0;
+            const FT inv_mu0 = FT(1) / rmax(mu0, Num<FT>::eps());
+            FT tau_cum = FT(0), dir_above = dir_top;
+            S(nlay, 4) = dir_top;
+            for (int k = nlay - 1; k >= 0; --k) {   // direct beam + layer coefficients, top down
+                FT tau, ssa, g, pf;
+                optics(k, tau, ssa, g, pf);
+                FT Rdir, Tdir, Rdif, Tdif;
+                sw_2stream_coeffs(tau, ssa, g, mu0, Rdir, Tdir, Rdif, Tdif);
+                tau_cum += tau;
+                S(k, 0) = Rdif; S(k, 1) = Tdif;
+                S(k, 2) = Rdir * dir_above;           // src_up of layer k
+                S(k, 3) = Tdir * dir_above;           // src_dn of layer k
+                dir_above = dir_top * rexp(-tau_cum * inv_mu0);
+                S(k, 4) = dir_above;                  // direct flux at level k
+            }
+            FT albedo = alb_dif, src = dir_above * alb_dir;
+            for (int k = 0; k < nlay; ++k) {        // bottom up: albedo / source of everything below
+                FT Rdif = S(k, 0), Tdif = S(k, 1), su = S(k, 2), sd = S(k, 3);
+                FT denom = FT(1) / (FT(1) - Rdif * albedo);
+                S(k, 0) = Tdif * denom;
+                S(k, 1) = (Rdif * src + sd) * denom;
+                S(k, 2) = albedo;
+                S(k, 3) = src;
+                FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
+                src = su + Tdif * denom * (src + albedo * sd);
+                albedo = albedo_n;
+            }
+            FT dn = FT(0);                           // diffuse incident flux (shortwave_2stream.jl:331)
+            FT up = dn * albedo + src;
+            S(nlay, 0) = lane_on ? up : FT(0);
+            S(nlay, 1) = lane_on ? dn + S(nlay, 4) : FT(0);
+            if (!lane_on) S(nlay, 4) = FT(0);
+            for (int k = nlay - 1; k >= 0; --k) {
+                dn = S(k, 0) * dn + S(k, 1);
+                up = dn * S(k, 2) + S(k, 3);
+                S(k, 0) = lane_on ? up : FT(0);
+                S(k, 1) = lane_on ? dn + S(k, 4) : FT(0);
+                if (!lane_on) S(k, 4) = FT(0);
+            }
+        } else {
+            // compute_optical_props.jl:43-82 sources + longwave_noscat.jl:224-301 per angle
+            const FT* pb = plk + (size_t)bl * 2 * nlev;
+            const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
+            const bool has_inc = P.io.inc_flux_lw != nullptr;
+            const FT inc = has_inc ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : FT(0);
+            FT sfc_source = FT(0), inc_prev = FT(0);
+            for (int k = 0; k < nlay; ++k) {
+                FT tau, ssa, g, pf;
+                optics(k, tau, ssa, g, pf);
+                S(k, 0) = tau;
+                S(k, 1) = pb[nlev + k] * pf;              // lay_source
+                FT src_inc = pb[k + 1] * pf, src_dec = pb[k] * pf;
+                if (k == 0) { sfc_source = pb[nlev + nlay] * pf; S(0, 2) = src_dec; }
+                else S(k, 2) = rsqrt_(inc_prev * src_dec);
+                inc_prev = src_inc;
+                S(k, 3) = FT(0); S(k, 4) = FT(0);
+            }
+            S(nlay, 2) = inc_prev; S(nlay, 3) = FT(0); S(nlay, 4) = FT(0);
+            for (int imu = 0; imu < P.n_mu; ++imu) {
+                const FT Ds = P.Ds[imu], i2f = Num<FT>::pi() * P.wts[imu];
+                FT I = has_inc ? inc / Num<FT>::pi() : FT(0);
+                S(nlay, 4) += I * i2f;
+                for (int k = nlay - 1; k >= 0; --k) {
+                    FT tau_loc = S(k, 0) * Ds;
+                    FT trans = rexp(-tau_loc);
+                    I = trans * I + lw_noscat_source(S(k, 2), S(k, 1), tau_loc, trans);
+                    S(k, 4) += I * i2f;
+                }
+                I = I * (FT(1) - emis) + emis * sfc_source;
+                S(0, 3) += I * i2f;
+                for (int k = 1; k <= nlay; ++k) {
+                    FT tau_loc = S(k - 1, 0) * Ds;
+                    FT trans = rexp(-tau_loc);
+                    I = trans * I + lw_noscat_source(S(k, 2), S(k - 1, 1), tau_loc, trans);
+                    S(k, 3) += I * i2f;
+                }
+            }
+            if (!lane_on)
+                for (int k = 0; k <= nlay; ++k) { S(k, 3) = FT(0); S(k, 4) = FT(0); }
+        }
+        __syncwarp();
+
+        // ---------------- g-point reduction: lane <-> level (driver_utils.jl:37-84) ----------------
+        {
+            constexpr int VU = NOSCAT ? 3 : 0, VD = NOSCAT ? 4 : 1;
+#pragma unroll
+            for (int i = 0; i < kMaxLevPerLane; ++i) {
+                const int lev = lane + 32 * i;
+                if (lev < nlev) {
+                    const FT* su = store + ((size_t)lev * NV + VU) * 32;
+                    const FT* sd = store + ((size_t)lev * NV + VD) * 32;
+                    FT u = FT(0), d = FT(0), dr = FT(0);
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j) {
+                        const int l2 = (lane + j) & 31;
+                        u += su[l2]; d += sd[l2];
+                        if (MODE == MODE_SW_2STREAM) dr += store[((size_t)lev * NV + 4) * 32 + l2];
+                    }
+                    acc_up[i] += u; acc_dn[i] += d; acc_dir[i] += dr;
+                    if (P.io.band_up != nullptr) {   // Fluxes.jl:199-215, bands of this block
+                        for (int b = 0; b < nb; ++b) {
+                            FT bu = FT(0), bd = FT(0);
+                            for (int j = 0; j < 32; ++j) {
+                                const int l2 = (lane + j) & 31;
+                                if (g0 + l2 < n_gpt && __ldg(L.gpt2bnd + g0 + l2) == b_first + b) { bu += su[l2]; bd += sd[l2]; }
+                            }
+                            size_t o = ((size_t)(b_first + b) * P.ncol + col) * nlev + lev;
+                            P.io.band_up[o] += bu; P.io.band_dn[o] += bd;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---------------- epilogue: (nlev, ncol) presentation, net, scaling, diagnostics ----------------
+#pragma unroll
+    for (int i = 0; i < kMaxLevPerLane; ++i) {
+        const int lev = lane + 32 * i;
+        if (lev < nlev) {
+            const size_t o = (size_t)col * nlev + lev;
+            FT up = day ? acc_up[i] : FT(0), dn = day ? acc_dn[i] : FT(0), dr = day ? acc_dir[i] : FT(0);
+            FT net = up - dn;                                    // Fluxes.jl:225-233
+            if (P.io.metric_scaling != nullptr) {                // Fluxes.jl:295-304, after net
+                FT sc = __ldg(P.io.metric_scaling + o);
+                up *= sc; dn *= sc; net *= sc; dr *= sc;
+            }
+            P.io.out_up[o] = up; P.io.out_dn[o] = dn; P.io.out_net[o] = net;
+            if (!LW) P.io.out_dir[o] = dr;
+            if (P.io.out_total_net != nullptr) P.io.out_total_net[o] = P.io.add_net[o] + net;   // Fluxes.jl:423-435
+            if (P.io.band_up != nullptr) {
+                for (int b = 0; b < L.n_bnd; ++b) {
+                    size_t ob = ((size_t)b * P.ncol + col) * nlev + lev;
+                    FT bu = P.io.band_up[ob], bd = P.io.band_dn[ob];
+                    if (!day) { bu = FT(0); bd = FT(0); }
+                    if (P.io.metric_scaling != nullptr) { FT sc = __ldg(P.io.metric_scaling + o); bu *= sc; bd *= sc; }
+                    P.io.band_up[ob] = bu; P.io.band_dn[ob] = bd; P.io.band_net[ob] = bu - bd;
+                }
+            }
+        }
+    }
+    if (lane == 0 && P.io.cld_cover != nullptr && use_cloud)
+        P.io.cld_cover[col] = FT(n_cloudy) / FT(n_gpt);         // ext/cuda/rte_longwave_2stream.jl:131-138
+}
+
+// Launches solve_kernel<FT, MODE>; returns cudaError_t as int.  Defined in solver.cu.
+template <typename FT> int launch_solve(int mode, SolveParams<FT>& P, int max_smem_optin, void* stream);
+// Fills the shared-memory layout fields of P; returns bytes per warp.
+template <typename FT> int plan_smem(int mode, SolveParams<FT>& P);
+
+}  // namespace rb

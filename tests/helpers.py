@@ -1,0 +1,64 @@
+"""Shared helpers: run the same synthetic problem through the CUDA engine (C ABI) and the CPU oracle."""
+from __future__ import annotations
+
+import numpy as np
+
+import rrtmgp_b200 as R
+from oracle import DEFAULT_PARAMS, Oracle
+
+# thresholds of the reference's Float32<->Float64 ratchet (test/float32_consistency.jl:53-62)
+F32_LW, F32_SW_CLEAR, F32_SW_CLOUDY = 1.0e-3, 3.0e-2, 1.2e-1
+
+_METHODS = {"clear_sky": R.ClearSkyRadiation, "all_sky": R.AllSkyRadiation,
+            "all_sky_with_clear": R.AllSkyRadiationWithClearSkyDiagnostics}
+
+_OUT_MAP = {"lw_up": "lw_flux_up", "lw_dn": "lw_flux_dn", "lw_net": "lw_flux_net", "sw_up": "sw_flux_up",
+            "sw_dn": "sw_flux_dn", "sw_net": "sw_flux_net", "sw_dir": "sw_flux_dn_dir", "net": "net_flux",
+            "clear_lw_up": "clear_lw_flux_up", "clear_lw_dn": "clear_lw_flux_dn", "clear_lw_net": "clear_lw_flux_net",
+            "clear_sw_up": "clear_sw_flux_up", "clear_sw_dn": "clear_sw_flux_dn", "clear_sw_net": "clear_sw_flux_net",
+            "clear_sw_dir": "clear_sw_flux_dn_dir", "clear_net": "clear_net_flux",
+            "cld_cover_lw": "cld_cover_lw", "cld_cover_sw": "cld_cover_sw", "aod_sw_ext": "aod_sw_ext",
+            "aod_sw_sca": "aod_sw_sca", "lw_band_up": "lw_band_flux_up", "lw_band_dn": "lw_band_flux_dn",
+            "sw_band_up": "sw_band_flux_up", "sw_band_dn": "sw_band_flux_dn"}
+
+
+def make_solver(pack, state, dtype, *, method="all_sky", aerosols=True, lw_noscat=False, n_gauss_angles=1,
+                spectral=False, ice_rgh=2, col_offset=0, isothermal_boundary_layer=False, params=None):
+    ncol, nlay = state["layerdata"].shape[:2]
+    p = R.default_parameters(**(params or DEFAULT_PARAMS))
+    gp = R.RRTMGPGridParams(FT=dtype, domain_nlay=nlay - int(isothermal_boundary_layer), ncol=ncol,
+                            isothermal_boundary_layer=isothermal_boundary_layer)
+    rm = _METHODS[method](aerosol_radiation=aerosols) if method == "clear_sky" else \
+        _METHODS[method](aerosol_radiation=aerosols, reset_rng_seed=True)
+    s = R.RRTMGPSolver(gp, rm, p, pack, op_lw="one_scalar" if lw_noscat else "two_stream",
+                       n_gauss_angles=n_gauss_angles, spectral_fluxes=spectral,
+                       vmr_kind="full" if "vmr_full" in state else "gm", ice_rgh=ice_rgh,
+                       inc_flux_lw="inc_flux_lw" in state, with_lat="lat" in state, col_offset=col_offset,
+                       deep_atmosphere_inverse_scaling=state.get("metric_scaling"))
+    s.set_state(state)
+    return s
+
+
+def run_engine(pack, state, dtype, *, seed=0, **kw):
+    """update_fluxes! through the C ABI; returns host numpy arrays under the oracle's key names."""
+    import torch
+    s = make_solver(pack, state, dtype, **kw)
+    R.update_fluxes(s, seed)
+    torch.cuda.synchronize()
+    out = {}
+    for k, b in _OUT_MAP.items():
+        t = s.buffers.get(b)
+        if t is not None:
+            out[k] = t.cpu().numpy()
+    out["state"] = {k: s.buffers[k].cpu().numpy() for k in ("layerdata", "p_lev", "t_lev")}
+    out["solver"] = s
+    return out
+
+
+def run_oracle(pack, state, dtype, *, seed=0, isothermal_boundary_layer=False, **kw):
+    assert not isothermal_boundary_layer
+    return Oracle(pack, dtype).update_fluxes(state, seed=seed, **kw)
+
+
+def maxdiff(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max())
