@@ -1,12 +1,24 @@
 // Scalar building blocks of the hot path, shared by every kernel.  Each function names the
-// reference routine it computes (file:line in CliMA/RRTMGP.jl v1.0.0).  IEEE division /
-// sqrt / full-precision exp, expm1, log are kept (no --use_fast_math): the reference's
-// numerics notes (docs/src/precision.md:36-72) depend on the exact guard constants below.
+// reference routine it computes (file:line in CliMA/RRTMGP.jl v1.0.0).
+//
+// Precision policy.  Float64 kernels use IEEE division / sqrt and the full-precision libdevice
+// exp / expm1 / log throughout.  Float32 kernels keep IEEE arithmetic for the once-per-column
+// and once-per-(layer, band) work (phase 0 / phase 1) but use the SFU approximations
+// (ex2.approx, rcp.approx, sqrt.approx: <= 2 ulp) inside the per-(layer, g-point) loop, where
+// a full-precision IEEE divide costs ~15 instructions with a divergent slow path.  The guard
+// constants of src/Numerics.jl are kept exactly; 1 - exp(-x) keeps its small-x accuracy (the
+// reason the reference uses expm1, longwave_2stream.jl:168-170) through a series below x = 0.25.
+// Parity against the Float64 oracle is asserted in tests/test_gpu_parity.py with the
+// reference's own Float32 thresholds.  Compile with -DRB_EXACT_MATH=1 to use IEEE everywhere.
 #pragma once
 #include <cuda_runtime.h>
 
 #include <cfloat>
 #include <cstdint>
+
+#ifndef RB_EXACT_MATH
+#define RB_EXACT_MATH 0
+#endif
 
 namespace rb {
 
@@ -25,6 +37,7 @@ template <> struct Num<double> {
     static __device__ __forceinline__ double pi() { return 3.141592653589793; }
 };
 
+// full-precision forms (phase 0 / phase 1, and everything in Float64)
 __device__ __forceinline__ float rexp(float x) { return expf(x); }
 __device__ __forceinline__ double rexp(double x) { return exp(x); }
 __device__ __forceinline__ float rexpm1(float x) { return expm1f(x); }
@@ -39,16 +52,46 @@ template <typename FT> __device__ __forceinline__ FT rmax(FT a, FT b) { return a
 template <typename FT> __device__ __forceinline__ FT rmin(FT a, FT b) { return a < b ? a : b; }
 template <typename FT> __device__ __forceinline__ FT rabs(FT a) { return a < FT(0) ? -a : a; }
 
+// hot-loop forms
+__device__ __forceinline__ double hdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ double hsqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double hexp(double x) { return exp(x); }
+__device__ __forceinline__ double h_one_minus_exp_neg(double x, double) { return -expm1(-x); }
+#if RB_EXACT_MATH
+__device__ __forceinline__ float hdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float hsqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float hexp(float x) { return expf(x); }
+__device__ __forceinline__ float h_one_minus_exp_neg(float x, float) { return -expm1f(-x); }
+#else
+__device__ __forceinline__ float hdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float hsqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float hexp(float x) { return __expf(x); }
+// 1 - exp(-x), x >= 0, given e = exp(-x): Taylor series below 0.25 (truncation < 2e-9 relative)
+__device__ __forceinline__ float h_one_minus_exp_neg(float x, float e) {
+    float p = fmaf(x, -1.0f / 5040.0f, 1.0f / 720.0f);
+    p = fmaf(x, -p, 1.0f / 120.0f);
+    p = fmaf(x, -p, 1.0f / 24.0f);
+    p = fmaf(x, -p, 1.0f / 6.0f);
+    p = fmaf(x, -p, 0.5f);
+    p = fmaf(x, -p, 1.0f);
+    return x < 0.25f ? x * p : 1.0f - e;
+}
+#endif
+
 // ---- optics_utils.jl:189-202 ----
 template <typename FT>
 __device__ __forceinline__ void increment_2stream(FT& t1, FT& s1, FT& g1, FT t2, FT s2, FT g2) {
     FT tau = t1 + t2;
     FT ssa = t1 * s1 + t2 * s2;
-    FT ssag = (t1 * s1 * g1 + t2 * s2 * g2) / rmax(Num<FT>::eps(), ssa);
-    ssa /= rmax(Num<FT>::eps(), tau);
+    FT ssag = hdiv(t1 * s1 * g1 + t2 * s2 * g2, rmax(Num<FT>::eps(), ssa));
+    ssa = hdiv(ssa, rmax(Num<FT>::eps(), tau));
     t1 = tau; s1 = ssa; g1 = ssag;
 }
-// ---- optics_utils.jl:208-223 ----
+// ---- optics_utils.jl:208-223 (phase 1: IEEE) ----
 template <typename FT> __device__ __forceinline__ void delta_scale(FT& tau, FT& ssa, FT& g) {
     FT ssa_one_minus_g2 = ssa * (FT(1) - g) * (FT(1) + g);
     FT one_minus_wf = (FT(1) - ssa) + ssa_one_minus_g2;
@@ -64,14 +107,20 @@ template <typename FT> __device__ __forceinline__ int loc_lower_eq(FT xi, FT dx,
     int j = (int)((xi - __ldg(x)) / dx) + 1;
     return j < n - 1 ? j : n - 1;
 }
-// ---- optics_utils.jl:34-44 ----
+// ---- optics_utils.jl:34-44 split into "locate" (per level) and "evaluate" (per band) ----
+// loc = 0 encodes "below range -> y[0]", loc = n encodes "above range -> y[n-1]"
 template <typename FT>
-__device__ __forceinline__ FT interp1d_equispaced(FT xi, const FT* __restrict__ x, const FT* __restrict__ y, int n) {
-    if (xi < __ldg(x)) return __ldg(y);
-    if (xi > __ldg(x + n - 1)) return __ldg(y + n - 1);
+__device__ __forceinline__ void interp1d_eq_locate(FT xi, const FT* __restrict__ x, int n, int& loc, FT& factor) {
+    if (xi < __ldg(x)) { loc = 0; factor = FT(0); return; }
+    if (xi > __ldg(x + n - 1)) { loc = n; factor = FT(0); return; }
     FT dx = __ldg(x + 1) - __ldg(x);
-    int loc = loc_lower_eq(xi, dx, n, x);
-    FT factor = (xi - __ldg(x + loc - 1)) / dx;
+    loc = loc_lower_eq(xi, dx, n, x);
+    factor = (xi - __ldg(x + loc - 1)) / dx;
+}
+template <typename FT>
+__device__ __forceinline__ FT interp1d_eq_eval(int loc, FT factor, const FT* __restrict__ y, int n) {
+    if (loc == 0) return __ldg(y);
+    if (loc == n) return __ldg(y + n - 1);
     return __ldg(y + loc - 1) * (FT(1) - factor) + __ldg(y + loc) * factor;
 }
 // ---- optics_utils.jl:51-62 + :21-27 (non-uniform x) ----
@@ -94,12 +143,13 @@ __device__ __forceinline__ void lw_2stream_coeffs(FT tau, FT ssa, FT g, FT lev_s
     const FT lw_diff_sec = FT(1.66);
     FT g1 = lw_diff_sec * (FT(1) - FT(0.5) * ssa * (FT(1) + g));
     FT g2 = lw_diff_sec * FT(0.5) * ssa * (FT(1) - g);
-    FT k = rsqrt_(rmax(lw_diff_sec * (FT(1) - ssa) * (g1 + g2), Num<FT>::k_min()));
-    FT e1 = rexp(-tau * k);
-    FT om1 = -rexpm1(-tau * k);
+    FT k = hsqrt(rmax(lw_diff_sec * (FT(1) - ssa) * (g1 + g2), Num<FT>::k_min()));
+    FT tk = tau * k;
+    FT e1 = hexp(-tk);
+    FT om1 = h_one_minus_exp_neg(tk, e1);
     FT coeff = e1 * e1;
     FT one_minus_e2kt = om1 * (FT(1) + e1);
-    FT RT_term = FT(1) / (k * (FT(1) + coeff) + g1 * one_minus_e2kt);
+    FT RT_term = hdiv(FT(1), k * (FT(1) + coeff) + g1 * one_minus_e2kt);
     Rdif = RT_term * g2 * one_minus_e2kt;
     Tdif = RT_term * FT(2) * k * e1;
     if (tau > FT(0)) {
@@ -107,7 +157,7 @@ __device__ __forceinline__ void lw_2stream_coeffs(FT tau, FT ssa, FT g, FT lev_s
         FT g_sum = g1 + g2;
         FT one_p_e1 = FT(1) + e1;
         FT emis_fac = om1 * (k * om1 + lw_diff_sec * (FT(1) - ssa) * one_p_e1) * RT_term;
-        FT dBz = dB * (om1 / tau) * (k * om1 + g_sum * one_p_e1) * RT_term / rmax(g_sum, Num<FT>::eps());
+        FT dBz = hdiv(dB * hdiv(om1, tau) * (k * om1 + g_sum * one_p_e1) * RT_term, rmax(g_sum, Num<FT>::eps()));
         src_up = Num<FT>::pi() * (lev_src_top * emis_fac - Tdif * dB + dBz);
         src_dn = Num<FT>::pi() * (lev_src_bot * emis_fac + Tdif * dB - dBz);
     } else {
@@ -117,33 +167,34 @@ __device__ __forceinline__ void lw_2stream_coeffs(FT tau, FT ssa, FT g, FT lev_s
 
 // ---- shortwave_2stream.jl:189-279 ----
 template <typename FT>
-__device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, FT& Rdir, FT& Tdir, FT& Rdif,
-                                                  FT& Tdif) {
+__device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, FT inv_mu0, FT& Rdir, FT& Tdir,
+                                                  FT& Rdif, FT& Tdif) {
     FT g1 = (FT(8) - ssa * (FT(5) + FT(3) * g)) * FT(0.25);
     FT g2 = FT(3) * (ssa * (FT(1) - g)) * FT(0.25);
     FT g3 = (FT(2) - (FT(3) * mu0) * g) * FT(0.25);
     FT g4 = FT(1) - g3;
     FT a1 = g1 * g4 + g2 * g3;
     FT a2 = g1 * g3 + g2 * g4;
-    FT k = rsqrt_(rmax(FT(2) * (FT(1) - ssa) * (g1 + g2), Num<FT>::k_min()));
-    FT e = rexp(-tau * k);
+    FT k = hsqrt(rmax(FT(2) * (FT(1) - ssa) * (g1 + g2), Num<FT>::k_min()));
+    FT tk = tau * k;
+    FT e = hexp(-tk);
     FT e2 = e * e;
-    FT om1 = -rexpm1(-tau * k);
+    FT om1 = h_one_minus_exp_neg(tk, e);
     FT one_minus_e2kt = om1 * (FT(1) + e);
-    FT RT_term = FT(1) / (k * (FT(1) + e2) + g1 * one_minus_e2kt);
+    FT RT_term = hdiv(FT(1), k * (FT(1) + e2) + g1 * one_minus_e2kt);
     Rdif = RT_term * g2 * one_minus_e2kt;
     Tdif = RT_term * FT(2) * k * e;
-    FT T0 = rexp(-tau / rmax(mu0, Num<FT>::eps()));   // mu0_min = eps (Numerics.jl:63)
+    FT T0 = hexp(-tau * inv_mu0);                       // inv_mu0 = 1 / max(mu0, eps) (Numerics.jl:63)
     FT k_mu = k * mu0;
     FT k_mu2 = k_mu * k_mu;
     FT diff = FT(1) - k_mu2;
-    const FT win = Num<FT>::k_min();                   // resonance_window = sqrt(eps) (Numerics.jl:49)
+    const FT win = Num<FT>::k_min();                    // resonance_window = sqrt(eps) (Numerics.jl:49)
     if (rabs(diff) < win) {
         k_mu2 = diff >= FT(0) ? FT(1) - win : FT(1) + win;
-        k_mu = rsqrt_(k_mu2);
+        k_mu = hsqrt(k_mu2);
     }
     FT k_g3 = k * g3, k_g4 = k * g4;
-    RT_term = ssa * RT_term / (FT(1) - k_mu2);
+    RT_term = hdiv(ssa * RT_term, FT(1) - k_mu2);
     FT Rdir_u = RT_term * ((FT(1) - k_mu) * (a2 + k_g3) - (FT(1) + k_mu) * (a2 - k_g3) * e2 -
                            FT(2) * (k_g3 - a2 * k_mu) * e * T0);
     FT Tdir_u = -RT_term * ((FT(1) + k_mu) * (a1 + k_g4) * T0 - (FT(1) - k_mu) * (a1 - k_g4) * e2 * T0 -
@@ -153,7 +204,7 @@ __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, 
     FT av_energy = rmax(FT(0), FT(1) - T0);
     FT tot_dir = Rdir + Tdir;
     if (tot_dir > av_energy) {
-        FT scale = av_energy / rmax(Num<FT>::eps(), tot_dir);
+        FT scale = hdiv(av_energy, rmax(Num<FT>::eps(), tot_dir));
         Rdir *= scale; Tdir *= scale;
     }
 }
@@ -161,7 +212,7 @@ __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, 
 // ---- longwave_noscat.jl:171-205 ----
 template <typename FT> __device__ __forceinline__ FT lw_noscat_source(FT lev_source, FT lay_source, FT tau_loc, FT trans) {
     FT fact = (tau_loc > Num<FT>::tau_thresh())
-                  ? ((FT(1) - trans) / tau_loc - trans)
+                  ? (hdiv(FT(1) - trans, tau_loc) - trans)
                   : tau_loc * (FT(0.5) + tau_loc * (-FT(1.0 / 3.0) + tau_loc * FT(0.125)));
     return (FT(1) - trans) * lev_source + FT(2) * fact * (lay_source - lev_source);
 }

@@ -8,7 +8,7 @@ static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 template <typename FT> int plan_smem(int mode, SolveParams<FT>& P) {
     const int nlay = P.nlay, nlev = nlay + 1, maxb = P.lut.maxb;
     const int nv = mode == MODE_LW_2STREAM ? 4 : 5;
-    P.rec_words = 4 + P.lut.nminor_max + 8;
+    P.rec_words = 4 + P.lut.nminor_max + 6;
     int off = 0;
     P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
     P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(FT), 16);

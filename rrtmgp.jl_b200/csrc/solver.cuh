@@ -1,23 +1,26 @@
 // Fused column-radiation kernels: one warp owns one column, the 32 lanes are 32 consecutive
 // g-points (two 16-g-point bands of the real tables), and the warp walks the column's
-// vertical recurrences with the per-level state of its 32 (column, g-point) problems in
-// shared memory.  Replaces the reference's one-thread-per-column kernels
+// vertical recurrences with the per-level state of its 32 (column, g-point) problems on chip.
+// Replaces the reference's one-thread-per-column kernels
 // (ext/cuda/rte_longwave_2stream.jl:86-141, rte_shortwave_2stream.jl:96-157,
 // rte_longwave_noscat.jl:91-146), which round-trip tau/ssa/g, sources and per-g-point fluxes
 // through global scratch for every g-point (src/rte/RTE.jl:121-128).
 //
-// Per column and per block of 32 g-points:
-//   phase 1 (lanes = layers x bands)  everything that depends on (layer, band) only:
-//            eta interpolation fractions, minor-gas scalings, Planck functions, LUT cloud
-//            optics, MERRA aerosol optics            -> shared "band records"
-//   McICA    (lanes = g-points)       max-random cloud mask, one bit per layer  -> registers
-//   phase 2  (lanes = g-points)       LUT gathers (64 B per band per corner), tau/ssa/g,
-//            two-stream coefficients, adding recurrences; 4-5 values per level per lane in
-//            the shared "level store"
-//   reduce   (lanes = levels)         g-point sum by a rotated (bank-conflict-free) transposed
-//            read of the level store into per-lane broadband accumulators
-// and once per column: clip-free state prefetch (phase 0) and the (nlev, ncol) epilogue with
-// net flux, metric scaling, night zeroing, cloud cover and AOD diagnostics folded in.
+// Per column:
+//   phase 0 (lane = layer)   everything that depends on (column, layer) only: T/p interpolation
+//            indices and fractions, aerosol size bins and RH interval, cloud-LUT and Planck
+//            interpolation positions.  The reference recomputes these for every g-point.
+// and per block of 32 g-points:
+//   phase 1 (lane = layer, loop over the block's bands)  everything that depends on (layer, band):
+//            eta interpolation, minor-gas scalings, Planck functions, LUT cloud optics, MERRA
+//            aerosol optics                                    -> shared-memory "band records"
+//   McICA    (lane = g-point)  max-random cloud mask, one bit per layer        -> registers
+//   phase 2  (lane = g-point)  LUT gathers (one 64 B segment per band per corner), tau/ssa/g,
+//            two-stream coefficients, adding recurrences with 4-5 values per level per lane in
+//            the on-chip "level store"
+//   reduce   g-point sum into per-lane broadband accumulators (lane = level)
+// and once per column the (nlev, ncol) epilogue with net flux, metric scaling, night zeroing,
+// cloud cover and AOD diagnostics folded in.
 #pragma once
 #include "device_math.cuh"
 #include "lut.cuh"
@@ -74,18 +77,21 @@ __device__ __forceinline__ FT get_vmr(const SolveParams<FT>& P, int ig, int lay,
     return __ldg(P.io.vmr + k * P.ngas + ig - 1);
 }
 
-// cloud_optics.jl:154-192 / :207-244
+// cloud_optics.jl:154-192 / :207-244, split into "locate" (per layer) and "evaluate" (per band)
 template <typename FT>
-__device__ __forceinline__ void cld_props(int nsize, FT lwr, FT upr, const FT* __restrict__ tbl, FT re, FT path,
-                                          FT& tau, FT& tau_ssa, FT& tau_ssag) {
+__device__ __forceinline__ void cld_locate(int nsize, FT lwr, FT upr, FT re, int& loc, FT& fac) {
+    FT dr = (upr - lwr) / FT(nsize - 1);
+    re = rmax(rmin(re, upr), lwr);
+    loc = (int)((re - lwr) / dr) + 1;
+    loc = loc < nsize - 1 ? loc : nsize - 1;
+    loc = loc > 1 ? loc : 1;
+    fac = (re - lwr - (loc - 1) * dr) / dr;
+}
+template <typename FT>
+__device__ __forceinline__ void cld_eval(int nsize, const FT* __restrict__ tbl, int loc, FT fac, FT path, FT& tau,
+                                         FT& tau_ssa, FT& tau_ssag) {
     tau = tau_ssa = tau_ssag = FT(0);
     if (path > Num<FT>::eps()) {
-        FT dr = (upr - lwr) / FT(nsize - 1);
-        re = rmax(rmin(re, upr), lwr);
-        int loc = (int)((re - lwr) / dr) + 1;
-        loc = loc < nsize - 1 ? loc : nsize - 1;
-        loc = loc > 1 ? loc : 1;
-        FT fac = (re - lwr - (loc - 1) * dr) / dr;
         FT fc1 = FT(1) - fac;
         tau = rmax((fc1 * __ldg(tbl + loc - 1) + fac * __ldg(tbl + loc)) * path, FT(0));
         tau_ssa = (fc1 * __ldg(tbl + nsize + loc - 1) + fac * __ldg(tbl + nsize + loc)) * tau;
@@ -103,15 +109,18 @@ template <typename FT> __device__ __forceinline__ int merra_size_bin(const FT* _
     return bin;
 }
 
+// Per-(column, layer) aerosol bookkeeping: which of the 15 species are present, the MERRA size
+// bin of the ten sized species (dust 1,8..11 then sea salt 2,12..15; 3 bits each) and the RH
+// interval (aerosol_optics.jl:141-235 hoisted out of the band loop).
+struct AeroLayer { unsigned active; unsigned bins; int rh_loc; };
+
 // aerosol_optics.jl:141-235 (+ species functions :243-431); ibnd 0-based
 template <typename FT>
-__device__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, const FT* __restrict__ mass, const FT* __restrict__ size,
-                               FT rh, FT& tc, FT& tsc, FT& tsgc) {
+__device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, const FT* __restrict__ mass,
+                                               const AeroLayer& al, FT f, FT& tc, FT& tsc, FT& tsgc) {
     tc = tsc = tsgc = FT(0);
-    const int nrh = A.nrh, nbin = A.nbin;
-    int loc = 0; FT f = FT(0); bool have_rh = false;
+    const int nrh = A.nrh, nbin = A.nbin, loc = al.rh_loc;
     auto rh_species = [&](const FT* __restrict__ t3, FT m) {   // t3 -> (3, nrh) slice
-        if (!have_rh) { interp1d_loc_factor(rh, A.rh_levels, nrh, loc, f); have_rh = true; }
         FT t = m * (__ldg(t3 + 3 * (loc - 1)) * (FT(1) - f) + __ldg(t3 + 3 * loc) * f);
         FT ts = t * (__ldg(t3 + 3 * (loc - 1) + 1) * (FT(1) - f) + __ldg(t3 + 3 * loc + 1) * f);
         FT tsg = ts * (__ldg(t3 + 3 * (loc - 1) + 2) * (FT(1) - f) + __ldg(t3 + 3 * loc + 2) * f);
@@ -121,62 +130,377 @@ __device__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, const FT* __restr
         FT t = m * __ldg(t3); FT ts = t * __ldg(t3 + 1); FT tsg = ts * __ldg(t3 + 2);
         tc += t; tsc += ts; tsgc += tsg;
     };
+    unsigned act = al.active;
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {   // dust: species 1, 8..11
         int i = k == 0 ? 0 : 6 + k;
-        FT m = __ldg(mass + i);
-        if (m > FT(0)) {
-            int bin = merra_size_bin(A.size_bin_limits, nbin, __ldg(size + i));
-            dry_species(A.dust + 3 * ((bin - 1) + (size_t)nbin * ibnd), m);
+        if ((act >> i) & 1u) {
+            int bin = (int)((al.bins >> (3 * k)) & 7u);
+            dry_species(A.dust + 3 * ((bin - 1) + (size_t)nbin * ibnd), __ldg(mass + i));
         }
     }
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {   // sea salt: species 2, 12..15
         int i = k == 0 ? 1 : 10 + k;
-        FT m = __ldg(mass + i);
-        if (m > FT(0)) {
-            int bin = merra_size_bin(A.size_bin_limits, nbin, __ldg(size + i));
-            rh_species(A.sea_salt + (size_t)3 * nrh * ((bin - 1) + (size_t)nbin * ibnd), m);
+        if ((act >> i) & 1u) {
+            int bin = (int)((al.bins >> (15 + 3 * k)) & 7u);
+            rh_species(A.sea_salt + (size_t)3 * nrh * ((bin - 1) + (size_t)nbin * ibnd), __ldg(mass + i));
         }
     }
-    FT m;
-    m = __ldg(mass + 2); if (m > FT(0)) rh_species(A.sulfate + (size_t)3 * nrh * ibnd, m);
-    m = __ldg(mass + 3); if (m > FT(0)) rh_species(A.black_carbon_rh + (size_t)3 * nrh * ibnd, m);
-    m = __ldg(mass + 4); if (m > FT(0)) dry_species(A.black_carbon + 3 * ibnd, m);
-    m = __ldg(mass + 5); if (m > FT(0)) rh_species(A.organic_carbon_rh + (size_t)3 * nrh * ibnd, m);
-    m = __ldg(mass + 6); if (m > FT(0)) dry_species(A.organic_carbon + 3 * ibnd, m);
-}
-
-// optics_utils.jl:85-98 on the g-point-fastest layout; tbl points at [t=0][eta=0][gpt]
-template <typename FT>
-__device__ __forceinline__ FT interp2d_g(const FT* __restrict__ tbl, int n_eta, int n_gpt, int je1, int je2, FT fe1,
-                                         FT fe2, int jt, FT ft) {
-    const size_t st = (size_t)n_eta * n_gpt;
-    const FT* r0 = tbl + (size_t)(jt - 1) * st;
-    const FT* r1 = r0 + st;
-    FT c11 = __ldg(r0 + (size_t)(je1 - 1) * n_gpt), c21 = __ldg(r0 + (size_t)je1 * n_gpt);
-    FT c12 = __ldg(r1 + (size_t)(je2 - 1) * n_gpt), c22 = __ldg(r1 + (size_t)je2 * n_gpt);
-    return (FT(1) - fe1) * (FT(1) - ft) * c11 + fe1 * (FT(1) - ft) * c21 + (FT(1) - fe2) * ft * c12 + fe2 * ft * c22;
-}
-// optics_utils.jl:136-181; tbl points at [p=0][t=0][eta=0][gpt]
-template <typename FT>
-__device__ __forceinline__ FT interp3d_g(const FT* __restrict__ tbl, int n_t, int n_eta, int n_gpt, int je1, int je2,
-                                         FT fe1, FT fe2, int jt, FT ft, int jp, FT fp, FT s1, FT s2) {
-    const size_t st = (size_t)n_eta * n_gpt, sp = st * n_t;
-    const FT* a0 = tbl + (size_t)(jp - 2) * sp + (size_t)(jt - 1) * st;   // (jp-1, jt)
-    const FT* a1 = a0 + sp;                                               // (jp,   jt)
-    const FT* b0 = a0 + st;                                               // (jp-1, jt+1)
-    const FT* b1 = a1 + st;                                               // (jp,   jt+1)
-    const size_t e1 = (size_t)(je1 - 1) * n_gpt, e2 = (size_t)(je2 - 1) * n_gpt;
-    FT c000 = __ldg(a0 + e1), c100 = __ldg(a0 + e1 + n_gpt), c010 = __ldg(a1 + e1), c110 = __ldg(a1 + e1 + n_gpt);
-    FT c001 = __ldg(b0 + e2), c101 = __ldg(b0 + e2 + n_gpt), c011 = __ldg(b1 + e2), c111 = __ldg(b1 + e2 + n_gpt);
-    FT omft = FT(1) - ft, omfp = FT(1) - fp, omfe1 = FT(1) - fe1, omfe2 = FT(1) - fe2;
-    return s1 * (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
-           s2 * (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)));
+    if ((act >> 2) & 1u) rh_species(A.sulfate + (size_t)3 * nrh * ibnd, __ldg(mass + 2));
+    if ((act >> 3) & 1u) rh_species(A.black_carbon_rh + (size_t)3 * nrh * ibnd, __ldg(mass + 3));
+    if ((act >> 4) & 1u) dry_species(A.black_carbon + 3 * ibnd, __ldg(mass + 4));
+    if ((act >> 5) & 1u) rh_species(A.organic_carbon_rh + (size_t)3 * nrh * ibnd, __ldg(mass + 5));
+    if ((act >> 6) & 1u) dry_species(A.organic_carbon + 3 * ibnd, __ldg(mass + 6));
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// Per-warp context shared by the kernels below
+// ---------------------------------------------------------------------------------------------
+template <typename FT, int MODE>
+struct Warp {
+    static constexpr bool LW = MODE != MODE_SW_2STREAM;
+    static constexpr bool NOSCAT = MODE == MODE_LW_NOSCAT;
+
+    const SolveParams<FT>& P;
+    const GasLut<FT>& L;
+    const int lane;
+    const long long col;
+    const int nlay, nlev;
+    // shared memory
+    int* colj;   // [nlay] jt | jp<<8 | tropo<<16 | aero<<17
+    FT* colp;    // [nlay][4] ft, fp, col_dry, vmr_h2o + 1
+    int* recj;   // [nlay][maxb] je1 | je2<<4 | nminor<<8
+    FT* rec;     // [nlay][maxb][RW]: fe1, fe2, s1, s2, minor scalings, cloud(3), aerosol(3)
+    FT* plk;     // LW: [maxb][2*nlev] B(t_lev) | B(t_lay) (noscat) | B(t_sfc)
+    const int RW, maxb;
+    // per-lane registers for the layers this lane owns in phase 0/1: lane, lane+32, lane+64
+    FT own_h2o[kMaxLevPerLane], own_dens[kMaxLevPerLane];
+    AeroLayer own_aero[kMaxLevPerLane];
+    FT own_rh_f[kMaxLevPerLane];
+    int own_cld[kMaxLevPerLane];          // loc_liq | loc_ice << 8 | cloudy << 16
+    FT own_cld_fl[kMaxLevPerLane], own_cld_fi[kMaxLevPerLane];
+    int own_pl_loc[kMaxLevPerLane], own_py_loc[kMaxLevPerLane];   // Planck positions: t_lev[k+1], t_lay[k]
+    FT own_pl_f[kMaxLevPerLane], own_py_f[kMaxLevPerLane];
+    int p0_loc, psfc_loc; FT p0_f, psfc_f;                        // t_lev[0], t_sfc (lane 0)
+    // current g-point block
+    int gpt, ibnd, bl, b_first, nb;
+    bool lane_on;
+    unsigned mask[kMaxLevPerLane];
+
+    __device__ __forceinline__ Warp(const SolveParams<FT>& P_, unsigned char* wbase, int lane_, long long col_)
+        : P(P_), L(P_.lut), lane(lane_), col(col_), nlay(P_.nlay), nlev(P_.nlay + 1),
+          colj(reinterpret_cast<int*>(wbase + P_.off_colj)), colp(reinterpret_cast<FT*>(wbase + P_.off_colp)),
+          recj(reinterpret_cast<int*>(wbase + P_.off_recj)), rec(reinterpret_cast<FT*>(wbase + P_.off_rec)),
+          plk(reinterpret_cast<FT*>(wbase + P_.off_plk)), RW(P_.rec_words), maxb(P_.lut.maxb) {}
+
+    // ---------------- phase 0 (gas_optics.jl:87-115,188 and the hoisted per-layer searches) ----------------
+    __device__ __forceinline__ void phase0() {
+        const FT* ld = P.io.layerdata + (size_t)col * nlay * 4;
+        const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
+        const int n_t = L.n_t;
+#pragma unroll
+        for (int j = 0; j < kMaxLevPerLane; ++j) {
+            const int k = lane + 32 * j;
+            own_h2o[j] = FT(0); own_dens[j] = FT(0); own_aero[j] = AeroLayer{0u, 0u, 1}; own_rh_f[j] = FT(0);
+            own_cld[j] = 0; own_cld_fl[j] = own_cld_fi[j] = FT(0);
+            own_pl_loc[j] = own_py_loc[j] = 0; own_pl_f[j] = own_py_f[j] = FT(0);
+            if (k >= nlay) continue;
+            FT col_dry = __ldg(ld + 4 * k + 0), p_lay = __ldg(ld + 4 * k + 1), t_lay = __ldg(ld + 4 * k + 2);
+            int tropo = p_lay > L.p_ref_tropo ? 1 : 2;
+            FT dT = __ldg(L.t_ref + 1) - __ldg(L.t_ref);
+            int jt = loc_lower_eq(t_lay, dT, n_t, L.t_ref);
+            FT ft = (t_lay - __ldg(L.t_ref + jt - 1)) / dT;
+            FT dlnp = __ldg(L.ln_p_ref) - __ldg(L.ln_p_ref + 1);
+            FT lp = rlog(p_lay);
+            int jpress = (int)((__ldg(L.ln_p_ref) - lp) / dlnp) + 1;
+            jpress = jpress > 1 ? jpress : 1;
+            jpress = (jpress < L.n_p_ref - 1 ? jpress : L.n_p_ref - 1) + 1;
+            FT fp = (__ldg(L.ln_p_ref + jpress - 2) - lp) / dlnp;
+            int jp = jpress + tropo - 1;
+            FT h2o = get_vmr(P, L.idx_h2o, k, col);
+            own_h2o[j] = h2o;
+            own_dens[j] = FT(0.01) * p_lay / t_lay;
+            int aero_on = 0;
+            if (use_aero) {   // aerosol_optics.jl:464-483, :438-451, optics_utils.jl:51-62
+                const FT* am = P.io.aero_mass + ((size_t)col * nlay + k) * 15;
+                const FT* as = P.io.aero_size + ((size_t)col * nlay + k) * 15;
+                unsigned act = 0u, bins = 0u;
+                for (int i = 0; i < 15; ++i) act |= (__ldg(am + i) > FT(0)) ? (1u << i) : 0u;
+                if (act) {
+                    for (int s = 0; s < 5; ++s) {
+                        int i = s == 0 ? 0 : 6 + s;
+                        if ((act >> i) & 1u) bins |= (unsigned)merra_size_bin(P.aero.size_bin_limits, P.aero.nbin, __ldg(as + i)) << (3 * s);
+                        i = s == 0 ? 1 : 10 + s;
+                        if ((act >> i) & 1u) bins |= (unsigned)merra_size_bin(P.aero.size_bin_limits, P.aero.nbin, __ldg(as + i)) << (15 + 3 * s);
+                    }
+                    int loc; FT f;
+                    interp1d_loc_factor(__ldg(ld + 4 * k + 3), P.aero.rh_levels, P.aero.nrh, loc, f);
+                    own_aero[j] = AeroLayer{act, bins, loc};
+                    own_rh_f[j] = f;
+                    aero_on = 1;
+                }
+            }
+            if (use_cloud) {
+                size_t kk = (size_t)col * nlay + k;
+                if (__ldg(P.io.cld_frac + kk) > FT(0)) {
+                    const CldLut<FT>& C = P.cld;
+                    int ll, li;
+                    cld_locate(C.nsize_liq, C.radliq_lwr, C.radliq_upr, __ldg(P.io.cld_r_eff_liq + kk), ll, own_cld_fl[j]);
+                    cld_locate(C.nsize_ice, C.radice_lwr, C.radice_upr, __ldg(P.io.cld_r_eff_ice + kk), li, own_cld_fi[j]);
+                    own_cld[j] = ll | (li << 8) | (1 << 16);
+                }
+            }
+            if (LW) {
+                const FT* tl = P.io.t_lev + (size_t)col * nlev;
+                interp1d_eq_locate(__ldg(tl + k + 1), L.t_planck, L.n_t_plnk, own_pl_loc[j], own_pl_f[j]);
+                if (NOSCAT) interp1d_eq_locate(t_lay, L.t_planck, L.n_t_plnk, own_py_loc[j], own_py_f[j]);
+            }
+            colj[k] = jt | (jp << 8) | ((tropo - 1) << 16) | (aero_on << 17);
+            colp[4 * k + 0] = ft; colp[4 * k + 1] = fp; colp[4 * k + 2] = col_dry; colp[4 * k + 3] = h2o + FT(1);
+        }
+        p0_loc = psfc_loc = 0; p0_f = psfc_f = FT(0);
+        if (LW && lane == 0) {
+            interp1d_eq_locate(__ldg(P.io.t_lev + (size_t)col * nlev), L.t_planck, L.n_t_plnk, p0_loc, p0_f);
+            interp1d_eq_locate(__ldg(P.io.t_sfc + col), L.t_planck, L.n_t_plnk, psfc_loc, psfc_f);
+        }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ void set_block(int g0) {
+        const int n_gpt = L.n_gpt;
+        lane_on = g0 + lane < n_gpt;
+        gpt = lane_on ? g0 + lane : n_gpt - 1;
+        b_first = __ldg(L.gpt2bnd + g0);
+        const int b_last = __ldg(L.gpt2bnd + (g0 + 31 < n_gpt ? g0 + 31 : n_gpt - 1));
+        nb = b_last - b_first + 1;
+        ibnd = __ldg(L.gpt2bnd + gpt);
+        bl = ibnd - b_first;
+    }
+
+    // ---------------- phase 1: band records of this block ----------------
+    // returns this lane's partial (aod_ext, aod_sca) of the 550 nm band if it is in the block
+    __device__ __forceinline__ void phase1(FT& aod_e, FT& aod_s) {
+        const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
+        const int n_eta = L.n_eta;
+        aod_e = aod_s = FT(0);
+#pragma unroll
+        for (int j = 0; j < kMaxLevPerLane; ++j) {
+            const int k = lane + 32 * j;
+            if (k >= nlay) continue;
+            const int cj = colj[k];
+            const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
+            const FT col_dry = colp[4 * k + 2];
+            const FT vmr_h2o = own_h2o[j];
+            const FT dry_fact = FT(1) / (FT(1) + vmr_h2o);
+            for (int b = 0; b < nb; ++b) {
+                const int ib = b_first + b;
+                FT* r = rec + ((size_t)k * maxb + b) * RW;
+                // gas_optics.jl:129-170
+                const int ig1 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib));
+                const int ig2 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib) + 1);
+                const FT vmr1 = get_vmr(P, ig1, k, col), vmr2 = get_vmr(P, ig2, k, col);
+                int je[2];
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const FT* vr = L.vmr_ref + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
+                    FT eta_half = __ldg(vr + 2 * ig1) / __ldg(vr + 2 * ig2);
+                    FT col_mix = vmr1 + eta_half * vmr2;
+                    FT eta = vmr1 * (FT(1) / col_mix);
+                    if (col_mix <= FT(0)) eta = FT(0.5);
+                    FT loc_eta = eta * FT(n_eta - 1);
+                    int jj = (int)loc_eta + 1;
+                    jj = jj < n_eta - 1 ? jj : n_eta - 1;
+                    je[it] = jj; r[it] = loc_eta - FT(jj - 1); r[2 + it] = col_mix;
+                }
+                // gas_optics.jl:344-412: per-absorber scalings
+                const int* bst = L.minor_bnd_st[tropo - 1];
+                const int m0 = __ldg(bst + ib), nmin = __ldg(bst + ib + 1) - m0;
+                for (int i = 0; i < nmin; ++i) {
+                    const int4 gd = __ldg(reinterpret_cast<const int4*>(L.minor_gasdata[tropo - 1]) + (m0 + i));
+                    FT vmr_i = get_vmr(P, gd.x, k, col);
+                    FT scaling = FT(0);
+                    if (vmr_i > FT(0)) {
+                        scaling = vmr_i * col_dry;
+                        if (gd.z == 1) {
+                            scaling *= own_dens[j];
+                            if (gd.y > 0) {
+                                if (gd.w == 1) scaling *= (FT(1) - get_vmr(P, gd.y, k, col) * dry_fact);
+                                else scaling *= get_vmr(P, gd.y, k, col) * dry_fact;
+                            }
+                        }
+                    }
+                    r[4 + i] = scaling;
+                }
+                recj[k * maxb + b] = je[0] | (je[1] << 4) | (nmin << 8);
+                FT* rc = r + 4 + L.nminor_max;   // cloud (3) then aerosol (3)
+                // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
+                if (use_cloud) {
+                    FT tc = FT(0), sc = FT(0), gc = FT(0);
+                    if ((own_cld[j] >> 16) & 1) {
+                        const CldLut<FT>& C = P.cld;
+                        size_t kk = (size_t)col * nlay + k;
+                        const FT* liq = C.liqdata + (size_t)3 * C.nsize_liq * ib;
+                        const FT* ice = C.icedata + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
+                        FT tl, tls, tlsg, ti, tis, tisg;
+                        cld_eval(C.nsize_liq, liq, own_cld[j] & 0xff, own_cld_fl[j], __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
+                        cld_eval(C.nsize_ice, ice, (own_cld[j] >> 8) & 0xff, own_cld_fi[j], __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
+                        if (NOSCAT) {
+                            tc = (tl - tls) + (ti - tis);
+                        } else {
+                            tc = tl + ti;
+                            sc = tls + tis;
+                            gc = (tlsg + tisg) / rmax(Num<FT>::eps(), sc);
+                            sc /= rmax(Num<FT>::eps(), tc);
+                            if (!LW) delta_scale(tc, sc, gc);
+                        }
+                    }
+                    rc[0] = tc; rc[1] = sc; rc[2] = gc;
+                }
+                // aerosol_optics.jl:80-133 (2-stream) / :18-61 (1-scalar)
+                if (use_aero) {
+                    FT ta = FT(0), sa = FT(0), ga = FT(0);
+                    if ((cj >> 17) & 1) {
+                        size_t kk = ((size_t)col * nlay + k) * 15;
+                        FT tsa, tsga;
+                        lookup_aerosol(P.aero, ib, P.io.aero_mass + kk, own_aero[j], own_rh_f[j], ta, tsa, tsga);
+                        if (!LW && ib + 1 == P.aero.iband_550nm) { aod_e += ta; aod_s += tsa; }   // :96-116
+                        if (NOSCAT) {
+                            ta = ta - tsa;
+                        } else {
+                            ga = tsga / rmax(Num<FT>::eps(), tsa);
+                            sa = tsa / rmax(Num<FT>::eps(), ta);
+                            if (!LW) delta_scale(ta, sa, ga);
+                        }
+                    }
+                    rc[3] = ta; rc[4] = sa; rc[5] = ga;
+                }
+                // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
+                if (LW) {
+                    const FT* totplnk = L.tot_planck + (size_t)L.n_t_plnk * ib;
+                    FT* pb = plk + (size_t)b * 2 * nlev;
+                    pb[k + 1] = interp1d_eq_eval(own_pl_loc[j], own_pl_f[j], totplnk, L.n_t_plnk);
+                    if (k == 0) {
+                        pb[0] = interp1d_eq_eval(p0_loc, p0_f, totplnk, L.n_t_plnk);
+                        pb[nlev + nlay] = interp1d_eq_eval(psfc_loc, psfc_f, totplnk, L.n_t_plnk);
+                    }
+                    if (NOSCAT) pb[nlev + k] = interp1d_eq_eval(own_py_loc[j], own_py_f[j], totplnk, L.n_t_plnk);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---------------- McICA mask of this lane's g-point (cloud_optics.jl:264-307) ----------------
+    // returns the number of this block's g-points with any cloudy layer
+    __device__ __forceinline__ int mcica(uint64_t col_key, int cld_start, int cld_finish) {
+#pragma unroll
+        for (int i = 0; i < kMaxLevPerLane; ++i) mask[i] = 0u;
+        if (!(P.use_cloud != 0) || cld_finish <= 0) return 0;
+        const FT* cf = P.io.cld_frac + (size_t)col * nlay;
+        const int swflag = LW ? 0 : 1;
+        FT cf_p1 = __ldg(cf + cld_finish - 1);
+        double r_p1 = mcica_rand(col_key, swflag, gpt + 1, cld_finish);
+        bool m_p1 = r_p1 >= (double)(FT(1) - cf_p1);
+        set_mask(cld_finish - 1, m_p1);
+        for (int ilay = cld_finish - 1; ilay >= cld_start; --ilay) {
+            FT cfk = __ldg(cf + ilay - 1);
+            bool m = false;
+            if (cfk > FT(0)) {
+                double r = m_p1 ? r_p1 : mcica_rand(col_key, swflag, gpt + 1, ilay) * (double)(FT(1) - cf_p1);
+                m = r >= (double)(FT(1) - cfk);
+                r_p1 = r;
+            }
+            set_mask(ilay - 1, m);
+            cf_p1 = cfk; m_p1 = m;
+        }
+        bool any = lane_on && ((mask[0] | mask[1] | mask[2]) != 0u);
+        return __popc(__ballot_sync(0xffffffffu, any));
+    }
+    __device__ __forceinline__ void set_mask(int k, bool m) {
+        const unsigned bit = m ? (1u << (k & 31)) : 0u;
+        if (k < 32) mask[0] |= bit; else if (k < 64) mask[1] |= bit; else mask[2] |= bit;
+    }
+    __device__ __forceinline__ bool mask_bit(int k) const {
+        unsigned w = k < 32 ? mask[0] : (k < 64 ? mask[1] : mask[2]);
+        return (w >> (k & 31)) & 1u;
+    }
+
+    // ---------------- gas + cloud + aerosol optics of layer k for this lane's g-point ----------------
+    // gas_optics.jl:176-320 with the (layer, band) work read from the band record; 32-bit table offsets
+    __device__ __forceinline__ void optics(int k, FT& tau, FT& ssa, FT& g, FT& pfrac) const {
+        const int n_gpt = L.n_gpt, n_eta = L.n_eta, n_t = L.n_t;
+        const int cj = colj[k];
+        const int jt = cj & 0xff, jp = (cj >> 8) & 0xff, tr = (cj >> 16) & 1;
+        const FT ft = colp[4 * k + 0], fp = colp[4 * k + 1], col_dry = colp[4 * k + 2];
+        const int rj = recj[k * maxb + bl];
+        const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf, nmin = rj >> 8;
+        const FT* r = rec + (k * maxb + bl) * RW;
+        const FT fe1 = r[0], fe2 = r[1];
+        const FT omfe1 = FT(1) - fe1, omfe2 = FT(1) - fe2, omft = FT(1) - ft, omfp = FT(1) - fp;
+        // element offsets (all tables < 2^31 elements)
+        const int st = n_eta * n_gpt, sp = st * n_t;
+        const int oa = (jp - 2) * sp + (jt - 1) * st + (je1 - 1) * n_gpt + gpt;    // (jp-1, jt,   je1)
+        const int ob = (jp - 2) * sp + jt * st + (je2 - 1) * n_gpt + gpt;          // (jp-1, jt+1, je2)
+        const int ma = (jt - 1) * st + (je1 - 1) * n_gpt + gpt;                    // minor / Rayleigh (jt, je1)
+        const int mb = jt * st + (je2 - 1) * n_gpt + gpt;                          //                  (jt+1, je2)
+        {
+            const FT* km = L.kmajor;
+            FT c000 = __ldg(km + oa), c100 = __ldg(km + oa + n_gpt), c010 = __ldg(km + oa + sp), c110 = __ldg(km + oa + sp + n_gpt);
+            FT c001 = __ldg(km + ob), c101 = __ldg(km + ob + n_gpt), c011 = __ldg(km + ob + sp), c111 = __ldg(km + ob + sp + n_gpt);
+            FT tau_major = (r[2] * (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
+                            r[3] * (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)))) * col_dry;
+            tau = tau_major;
+        }
+        const FT w11 = omfe1 * omft, w21 = fe1 * omft, w12 = omfe2 * ft, w22 = fe2 * ft;   // optics_utils.jl:85-98
+        {
+            const FT* kmn = L.kminor[tr];
+            FT tau_minor = FT(0);
+            const int slot = n_t * st;
+            for (int i = 0; i < nmin; ++i) {
+                const FT* t = kmn + i * slot;
+                FT v = w11 * __ldg(t + ma) + w21 * __ldg(t + ma + n_gpt) + w12 * __ldg(t + mb) + w22 * __ldg(t + mb + n_gpt);
+                tau_minor += v * r[4 + i];
+            }
+            tau += tau_minor;
+        }
+        if (LW) {
+            const FT* pf = L.pfrac;
+            FT c000 = __ldg(pf + oa), c100 = __ldg(pf + oa + n_gpt), c010 = __ldg(pf + oa + sp), c110 = __ldg(pf + oa + sp + n_gpt);
+            FT c001 = __ldg(pf + ob), c101 = __ldg(pf + ob + n_gpt), c011 = __ldg(pf + ob + sp), c111 = __ldg(pf + ob + sp + n_gpt);
+            pfrac = (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
+                    (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)));
+            tau = rmax(tau, FT(0));
+            ssa = FT(0); g = FT(0);
+        } else {
+            const FT* t = L.rayl + tr * (n_t * st);
+            FT tau_ray = (w11 * __ldg(t + ma) + w21 * __ldg(t + ma + n_gpt) + w12 * __ldg(t + mb) + w22 * __ldg(t + mb + n_gpt)) *
+                         colp[4 * k + 3] * col_dry;
+            tau = rmax(tau + tau_ray, FT(0));
+            ssa = tau > FT(0) ? hdiv(tau_ray, tau) : FT(0);
+            g = FT(0); pfrac = FT(0);
+        }
+        const FT* rc = r + 4 + L.nminor_max;
+        if (P.use_cloud != 0 && mask_bit(k)) {
+            if (NOSCAT) tau += rc[0];
+            else increment_2stream(tau, ssa, g, rc[0], rc[1], rc[2]);
+        }
+        if (P.use_aero != 0 && ((cj >> 17) & 1)) {
+            if (NOSCAT) tau += rc[3];
+            else increment_2stream(tau, ssa, g, rc[3], rc[4], rc[5]);
+        }
+    }
+};
+
+// warp-wide sum, every lane gets the total
+template <typename FT> __device__ __forceinline__ FT warp_sum(FT v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel with the level store in shared memory (any precision, nlev <= 96)
 // ---------------------------------------------------------------------------------------------
 template <typename FT, int MODE>
 __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
@@ -191,46 +515,14 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
     constexpr bool NOSCAT = MODE == MODE_LW_NOSCAT;
     constexpr int NV = MODE == MODE_LW_2STREAM ? 4 : 5;   // level-store values per level
 
-    const GasLut<FT>& L = P.lut;
-    const int nlay = P.nlay, nlev = nlay + 1;
-    const int n_gpt = L.n_gpt, n_eta = L.n_eta, n_t = L.n_t;
-
     unsigned char* wbase = smem_raw + (size_t)warp * P.warp_bytes;
-    int* colj = reinterpret_cast<int*>(wbase + P.off_colj);   // [nlay] jt | jp<<8 | tropo<<16 | aero<<17
-    FT* colp = reinterpret_cast<FT*>(wbase + P.off_colp);     // [nlay][4] ft, fp, col_dry, vmr_h2o+1
-    int* recj = reinterpret_cast<int*>(wbase + P.off_recj);   // [nlay][maxb] je1 | je2<<4 | nminor<<8
-    FT* rec = reinterpret_cast<FT*>(wbase + P.off_rec);       // [nlay][maxb][rec_words]
-    FT* plk = reinterpret_cast<FT*>(wbase + P.off_plk);       // LW: [maxb][2*nlev] B(t_lev), B(t_lay)/B(t_sfc)
+    Warp<FT, MODE> W(P, wbase, lane, col);
+    const GasLut<FT>& L = P.lut;
+    const int nlay = P.nlay, nlev = nlay + 1, n_gpt = L.n_gpt;
     FT* store = reinterpret_cast<FT*>(wbase + P.off_store);   // [nlev][NV][32]
-    const int RW = P.rec_words, maxb = L.maxb;
+    const bool use_cloud = P.use_cloud != 0;
 
-    const FT* ld = P.io.layerdata + (size_t)col * nlay * 4;
-    const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
-
-    // ---------------- phase 0: per-(column, layer) quantities (gas_optics.jl:87-115,188) ----------------
-    for (int k = lane; k < nlay; k += 32) {
-        FT col_dry = __ldg(ld + 4 * k + 0), p_lay = __ldg(ld + 4 * k + 1), t_lay = __ldg(ld + 4 * k + 2);
-        int tropo = p_lay > L.p_ref_tropo ? 1 : 2;
-        FT dT = __ldg(L.t_ref + 1) - __ldg(L.t_ref);
-        int jt = loc_lower_eq(t_lay, dT, n_t, L.t_ref);
-        FT ft = (t_lay - __ldg(L.t_ref + jt - 1)) / dT;
-        FT dlnp = __ldg(L.ln_p_ref) - __ldg(L.ln_p_ref + 1);
-        FT lp = rlog(p_lay);
-        int jpress = (int)((__ldg(L.ln_p_ref) - lp) / dlnp) + 1;
-        jpress = jpress > 1 ? jpress : 1;
-        jpress = (jpress < L.n_p_ref - 1 ? jpress : L.n_p_ref - 1) + 1;
-        FT fp = (__ldg(L.ln_p_ref + jpress - 2) - lp) / dlnp;
-        int jp = jpress + tropo - 1;
-        int aero_on = 0;
-        if (use_aero) {   // aerosol_optics.jl:464-483
-            const FT* am = P.io.aero_mass + ((size_t)col * nlay + k) * 15;
-            for (int i = 0; i < 15; ++i) aero_on |= (__ldg(am + i) > FT(0)) ? 1 : 0;
-        }
-        colj[k] = jt | (jp << 8) | ((tropo - 1) << 16) | (aero_on << 17);
-        colp[4 * k + 0] = ft; colp[4 * k + 1] = fp; colp[4 * k + 2] = col_dry;
-        colp[4 * k + 3] = get_vmr(P, L.idx_h2o, k, col) + FT(1);
-    }
-    __syncwarp();
+    W.phase0();
 
     // McICA column key; cloudy span (cloud_optics.jl:271-275,309-321)
     const uint64_t col_key = mcica_col_key(P.seed, (uint64_t)(P.col_offset + col));
@@ -254,219 +546,30 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
     for (int i = 0; i < kMaxLevPerLane; ++i) acc_up[i] = acc_dn[i] = acc_dir[i] = FT(0);
     int n_cloudy = 0;
 
-    // =====================================================================================
     for (int g0 = 0; g0 < n_gpt; g0 += 32) {
-        const bool lane_on = g0 + lane < n_gpt;
-        const int gpt = lane_on ? g0 + lane : n_gpt - 1;
-        const int b_first = __ldg(L.gpt2bnd + g0);
-        const int b_last = __ldg(L.gpt2bnd + (g0 + 31 < n_gpt ? g0 + 31 : n_gpt - 1));
-        const int nb = b_last - b_first + 1;
-        const int ibnd = __ldg(L.gpt2bnd + gpt);
-        const int bl = ibnd - b_first;
+        W.set_block(g0);
         __syncwarp();
-
-        // ---------------- phase 1: band records ----------------
-        for (int item = lane; item < nb * nlay; item += 32) {
-            const int b = item / nlay, k = item - b * nlay;
-            const int ib = b_first + b;
-            const int cj = colj[k];
-            const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
-            const FT col_dry = colp[4 * k + 2];
-            const FT vmr_h2o = get_vmr(P, L.idx_h2o, k, col);
-            FT* r = rec + ((size_t)k * maxb + b) * RW;
-            // gas_optics.jl:129-170
-            const int ig1 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib));
-            const int ig2 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib) + 1);
-            const FT vmr1 = get_vmr(P, ig1, k, col), vmr2 = get_vmr(P, ig2, k, col);
-            int je[2]; FT fe[2], cm[2];
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const FT* vr = L.vmr_ref + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
-                FT eta_half = __ldg(vr + 2 * ig1) / __ldg(vr + 2 * ig2);
-                FT col_mix = vmr1 + eta_half * vmr2;
-                FT eta = vmr1 * (FT(1) / col_mix);
-                if (col_mix <= FT(0)) eta = FT(0.5);
-                FT loc_eta = eta * FT(n_eta - 1);
-                int j = (int)loc_eta + 1;
-                j = j < n_eta - 1 ? j : n_eta - 1;
-                je[it] = j; fe[it] = loc_eta - FT(j - 1); cm[it] = col_mix;
-            }
-            r[0] = fe[0]; r[1] = fe[1]; r[2] = cm[0]; r[3] = cm[1];
-            // gas_optics.jl:344-412: per-absorber scalings
-            const int* bst = L.minor_bnd_st[tropo - 1];
-            const int m0 = __ldg(bst + ib), nmin = __ldg(bst + ib + 1) - m0;
-            {
-                const FT p_lay = __ldg(ld + 4 * k + 1), t_lay = __ldg(ld + 4 * k + 2);
-                const FT dry_fact = FT(1) / (FT(1) + vmr_h2o);
-                const FT density_fact = FT(0.01) * p_lay / t_lay;
-                for (int i = 0; i < nmin; ++i) {
-                    const int* gd = L.minor_gasdata[tropo - 1] + 4 * (m0 + i);
-                    const int idx_gas = __ldg(gd), idx_sc = __ldg(gd + 1), swd = __ldg(gd + 2), sbc = __ldg(gd + 3);
-                    FT vmr_i = get_vmr(P, idx_gas, k, col);
-                    FT scaling = FT(0);
-                    if (vmr_i > FT(0)) {
-                        scaling = vmr_i * col_dry;
-                        if (swd == 1) {
-                            scaling *= density_fact;
-                            if (idx_sc > 0) {
-                                if (sbc == 1) scaling *= (FT(1) - get_vmr(P, idx_sc, k, col) * dry_fact);
-                                else scaling *= get_vmr(P, idx_sc, k, col) * dry_fact;
-                            }
-                        }
-                    }
-                    r[4 + i] = scaling;
-                }
-            }
-            recj[k * maxb + b] = je[0] | (je[1] << 4) | (nmin << 8);
-            FT* rc = r + 4 + L.nminor_max;   // cloud (3) then aerosol (3)
-            // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
-            if (use_cloud) {
-                FT tc = FT(0), sc = FT(0), gc = FT(0);
-                size_t kk = (size_t)col * nlay + k;
-                if (__ldg(P.io.cld_frac + kk) > FT(0)) {
-                    const CldLut<FT>& C = P.cld;
-                    const FT* liq = C.liqdata + (size_t)3 * C.nsize_liq * ib;
-                    const FT* ice = C.icedata + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
-                    FT tl, tls, tlsg, ti, tis, tisg;
-                    cld_props(C.nsize_liq, C.radliq_lwr, C.radliq_upr, liq, __ldg(P.io.cld_r_eff_liq + kk),
-                              __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
-                    cld_props(C.nsize_ice, C.radice_lwr, C.radice_upr, ice, __ldg(P.io.cld_r_eff_ice + kk),
-                              __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
-                    if (NOSCAT) {
-                        tc = (tl - tls) + (ti - tis);
-                    } else {
-                        tc = tl + ti;
-                        sc = tls + tis;
-                        gc = (tlsg + tisg) / rmax(Num<FT>::eps(), sc);
-                        sc /= rmax(Num<FT>::eps(), tc);
-                        if (!LW) delta_scale(tc, sc, gc);
-                    }
-                }
-                rc[0] = tc; rc[1] = sc; rc[2] = gc;
-            }
-            // aerosol_optics.jl:80-133 (2-stream) / :18-61 (1-scalar)
-            if (use_aero) {
-                FT ta = FT(0), sa = FT(0), ga = FT(0), t_ext = FT(0), t_sca = FT(0);
-                if ((cj >> 17) & 1) {
-                    size_t kk = ((size_t)col * nlay + k) * 15;
-                    FT tsa, tsga;
-                    lookup_aerosol(P.aero, ib, P.io.aero_mass + kk, P.io.aero_size + kk, __ldg(ld + 4 * k + 3), ta, tsa, tsga);
-                    t_ext = ta; t_sca = tsa;
-                    if (NOSCAT) {
-                        ta = ta - tsa;
-                    } else {
-                        ga = tsga / rmax(Num<FT>::eps(), tsa);
-                        sa = tsa / rmax(Num<FT>::eps(), ta);
-                        if (!LW) delta_scale(ta, sa, ga);
-                    }
-                }
-                rc[3] = ta; rc[4] = sa; rc[5] = ga;
-                if (!LW && ib + 1 == P.aero.iband_550nm) { rc[6] = t_ext; rc[7] = t_sca; }
-            }
-            // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
-            if (LW) {
-                const FT* totplnk = L.tot_planck + (size_t)L.n_t_plnk * ib;
-                FT* pb = plk + (size_t)b * 2 * nlev;
-                const FT* tl = P.io.t_lev + (size_t)col * nlev;
-                pb[k + 1] = interp1d_equispaced(__ldg(tl + k + 1), L.t_planck, totplnk, L.n_t_plnk);
-                if (k == 0) {
-                    pb[0] = interp1d_equispaced(__ldg(tl), L.t_planck, totplnk, L.n_t_plnk);
-                    pb[nlev + nlay] = interp1d_equispaced(__ldg(P.io.t_sfc + col), L.t_planck, totplnk, L.n_t_plnk);
-                }
-                if (NOSCAT) pb[nlev + k] = interp1d_equispaced(__ldg(ld + 4 * k + 2), L.t_planck, totplnk, L.n_t_plnk);
-            }
+        FT aod_e, aod_s;
+        W.phase1(aod_e, aod_s);
+        if (!LW && P.use_aero != 0 && P.io.aod_ext != nullptr && P.aero.iband_550nm >= W.b_first + 1 &&
+            P.aero.iband_550nm <= W.b_first + W.nb) {
+            aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
+            if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
         }
-        __syncwarp();
-
-        // AOD diagnostic at 550 nm (aerosol_optics.jl:96-116): sequential layer sum of the band's records
-        if (!LW && use_aero && P.io.aod_ext != nullptr && P.aero.iband_550nm >= b_first + 1 &&
-            P.aero.iband_550nm <= b_last + 1 && lane == 0) {
-            const int b = P.aero.iband_550nm - 1 - b_first;
-            FT e = FT(0), s = FT(0);
-            for (int k = 0; k < nlay; ++k)
-                if ((colj[k] >> 17) & 1) {
-                    const FT* rc = rec + ((size_t)k * maxb + b) * RW + 4 + L.nminor_max;
-                    e += rc[6]; s += rc[7];
-                }
-            P.io.aod_ext[col] = e; P.io.aod_sca[col] = s;
-        }
-
-        // ---------------- McICA mask for this lane's g-point (cloud_optics.jl:264-307) ----------------
-        unsigned mask[kMaxLevPerLane] = {0u, 0u, 0u};
-        if (use_cloud && cld_finish > 0) {
-            const FT* cf = P.io.cld_frac + (size_t)col * nlay;
-            const int swflag = LW ? 0 : 1;
-            FT cf_p1 = __ldg(cf + cld_finish - 1);
-            double r_p1 = mcica_rand(col_key, swflag, gpt + 1, cld_finish);
-            bool m_p1 = r_p1 >= (double)(FT(1) - cf_p1);
-            if (m_p1) mask[(cld_finish - 1) >> 5] |= 1u << ((cld_finish - 1) & 31);
-            for (int ilay = cld_finish - 1; ilay >= cld_start; --ilay) {
-                FT cfk = __ldg(cf + ilay - 1);
-                bool m = false;
-                if (cfk > FT(0)) {
-                    double r = m_p1 ? r_p1 : mcica_rand(col_key, swflag, gpt + 1, ilay) * (double)(FT(1) - cf_p1);
-                    m = r >= (double)(FT(1) - cfk);
-                    r_p1 = r;
-                }
-                if (m) mask[(ilay - 1) >> 5] |= 1u << ((ilay - 1) & 31);
-                cf_p1 = cfk; m_p1 = m;
-            }
-            bool any = lane_on && ((mask[0] | mask[1] | mask[2]) != 0u);
-            n_cloudy += __popc(__ballot_sync(0xffffffffu, any));
-        }
-        auto mask_bit = [&](int k) -> bool {
-            unsigned w = k < 32 ? mask[0] : (k < 64 ? mask[1] : mask[2]);
-            return (w >> (k & 31)) & 1u;
-        };
-
+        n_cloudy += W.mcica(col_key, cld_start, cld_finish);
         if (!day) continue;   // night: masks/AOD only (shortwave_2stream.jl:66-102)
 
-        // ---------------- phase 2 ----------------
-        // gas + cloud + aerosol optics of layer k for this lane's g-point
-        auto optics = [&](int k, FT& tau, FT& ssa, FT& g, FT& pfrac) {
-            const int cj = colj[k];
-            const int jt = cj & 0xff, jp = (cj >> 8) & 0xff, tr = (cj >> 16) & 1;
-            const FT ft = colp[4 * k + 0], fp = colp[4 * k + 1], col_dry = colp[4 * k + 2];
-            const int rj = recj[k * maxb + bl];
-            const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf, nmin = rj >> 8;
-            const FT* r = rec + ((size_t)k * maxb + bl) * RW;
-            const FT fe1 = r[0], fe2 = r[1];
-            FT tau_major = interp3d_g(L.kmajor + gpt, n_t, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft, jp, fp, r[2], r[3]) * col_dry;
-            FT tau_minor = FT(0);
-            const FT* km = L.kminor[tr] + gpt;
-            for (int i = 0; i < nmin; ++i)
-                tau_minor += interp2d_g(km + (size_t)i * n_t * n_eta * n_gpt, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft) * r[4 + i];
-            if (LW) {
-                pfrac = interp3d_g(L.pfrac + gpt, n_t, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft, jp, fp, FT(1), FT(1));
-                tau = rmax(tau_major + tau_minor, FT(0));
-                ssa = FT(0); g = FT(0);
-            } else {
-                FT tau_ray = interp2d_g(L.rayl + (size_t)tr * n_t * n_eta * n_gpt + gpt, n_eta, n_gpt, je1, je2, fe1, fe2, jt, ft) *
-                             colp[4 * k + 3] * col_dry;
-                tau = rmax(tau_major + tau_minor + tau_ray, FT(0));
-                ssa = tau_ray * (FT(1) / tau);
-                if (tau <= FT(0)) ssa = FT(0);
-                g = FT(0); pfrac = FT(0);
-            }
-            const FT* rc = r + 4 + L.nminor_max;
-            if (use_cloud && mask_bit(k)) {
-                if (NOSCAT) tau += rc[0];
-                else increment_2stream(tau, ssa, g, rc[0], rc[1], rc[2]);
-            }
-            if (use_aero && ((cj >> 17) & 1)) {
-                if (NOSCAT) tau += rc[3];
-                else increment_2stream(tau, ssa, g, rc[3], rc[4], rc[5]);
-            }
-        };
-        auto S = [&](int lev, int v) -> FT& { return store[((size_t)lev * NV + v) * 32 + lane]; };
+        const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
+        const bool lane_on = W.lane_on;
+        auto S = [&](int lev, int v) -> FT& { return store[(lev * NV + v) * 32 + lane]; };
 
         if (MODE == MODE_LW_2STREAM) {
             // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding
-            const FT* pb = plk + (size_t)bl * 2 * nlev;
+            const FT* pb = W.plk + bl * 2 * nlev;
             const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
             const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : FT(0);
             FT tau, ssa, g, pf;
-            optics(0, tau, ssa, g, pf);
+            W.optics(0, tau, ssa, g, pf);
             FT lev_bot = pb[0] * pf;
             FT albedo = FT(1) - emis;
             FT src = Num<FT>::pi() * emis * (pb[nlev + nlay] * pf);
@@ -474,14 +577,14 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
                 FT tau_n = FT(0), ssa_n = FT(0), g_n = FT(0), pf_n = FT(0), lev_top;
                 FT inc_k = pb[k + 1] * pf;                       // lev_src_inc of layer k
                 if (k + 1 < nlay) {
-                    optics(k + 1, tau_n, ssa_n, g_n, pf_n);
-                    lev_top = rsqrt_(inc_k * (pb[k + 1] * pf_n));   // sqrt(inc_prev * dec)
+                    W.optics(k + 1, tau_n, ssa_n, g_n, pf_n);
+                    lev_top = hsqrt(inc_k * (pb[k + 1] * pf_n));   // sqrt(inc_prev * dec)
                 } else {
                     lev_top = inc_k;
                 }
                 FT Rdif, Tdif, su, sd;
                 lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
-                FT denom = FT(1) / (FT(1) - Rdif * albedo);
+                FT denom = hdiv(FT(1), FT(1) - Rdif * albedo);
                 // level k (bottom of layer k): what the downward sweep needs
                 S(k, 0) = Tdif * denom;                           // A_k
                 S(k, 1) = (Rdif * src + sd) * denom;              // B_k
@@ -513,20 +616,20 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
             S(nlay, 4) = dir_top;
             for (int k = nlay - 1; k >= 0; --k) {   // direct beam + layer coefficients, top down
                 FT tau, ssa, g, pf;
-                optics(k, tau, ssa, g, pf);
+                W.optics(k, tau, ssa, g, pf);
                 FT Rdir, Tdir, Rdif, Tdif;
-                sw_2stream_coeffs(tau, ssa, g, mu0, Rdir, Tdir, Rdif, Tdif);
+                sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
                 tau_cum += tau;
                 S(k, 0) = Rdif; S(k, 1) = Tdif;
                 S(k, 2) = Rdir * dir_above;           // src_up of layer k
                 S(k, 3) = Tdir * dir_above;           // src_dn of layer k
-                dir_above = dir_top * rexp(-tau_cum * inv_mu0);
+                dir_above = dir_top * hexp(-tau_cum * inv_mu0);
                 S(k, 4) = dir_above;                  // direct flux at level k
             }
             FT albedo = alb_dif, src = dir_above * alb_dir;
             for (int k = 0; k < nlay; ++k) {        // bottom up: albedo / source of everything below
                 FT Rdif = S(k, 0), Tdif = S(k, 1), su = S(k, 2), sd = S(k, 3);
-                FT denom = FT(1) / (FT(1) - Rdif * albedo);
+                FT denom = hdiv(FT(1), FT(1) - Rdif * albedo);
                 S(k, 0) = Tdif * denom;
                 S(k, 1) = (Rdif * src + sd) * denom;
                 S(k, 2) = albedo;
@@ -549,19 +652,19 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
             }
         } else {
             // compute_optical_props.jl:43-82 sources + longwave_noscat.jl:224-301 per angle
-            const FT* pb = plk + (size_t)bl * 2 * nlev;
+            const FT* pb = W.plk + bl * 2 * nlev;
             const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
             const bool has_inc = P.io.inc_flux_lw != nullptr;
             const FT inc = has_inc ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : FT(0);
             FT sfc_source = FT(0), inc_prev = FT(0);
             for (int k = 0; k < nlay; ++k) {
                 FT tau, ssa, g, pf;
-                optics(k, tau, ssa, g, pf);
+                W.optics(k, tau, ssa, g, pf);
                 S(k, 0) = tau;
                 S(k, 1) = pb[nlev + k] * pf;              // lay_source
                 FT src_inc = pb[k + 1] * pf, src_dec = pb[k] * pf;
                 if (k == 0) { sfc_source = pb[nlev + nlay] * pf; S(0, 2) = src_dec; }
-                else S(k, 2) = rsqrt_(inc_prev * src_dec);
+                else S(k, 2) = hsqrt(inc_prev * src_dec);
                 inc_prev = src_inc;
                 S(k, 3) = FT(0); S(k, 4) = FT(0);
             }
@@ -572,7 +675,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
                 S(nlay, 4) += I * i2f;
                 for (int k = nlay - 1; k >= 0; --k) {
                     FT tau_loc = S(k, 0) * Ds;
-                    FT trans = rexp(-tau_loc);
+                    FT trans = hexp(-tau_loc);
                     I = trans * I + lw_noscat_source(S(k, 2), S(k, 1), tau_loc, trans);
                     S(k, 4) += I * i2f;
                 }
@@ -580,7 +683,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
                 S(0, 3) += I * i2f;
                 for (int k = 1; k <= nlay; ++k) {
                     FT tau_loc = S(k - 1, 0) * Ds;
-                    FT trans = rexp(-tau_loc);
+                    FT trans = hexp(-tau_loc);
                     I = trans * I + lw_noscat_source(S(k, 2), S(k - 1, 1), tau_loc, trans);
                     S(k, 3) += I * i2f;
                 }
@@ -597,24 +700,24 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
             for (int i = 0; i < kMaxLevPerLane; ++i) {
                 const int lev = lane + 32 * i;
                 if (lev < nlev) {
-                    const FT* su = store + ((size_t)lev * NV + VU) * 32;
-                    const FT* sd = store + ((size_t)lev * NV + VD) * 32;
+                    const FT* su = store + (lev * NV + VU) * 32;
+                    const FT* sd = store + (lev * NV + VD) * 32;
                     FT u = FT(0), d = FT(0), dr = FT(0);
 #pragma unroll 8
                     for (int j = 0; j < 32; ++j) {
                         const int l2 = (lane + j) & 31;
                         u += su[l2]; d += sd[l2];
-                        if (MODE == MODE_SW_2STREAM) dr += store[((size_t)lev * NV + 4) * 32 + l2];
+                        if (MODE == MODE_SW_2STREAM) dr += store[(lev * NV + 4) * 32 + l2];
                     }
                     acc_up[i] += u; acc_dn[i] += d; acc_dir[i] += dr;
                     if (P.io.band_up != nullptr) {   // Fluxes.jl:199-215, bands of this block
-                        for (int b = 0; b < nb; ++b) {
+                        for (int b = 0; b < W.nb; ++b) {
                             FT bu = FT(0), bd = FT(0);
                             for (int j = 0; j < 32; ++j) {
                                 const int l2 = (lane + j) & 31;
-                                if (g0 + l2 < n_gpt && __ldg(L.gpt2bnd + g0 + l2) == b_first + b) { bu += su[l2]; bd += sd[l2]; }
+                                if (g0 + l2 < n_gpt && __ldg(L.gpt2bnd + g0 + l2) == W.b_first + b) { bu += su[l2]; bd += sd[l2]; }
                             }
-                            size_t o = ((size_t)(b_first + b) * P.ncol + col) * nlev + lev;
+                            size_t o = ((size_t)(W.b_first + b) * P.ncol + col) * nlev + lev;
                             P.io.band_up[o] += bu; P.io.band_dn[o] += bd;
                         }
                     }
