@@ -157,7 +157,7 @@ __device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, c
 // ---------------------------------------------------------------------------------------------
 // Per-warp context shared by the kernels below
 // ---------------------------------------------------------------------------------------------
-template <typename FT, int MODE>
+template <typename FT, int MODE, int NOWN>
 struct Warp {
     static constexpr bool LW = MODE != MODE_SW_2STREAM;
     static constexpr bool NOSCAT = MODE == MODE_LW_NOSCAT;
@@ -175,18 +175,18 @@ struct Warp {
     FT* plk;     // LW: [maxb][2*nlev] B(t_lev) | B(t_lay) (noscat) | B(t_sfc)
     const int RW, maxb;
     // per-lane registers for the layers this lane owns in phase 0/1: lane, lane+32, lane+64
-    FT own_h2o[kMaxLevPerLane], own_dens[kMaxLevPerLane];
-    AeroLayer own_aero[kMaxLevPerLane];
-    FT own_rh_f[kMaxLevPerLane];
-    int own_cld[kMaxLevPerLane];          // loc_liq | loc_ice << 8 | cloudy << 16
-    FT own_cld_fl[kMaxLevPerLane], own_cld_fi[kMaxLevPerLane];
-    int own_pl_loc[kMaxLevPerLane], own_py_loc[kMaxLevPerLane];   // Planck positions: t_lev[k+1], t_lay[k]
-    FT own_pl_f[kMaxLevPerLane], own_py_f[kMaxLevPerLane];
+    FT own_h2o[NOWN], own_dens[NOWN];
+    AeroLayer own_aero[NOWN];
+    FT own_rh_f[NOWN];
+    int own_cld[NOWN];          // loc_liq | loc_ice << 8 | cloudy << 16
+    FT own_cld_fl[NOWN], own_cld_fi[NOWN];
+    int own_pl_loc[NOWN], own_py_loc[NOWN];   // Planck positions: t_lev[k+1], t_lay[k]
+    FT own_pl_f[NOWN], own_py_f[NOWN];
     int p0_loc, psfc_loc; FT p0_f, psfc_f;                        // t_lev[0], t_sfc (lane 0)
     // current g-point block
     int gpt, ibnd, bl, b_first, nb;
     bool lane_on;
-    unsigned mask[kMaxLevPerLane];
+    unsigned mask[NOWN];
 
     __device__ __forceinline__ Warp(const SolveParams<FT>& P_, unsigned char* wbase, int lane_, long long col_)
         : P(P_), L(P_.lut), lane(lane_), col(col_), nlay(P_.nlay), nlev(P_.nlay + 1),
@@ -200,7 +200,7 @@ struct Warp {
         const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
         const int n_t = L.n_t;
 #pragma unroll
-        for (int j = 0; j < kMaxLevPerLane; ++j) {
+        for (int j = 0; j < NOWN; ++j) {
             const int k = lane + 32 * j;
             own_h2o[j] = FT(0); own_dens[j] = FT(0); own_aero[j] = AeroLayer{0u, 0u, 1}; own_rh_f[j] = FT(0);
             own_cld[j] = 0; own_cld_fl[j] = own_cld_fi[j] = FT(0);
@@ -285,7 +285,7 @@ struct Warp {
         const int n_eta = L.n_eta;
         aod_e = aod_s = FT(0);
 #pragma unroll
-        for (int j = 0; j < kMaxLevPerLane; ++j) {
+        for (int j = 0; j < NOWN; ++j) {
             const int k = lane + 32 * j;
             if (k >= nlay) continue;
             const int cj = colj[k];
@@ -395,7 +395,7 @@ struct Warp {
     // returns the number of this block's g-points with any cloudy layer
     __device__ __forceinline__ int mcica(uint64_t col_key, int cld_start, int cld_finish) {
 #pragma unroll
-        for (int i = 0; i < kMaxLevPerLane; ++i) mask[i] = 0u;
+        for (int i = 0; i < NOWN; ++i) mask[i] = 0u;
         if (!(P.use_cloud != 0) || cld_finish <= 0) return 0;
         const FT* cf = P.io.cld_frac + (size_t)col * nlay;
         const int swflag = LW ? 0 : 1;
@@ -414,15 +414,18 @@ struct Warp {
             set_mask(ilay - 1, m);
             cf_p1 = cfk; m_p1 = m;
         }
-        bool any = lane_on && ((mask[0] | mask[1] | mask[2]) != 0u);
+        unsigned anyw = 0u;
+#pragma unroll
+        for (int i = 0; i < NOWN; ++i) anyw |= mask[i];
+        bool any = lane_on && anyw != 0u;
         return __popc(__ballot_sync(0xffffffffu, any));
     }
     __device__ __forceinline__ void set_mask(int k, bool m) {
         const unsigned bit = m ? (1u << (k & 31)) : 0u;
-        if (k < 32) mask[0] |= bit; else if (k < 64) mask[1] |= bit; else mask[2] |= bit;
+        if (k < 32) mask[0] |= bit; else if (NOWN < 3 || k < 64) mask[NOWN > 1 ? 1 : 0] |= bit; else mask[NOWN - 1] |= bit;
     }
     __device__ __forceinline__ bool mask_bit(int k) const {
-        unsigned w = k < 32 ? mask[0] : (k < 64 ? mask[1] : mask[2]);
+        unsigned w = k < 32 ? mask[0] : ((NOWN < 3 || k < 64) ? mask[NOWN > 1 ? 1 : 0] : mask[NOWN - 1]);
         return (w >> (k & 31)) & 1u;
     }
 
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
     constexpr int NV = MODE == MODE_LW_2STREAM ? 4 : 5;   // level-store values per level
 
     unsigned char* wbase = smem_raw + (size_t)warp * P.warp_bytes;
-    Warp<FT, MODE> W(P, wbase, lane, col);
+    Warp<FT, MODE, kMaxLevPerLane> W(P, wbase, lane, col);
     const GasLut<FT>& L = P.lut;
     const int nlay = P.nlay, nlev = nlay + 1, n_gpt = L.n_gpt;
     FT* store = reinterpret_cast<FT*>(wbase + P.off_store);   // [nlev][NV][32]
