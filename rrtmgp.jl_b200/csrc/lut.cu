@@ -142,7 +142,15 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
     L.nminor_max = nmax;
     for (int tr = 0; tr < 2; ++tr) {
         std::vector<double> kmin = getd(p, pre + tags[tr] + "/kminor");
-        std::vector<FT> dst((size_t)std::max(nmax, 1) * n_t * n_eta * n_gpt, FT(0));
+        std::vector<FT> dst((size_t)(std::max(nmax, 1) + (sw ? 1 : 0)) * n_t * n_eta * n_gpt, FT(0));
+        if (sw) {   // Rayleigh as the slot after the minors (fast kernels gather it with the same two address registers)
+            std::vector<double> ray = getd(p, pre + (tr == 0 ? "/rayl_lower" : "/rayl_upper"));
+            for (int g = 0; g < n_gpt; ++g)
+                for (int t = 0; t < n_t; ++t)
+                    for (int e = 0; e < n_eta; ++e)
+                        dst[(((size_t)std::max(nmax, 1) * n_t + t) * n_eta + e) * n_gpt + g] =
+                            (FT)ray[e + (size_t)n_eta * (t + (size_t)n_t * g)];
+        }
         for (int g = 0; g < n_gpt; ++g) {
             int n = gst[tr][g + 1] - gst[tr][g];
             int b = g2b[g];
@@ -164,7 +172,21 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
 
     L.pfrac = nullptr; L.t_planck = nullptr; L.tot_planck = nullptr; L.rayl = nullptr; L.solar_src_scaled = nullptr;
     L.n_t_plnk = 0;
+    L.kmaj_pf = nullptr;
     if (!sw) {
+        {
+            std::vector<double> km = getd(p, pre + "/kmajor"), pfr = getd(p, pre + "/planck_fraction");
+            std::vector<FT> dst(km.size() * 2);
+            for (int g = 0; g < n_gpt; ++g)
+                for (int t = 0; t < n_t; ++t)
+                    for (int pp = 0; pp < n_p; ++pp)
+                        for (int e = 0; e < n_eta; ++e) {
+                            size_t src = e + (size_t)n_eta * (pp + (size_t)n_p * (t + (size_t)n_t * g));
+                            size_t d0 = ((((size_t)pp * n_t + t) * n_eta + e) * 2) * n_gpt + g;
+                            dst[d0] = (FT)km[src]; dst[d0 + n_gpt] = (FT)pfr[src];
+                        }
+            A.add(dst, L.kmaj_pf);
+        }
         A.add(relayout4(pre + "/planck_fraction"), L.pfrac);
         std::vector<FT> tp = cast<FT>(getd(p, pre + "/t_planck"));
         L.n_t_plnk = (int)tp.size();

@@ -1,5 +1,5 @@
 // Host-side launch of the fused column kernels (solver.cuh).
-#include "solver_tmem.cuh"
+#include "solver_fast.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -39,9 +39,9 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
     return (int)cudaGetLastError();
 }
 
-// Shared-memory plan of the TMEM kernels: the level store shrinks to the albedo array (or nothing).
-static int plan_smem_tmem(SolveParams<float>& P, bool alpha_tmem) {
-    const int nlay = P.nlay, nlev = nlay + 1, maxb = P.lut.maxb;
+// Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
+static int plan_smem_fast(SolveParams<float>& P, FastSmem& F) {
+    const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
     P.rec_words = 4 + P.lut.nminor_max + 6;
     int off = 0;
     P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
@@ -49,48 +49,69 @@ static int plan_smem_tmem(SolveParams<float>& P, bool alpha_tmem) {
     P.off_recj = off; off = align_up(off + nlay * maxb * (int)sizeof(int), 16);
     P.off_rec = off;  off = align_up(off + nlay * maxb * P.rec_words * (int)sizeof(float), 16);
     P.off_plk = off;  off = align_up(off + maxb * 2 * nlev * (int)sizeof(float), 16);
-    P.off_store = off; off = align_up(off + (alpha_tmem ? 0 : nlay * 32 * (int)sizeof(float)), 128);
+    P.off_store = off;
+    const int n_hi = nlay > kAlphaTmemLevels ? nlay - kAlphaTmemLevels : 0;
+    F.off_alpha = off; off = align_up(off + n_hi * 32 * (int)sizeof(float), 128);
+    F.off_stage = off; off = align_up(off + 32 * 32 * (int)sizeof(float), 16);
+    F.off_acc = off;   off = align_up(off + 3 * kAccStride * (int)sizeof(float), 128);
     P.warp_bytes = off;
     return off;
 }
 
-template <int MODE, bool ALPHA_TMEM>
-static int launch_tmem(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
-    const int wb = plan_smem_tmem(P, ALPHA_TMEM);
-    size_t smem = (size_t)kTmemWarpsPerCta * wb;
-    // residency must match the TMEM budget (512 columns / SM): 2 CTAs x 256 or <= 4 CTAs x 128
-    if (ALPHA_TMEM && smem < 80 * 1024) smem = 80 * 1024;
-    if ((int)smem > max_smem_optin) return (int)cudaErrorInvalidConfiguration;
-    auto kern = solve_kernel_tmem<MODE, ALPHA_TMEM>;
+static int sm_count_of_current_device() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cached[dev] > 0 ? cached[dev] : 148;
+}
+
+template <int MODE, int NGPT, bool HAS_CLD, bool HAS_AER>
+static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
+    FastSmem F;
+    const int wb = plan_smem_fast(P, F);
+    const size_t smem = (size_t)kFastWarps * wb;
+    if ((int)smem > max_smem_optin) return -1;   // does not fit: generic kernel
+    auto kern = solve_kernel_fast<MODE, NGPT, HAS_CLD, HAS_AER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int grid = (P.ncol + kTmemWarpsPerCta - 1) / kTmemWarpsPerCta;
-    kern<<<grid, kTmemWarpsPerCta * 32, smem, stream>>>(P);
+    const int need = (P.ncol + kFastWarps - 1) / kFastWarps;
+    const int sms = sm_count_of_current_device();
+    const int grid = need < sms ? need : sms;   // persistent: one CTA per SM
+    kern<<<grid, kFastWarps * 32, smem, stream>>>(P, F);
     return (int)cudaGetLastError();
 }
 
-// RRTMGP_B200_KERNEL = smem | tmem2 | tmem3 overrides the level-store placement (experiments);
-// default: TMEM (A, B) + shared-memory albedo whenever the configuration allows it.
-static int kernel_choice() {
-    const char* e = std::getenv("RRTMGP_B200_KERNEL");
-    if (!e) return 2;
-    if (!std::strcmp(e, "smem")) return 0;
-    if (!std::strcmp(e, "tmem3")) return 3;
-    return 2;
+template <int MODE, int NGPT>
+static int launch_fast_flags(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
+    const bool c = P.use_cloud != 0, a = P.use_aero != 0;
+    if (c && a) return launch_fast_t<MODE, NGPT, true, true>(P, max_smem_optin, s);
+    if (c) return launch_fast_t<MODE, NGPT, true, false>(P, max_smem_optin, s);
+    if (a) return launch_fast_t<MODE, NGPT, false, true>(P, max_smem_optin, s);
+    return launch_fast_t<MODE, NGPT, false, false>(P, max_smem_optin, s);
 }
 
-template <typename FT> static int try_tmem(int, SolveParams<FT>&, int, cudaStream_t) { return -1; }
-template <> int try_tmem<float>(int mode, SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
-    const int choice = kernel_choice();
-    if (choice == 0 || P.nlay > 64 || mode == MODE_LW_NOSCAT || P.io.band_up != nullptr) return -1;
-    if (mode == MODE_LW_2STREAM)
-        return choice == 3 ? launch_tmem<MODE_LW_2STREAM, true>(P, max_smem_optin, s) : launch_tmem<MODE_LW_2STREAM, false>(P, max_smem_optin, s);
-    return choice == 3 ? launch_tmem<MODE_SW_2STREAM, true>(P, max_smem_optin, s) : launch_tmem<MODE_SW_2STREAM, false>(P, max_smem_optin, s);
+// RRTMGP_B200_KERNEL=generic forces the shared-memory kernels of solver.cuh (experiments / A-B tests).
+static bool fast_enabled() {
+    const char* e = std::getenv("RRTMGP_B200_KERNEL");
+    return !(e && !std::strcmp(e, "generic"));
+}
+
+// Fast path: Float32, two-stream, nlay <= 64, real-table shape. Returns -1 when not applicable.
+template <typename FT> static int try_fast(int, SolveParams<FT>&, int, cudaStream_t) { return -1; }
+template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
+    const GasLut<float>& L = P.lut;
+    if (!fast_enabled() || P.nlay > 64 || P.nlay < 2 || mode == MODE_LW_NOSCAT || P.io.band_up != nullptr) return -1;
+    if (L.n_eta != 9 || L.n_t != 14 || L.maxb != 2 || L.nminor_max > kFastMaxMinor || (L.n_gpt % 32) != 0) return -1;
+    if (mode == MODE_LW_2STREAM && L.n_gpt == 256 && L.kmaj_pf != nullptr) return launch_fast_flags<MODE_LW_2STREAM, 256>(P, max_smem_optin, s);
+    if (mode == MODE_SW_2STREAM && L.n_gpt == 224) return launch_fast_flags<MODE_SW_2STREAM, 224>(P, max_smem_optin, s);
+    return -1;
 }
 
 template <typename FT> int launch_solve(int mode, SolveParams<FT>& P, int max_smem_optin, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    int t = try_tmem<FT>(mode, P, max_smem_optin, s);
+    int t = try_fast<FT>(mode, P, max_smem_optin, s);
     if (t >= 0) return t;
     switch (mode) {
         case MODE_LW_2STREAM: return launch_mode<FT, MODE_LW_2STREAM>(P, max_smem_optin, s);

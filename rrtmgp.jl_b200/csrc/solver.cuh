@@ -157,7 +157,7 @@ __device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, c
 // ---------------------------------------------------------------------------------------------
 // Per-warp context shared by the kernels below
 // ---------------------------------------------------------------------------------------------
-template <typename FT, int MODE, int NOWN>
+template <typename FT, int MODE, int NOWN, bool FUSED = false>
 struct Warp {
     static constexpr bool LW = MODE != MODE_SW_2STREAM;
     static constexpr bool NOSCAT = MODE == MODE_LW_NOSCAT;
@@ -332,11 +332,10 @@ struct Warp {
                     }
                     r[4 + i] = scaling;
                 }
-                recj[k * maxb + b] = je[0] | (je[1] << 4) | (nmin << 8);
-                FT* rc = r + 4 + L.nminor_max;   // cloud (3) then aerosol (3)
+                FT* rc = r + 4 + L.nminor_max;   // cloud (3) then aerosol (3)  [FUSED: aerosol-only / cloud+aerosol products]
+                FT tc = FT(0), sc = FT(0), gc = FT(0);
                 // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
                 if (use_cloud) {
-                    FT tc = FT(0), sc = FT(0), gc = FT(0);
                     if ((own_cld[j] >> 16) & 1) {
                         const CldLut<FT>& C = P.cld;
                         size_t kk = (size_t)col * nlay + k;
@@ -355,11 +354,10 @@ struct Warp {
                             if (!LW) delta_scale(tc, sc, gc);
                         }
                     }
-                    rc[0] = tc; rc[1] = sc; rc[2] = gc;
                 }
                 // aerosol_optics.jl:80-133 (2-stream) / :18-61 (1-scalar)
+                FT ta = FT(0), sa = FT(0), ga = FT(0);
                 if (use_aero) {
-                    FT ta = FT(0), sa = FT(0), ga = FT(0);
                     if ((cj >> 17) & 1) {
                         size_t kk = ((size_t)col * nlay + k) * 15;
                         FT tsa, tsga;
@@ -373,8 +371,18 @@ struct Warp {
                             if (!LW) delta_scale(ta, sa, ga);
                         }
                     }
-                    rc[3] = ta; rc[4] = sa; rc[5] = ga;
                 }
+                if (FUSED) {
+                    // increment_2stream (optics_utils.jl:189-202) is additive in (tau, tau ssa, tau ssa g):
+                    // store those products for "aerosol only" and "cloud + aerosol"; one increment per lane
+                    const FT a0 = ta, a1 = ta * sa, a2 = ta * sa * ga;
+                    rc[0] = a0; rc[1] = a1; rc[2] = a2;
+                    rc[3] = a0 + tc; rc[4] = a1 + tc * sc; rc[5] = a2 + tc * sc * gc;
+                } else {
+                    if (use_cloud) { rc[0] = tc; rc[1] = sc; rc[2] = gc; }
+                    if (use_aero) { rc[3] = ta; rc[4] = sa; rc[5] = ga; }
+                }
+                recj[k * maxb + b] = je[0] | (je[1] << 4) | (nmin << 8);
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {
                     const FT* totplnk = L.tot_planck + (size_t)L.n_t_plnk * ib;

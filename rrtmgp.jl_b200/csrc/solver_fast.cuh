@@ -1,0 +1,370 @@
+// Blackwell-native fast path of the two-stream kernels: Float32, nlay <= 64, real-table shape
+// (n_eta = 9, n_T = 14, 16-g-point bands, n_gpt a template constant).
+//
+//  * PERSISTENT: one CTA of 12 warps per SM; every warp walks its own sequence of columns
+//    (warp = column, lane = g-point, as in solver.cuh).
+//  * TENSOR MEMORY as the level store.  The adding method needs, for every level, three values
+//    per (column, g-point) from the first sweep when the second sweep passes the same level:
+//    768 B per lane, 24.6 KB per warp.  In shared memory that caps residency at 4-6 warps per
+//    SM and the kernel is latency bound (profiles/r1a_*).  B200's 256 KB of TMEM per SM are
+//    otherwise idle here (no MMA on this path) and tcgen05.ld/st give every thread a private
+//    column array in its own TMEM lane -- exactly the access pattern of this store.  The CTA
+//    allocates all 512 columns; the three warps that share a lane quadrant get 170 columns
+//    each: (A, B) of 64 levels + the albedo of the lowest 42 levels; the other 22 albedos sit
+//    in shared memory.
+//  * COMPILE-TIME TABLE STRIDES: the 16 (LW: kmajor + Planck fraction, interleaved) + 4 n_minor
+//    (+ 4 Rayleigh) gathers of a cell use four address registers and immediate offsets.
+//  * G-POINT REDUCTION through a 4 KB shared staging tile read transposed (lane = level),
+//    ~2 instructions per (level, quantity) instead of a 10-instruction shuffle tree.
+//  * SW adding marched from the TOP (reflectance/source of everything ABOVE a level),
+//    algebraically identical to shortwave_2stream.jl:300-392, so the direct beam, the layer
+//    coefficients and the first recurrence share one sweep; see DESIGN.md.
+#pragma once
+#include "solver.cuh"
+
+namespace rb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(a)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
+    uint32_t x, y;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(taddr) : "memory");
+    a = __uint_as_float(x); b = __uint_as_float(y);
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& a) {
+    uint32_t x;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(taddr) : "memory");
+    a = __uint_as_float(x);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int kFastWarps = 12;        // warps per CTA = per SM
+constexpr int kFastColsPerWarp = 170; // TMEM columns per warp (3 warps share the 512 columns of a lane quadrant)
+constexpr int kAlphaTmemLevels = kFastColsPerWarp - 128;   // 42 albedos in TMEM, the rest in shared memory
+constexpr int kAccStride = 68;        // per-quantity stride of the shared broadband accumulators
+constexpr int kFastMaxMinor = 8;
+
+struct FastSmem {   // byte offsets from the warp's base, extending SolveParams' layout
+    int off_alpha, off_stage, off_acc;
+};
+
+template <int MODE, int NGPT, bool HAS_CLD, bool HAS_AER>
+__global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const SolveParams<float> P, const FastSmem F) {
+    using FT = float;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_smem;
+    constexpr bool LW = MODE == MODE_LW_2STREAM;
+    constexpr int NETA = 9, NT = 14;
+    constexpr int NW = LW ? 2 : 1;                                   // kmajor (+ Planck fraction) interleave
+    constexpr int KE = NW * NGPT, KT = NETA * KE, KP = NT * KT;      // major-table strides: eta, T, p
+    constexpr int ME = NGPT, MT = NETA * NGPT, MS = NT * MT;         // minor-table strides: eta, T, slot
+    constexpr int UP = 0, DN = 1, DIR = 2;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (warp == 0) tmem_alloc(&tmem_base_smem, 512u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // lane field (bits 31:16) = 32 * (warp % 4); column = 170 * (warp / 4)
+    const uint32_t tA = tmem_base_smem + ((uint32_t)(warp & 3) << 21) + (uint32_t)((warp >> 2) * kFastColsPerWarp);
+    const uint32_t tAl = tA + 128u;
+
+    unsigned char* wbase = smem_raw + (size_t)warp * P.warp_bytes;
+    FT* alpha_hi = reinterpret_cast<FT*>(wbase + F.off_alpha);   // [nlay - 42][32]
+    FT* stage = reinterpret_cast<FT*>(wbase + F.off_stage);      // [32][32]
+    FT* accs = reinterpret_cast<FT*>(wbase + F.off_acc);         // [3][kAccStride]
+    const GasLut<FT>& L = P.lut;
+    const int nlay = P.nlay, nlev = nlay + 1;
+    const FT* major = LW ? L.kmaj_pf : L.kmajor;
+    const int RW = P.rec_words;
+    const int rayl_slot = L.nminor_max > 0 ? L.nminor_max : 1;
+
+    for (long long col = (long long)blockIdx.x * kFastWarps + warp; col < P.ncol; col += (long long)gridDim.x * kFastWarps) {
+        Warp<FT, MODE, 2, true> W(P, wbase, lane, col);
+        W.phase0();
+        for (int i = lane; i < 3 * kAccStride; i += 32) accs[i] = FT(0);
+
+        const uint64_t col_key = mcica_col_key(P.seed, (uint64_t)(P.col_offset + col));
+        int cld_start = 0, cld_finish = 0;
+        if (HAS_CLD) {
+            const FT* cf = P.io.cld_frac + (size_t)col * nlay;
+            unsigned lo = 0xffffffffu, hi = 0;
+            for (int k = lane; k < nlay; k += 32)
+                if (__ldg(cf + k) > FT(0)) { lo = lo < (unsigned)(k + 1) ? lo : (unsigned)(k + 1); hi = hi > (unsigned)(k + 1) ? hi : (unsigned)(k + 1); }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (hi > 0) { cld_start = (int)lo; cld_finish = (int)hi; }
+        }
+        const FT mu0 = LW ? FT(1) : __ldg(P.io.cos_zenith + col);
+        const bool day = LW || mu0 > FT(0);
+        const FT toa = LW ? FT(0) : __ldg(P.io.toa_flux + col);
+        int n_cloudy = 0;
+        __syncwarp();
+
+        for (int g0 = 0; g0 < NGPT; g0 += 32) {
+            W.set_block(g0);
+            __syncwarp();
+            FT aod_e, aod_s;
+            W.phase1(aod_e, aod_s);
+            if (!LW && HAS_AER && P.io.aod_ext != nullptr && P.aero.iband_550nm >= W.b_first + 1 &&
+                P.aero.iband_550nm <= W.b_first + W.nb) {
+                aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
+                if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
+            }
+            if (HAS_CLD) n_cloudy += W.mcica(col_key, cld_start, cld_finish);
+            if (!day) continue;
+
+            const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
+            const FT on = W.lane_on ? 1.f : 0.f;
+
+            // ---- gas + cloud + aerosol optics of layer k, compile-time strides ----
+            auto optics = [&](int k, FT& tau, FT& ssa, FT& g, FT& pfrac) {
+                const int cj = W.colj[k];
+                const int jt = cj & 0xff, jp = (cj >> 8) & 0xff, tr = (cj >> 16) & 1;
+                const float4 cp = reinterpret_cast<const float4*>(W.colp)[k];   // ft, fp, col_dry, vmr_h2o + 1
+                const FT ft = cp.x, fp = cp.y, col_dry = cp.z;
+                const int rj = W.recj[k * 2 + bl];
+                const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf, nmin = rj >> 8;
+                const FT* r = W.rec + (k * 2 + bl) * RW;
+                const FT fe1 = r[0], fe2 = r[1];
+                const FT omfe1 = 1.f - fe1, omfe2 = 1.f - fe2, omft = 1.f - ft, omfp = 1.f - fp;
+                const FT* pa = major + ((jp - 2) * KP + (jt - 1) * KT + (je1 - 1) * KE + gpt);   // (jp-1, jt,   je1)
+                const FT* pb = major + ((jp - 2) * KP + jt * KT + (je2 - 1) * KE + gpt);         // (jp-1, jt+1, je2)
+                {
+                    FT c000 = __ldg(pa), c100 = __ldg(pa + KE), c010 = __ldg(pa + KP), c110 = __ldg(pa + KP + KE);
+                    FT c001 = __ldg(pb), c101 = __ldg(pb + KE), c011 = __ldg(pb + KP), c111 = __ldg(pb + KP + KE);
+                    tau = (r[2] * (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
+                           r[3] * (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)))) * col_dry;
+                }
+                const FT w11 = omfe1 * omft, w21 = fe1 * omft, w12 = omfe2 * ft, w22 = fe2 * ft;
+                const FT* ma = L.kminor[tr] + ((jt - 1) * MT + (je1 - 1) * ME + gpt);
+                const FT* mb = L.kminor[tr] + (jt * MT + (je2 - 1) * ME + gpt);
+                {
+                    FT tau_minor = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kFastMaxMinor; ++i) {
+                        if (i >= nmin) break;
+                        FT v = w11 * __ldg(ma + i * MS) + w21 * __ldg(ma + i * MS + ME) + w12 * __ldg(mb + i * MS) + w22 * __ldg(mb + i * MS + ME);
+                        tau_minor += v * r[4 + i];
+                    }
+                    tau += tau_minor;
+                }
+                if (LW) {
+                    FT c000 = __ldg(pa + NGPT), c100 = __ldg(pa + KE + NGPT), c010 = __ldg(pa + KP + NGPT), c110 = __ldg(pa + KP + KE + NGPT);
+                    FT c001 = __ldg(pb + NGPT), c101 = __ldg(pb + KE + NGPT), c011 = __ldg(pb + KP + NGPT), c111 = __ldg(pb + KP + KE + NGPT);
+                    pfrac = (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
+                            (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)));
+                    tau = rmax(tau, 0.f);
+                    ssa = 0.f; g = 0.f;
+                } else {
+                    const FT* ra = ma + rayl_slot * MS;
+                    const FT* rb = mb + rayl_slot * MS;
+                    FT tau_ray = (w11 * __ldg(ra) + w21 * __ldg(ra + ME) + w12 * __ldg(rb) + w22 * __ldg(rb + ME)) * cp.w * col_dry;
+                    tau = rmax(tau + tau_ray, 0.f);
+                    ssa = tau > 0.f ? hdiv(tau_ray, tau) : 0.f;
+                    g = 0.f; pfrac = 0.f;
+                }
+                // one fused increment (optics_utils.jl:189-202 is additive in tau, tau ssa, tau ssa g)
+                const bool cb = HAS_CLD && W.mask_bit(k);
+                const bool ab = HAS_AER && ((cj >> 17) & 1);
+                if (cb || ab) {
+                    const FT* x = r + 4 + L.nminor_max + (cb ? 3 : 0);
+                    const FT tn = tau + x[0];
+                    const FT w = tau * ssa + x[1];
+                    const FT h = tau * ssa * g + x[2];
+                    g = hdiv(h, rmax(FLT_EPSILON, w));
+                    ssa = hdiv(w, rmax(FLT_EPSILON, tn));
+                    tau = tn;
+                }
+            };
+            auto st_alpha = [&](int k, FT v) {
+                if (k < kAlphaTmemLevels) tmem_st1(tAl + k, v); else alpha_hi[(k - kAlphaTmemLevels) * 32 + lane] = v;
+            };
+            auto ld_alpha = [&](int k, FT& v) {
+                if (k < kAlphaTmemLevels) tmem_ld1(tAl + k, v); else v = alpha_hi[(k - kAlphaTmemLevels) * 32 + lane];
+            };
+            // transposed row sum of the staging tile: lane <-> row
+            auto row_sum = [&]() -> FT {
+                FT s = 0.f;
+                const FT* row = stage + lane * 32;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) s += row[(lane + j) & 31];
+                return s;
+            };
+
+            if (LW) {
+                // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom)
+                const FT* pbk = W.plk + bl * 2 * nlev;
+                const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
+                const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : 0.f;
+                FT tau, ssa, g, pf;
+                optics(0, tau, ssa, g, pf);
+                FT lev_bot = pbk[0] * pf;
+                FT albedo = 1.f - emis;
+                FT src = Num<FT>::pi() * emis * (pbk[nlev + nlay] * pf);
+                for (int k = 0; k < nlay; ++k) {
+                    FT tau_n = 0.f, ssa_n = 0.f, g_n = 0.f, pf_n = 0.f, lev_top;
+                    FT inc_k = pbk[k + 1] * pf;
+                    if (k + 1 < nlay) {
+                        optics(k + 1, tau_n, ssa_n, g_n, pf_n);
+                        lev_top = hsqrt(inc_k * (pbk[k + 1] * pf_n));
+                    } else {
+                        lev_top = inc_k;
+                    }
+                    FT Rdif, Tdif, su, sd;
+                    lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
+                    FT denom = hdiv(1.f, 1.f - Rdif * albedo);
+                    // level k: F_dn(k) = A_k F_dn(k+1) + B_k ; F_up(k) = albedo_k F_dn(k) + src_k
+                    tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * src + sd) * denom);
+                    st_alpha(k, albedo);
+                    stage[(k & 31) * 32 + lane] = src * on;
+                    if ((k & 31) == 31 || k == nlay - 1) {       // sum_g src_k for up to 32 levels
+                        __syncwarp();
+                        const int kb = k & ~31;
+                        FT s = row_sum();
+                        if (kb + lane <= k) accs[UP * kAccStride + kb + lane] += s;
+                        __syncwarp();
+                    }
+                    FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
+                    src = su + Tdif * denom * (src + albedo * sd);
+                    albedo = albedo_n;
+                    lev_bot = lev_top; tau = tau_n; ssa = ssa_n; g = g_n; pf = pf_n;
+                }
+                FT dn = inc;
+                {
+                    FT u = warp_sum((dn * albedo + src) * on), d = warp_sum(dn * on);
+                    if (lane == 0) { accs[UP * kAccStride + nlay] += u; accs[DN * kAccStride + nlay] += d; }
+                }
+                tmem_wait_st();
+                FT A, B, al;
+                tmem_ld2(tA + 2 * (nlay - 1), A, B);
+                ld_alpha(nlay - 1, al);
+                tmem_wait_ld();
+                for (int k = nlay - 1; k >= 0; --k) {
+                    const FT Ak = A, Bk = B, alk = al;
+                    if (k > 0) { tmem_ld2(tA + 2 * (k - 1), A, B); ld_alpha(k - 1, al); }   // prefetch
+                    dn = Ak * dn + Bk;
+                    stage[((k & 15) * 2 + 0) * 32 + lane] = dn * on;
+                    stage[((k & 15) * 2 + 1) * 32 + lane] = alk * dn * on;
+                    if ((k & 15) == 0) {                          // 16 levels x (dn, albedo*dn)
+                        __syncwarp();
+                        const int lev = k + (lane >> 1);
+                        FT s = row_sum();
+                        if (lev < nlay) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += s;
+                        __syncwarp();
+                    }
+                    tmem_wait_ld();
+                }
+            } else {
+                // shortwave_2stream.jl:300-392 with the adding marched from the top
+                const FT alb_dir = __ldg(P.io.sfc_alb_direct + (size_t)col * L.n_bnd + ibnd);
+                const FT alb_dif = __ldg(P.io.sfc_alb_diffuse + (size_t)col * L.n_bnd + ibnd);
+                const FT dir_top = toa * __ldg(L.solar_src_scaled + gpt) * mu0;
+                const FT inv_mu0 = 1.f / rmax(mu0, FLT_EPSILON);
+                FT tau_cum = 0.f, dir = dir_top;
+                FT beta = 0.f, d = 0.f;   // reflectance / downward diffuse source of everything above the level
+                {
+                    FT s = warp_sum(dir_top * on);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
+                    if (lane == 0) { accs[DIR * kAccStride + nlay] += s; accs[DN * kAccStride + nlay] += s; }
+                }
+                for (int k = nlay - 1; k >= 0; --k) {
+                    FT tau, ssa, g, pf;
+                    optics(k, tau, ssa, g, pf);
+                    FT Rdir, Tdir, Rdif, Tdif;
+                    sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
+                    const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
+                    const FT denom = hdiv(1.f, 1.f - Rdif * beta);
+                    // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
+                    tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
+                    st_alpha(k, beta);
+                    stage[((k & 15) * 2 + 0) * 32 + lane] = d * on;  // d_{k+1}
+                    d = sd + Tdif * denom * (d + beta * su);
+                    beta = Rdif + Tdif * Tdif * beta * denom;
+                    tau_cum += tau;
+                    dir = dir_top * hexp(-tau_cum * inv_mu0);         // direct flux at level k
+                    stage[((k & 15) * 2 + 1) * 32 + lane] = dir * on;
+                    if ((k & 15) == 0) {                              // 16 levels x (d_{k+1}, dir_k)
+                        __syncwarp();
+                        const int kk = k + (lane >> 1);
+                        FT s = row_sum();
+                        if (kk < nlay) {
+                            if (lane & 1) { accs[DN * kAccStride + kk] += s; accs[DIR * kAccStride + kk] += s; }
+                            else accs[DN * kAccStride + kk + 1] += s;
+                        }
+                        __syncwarp();
+                    }
+                }
+                // surface: F_up(0) = alb_dif F_dn_dif(0) + alb_dir dir(0) ; F_dn_dif(0) = d_0 + beta_0 F_up(0)
+                FT up = hdiv(alb_dif * d + alb_dir * dir, 1.f - alb_dif * beta);
+                {
+                    FT u = warp_sum(up * on), dd = warp_sum((d + beta * up) * on);
+                    if (lane == 0) { accs[UP * kAccStride] += u; accs[DN * kAccStride] += dd; }
+                }
+                tmem_wait_st();
+                FT A, B, be;
+                tmem_ld2(tA, A, B);
+                ld_alpha(0, be);
+                tmem_wait_ld();
+                for (int k = 0; k < nlay; ++k) {
+                    const FT Ak = A, Bk = B, bek = be;
+                    if (k + 1 < nlay) { tmem_ld2(tA + 2 * (k + 1), A, B); ld_alpha(k + 1, be); }
+                    up = Ak * up + Bk;                                  // F_up(k+1)
+                    stage[((k & 15) * 2 + 0) * 32 + lane] = up * on;
+                    stage[((k & 15) * 2 + 1) * 32 + lane] = bek * up * on;
+                    if ((k & 15) == 15 || k == nlay - 1) {
+                        __syncwarp();
+                        const int kk = (k & ~15) + (lane >> 1);
+                        FT s = row_sum();
+                        if (kk <= k) accs[((lane & 1) ? DN : UP) * kAccStride + kk + 1] += s;
+                        __syncwarp();
+                    }
+                    tmem_wait_ld();
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---------------- epilogue: (nlev, ncol) presentation, net, scaling, diagnostics ----------------
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int lev = lane + 32 * i;
+            if (lev < nlev) {
+                const size_t o = (size_t)col * nlev + lev;
+                FT up = accs[UP * kAccStride + lev], dn = accs[DN * kAccStride + lev], dr = accs[DIR * kAccStride + lev];
+                if (!day) { up = dn = dr = 0.f; }
+                FT net = up - dn;
+                if (P.io.metric_scaling != nullptr) {
+                    FT sc = __ldg(P.io.metric_scaling + o);
+                    up *= sc; dn *= sc; net *= sc; dr *= sc;
+                }
+                P.io.out_up[o] = up; P.io.out_dn[o] = dn; P.io.out_net[o] = net;
+                if (!LW) P.io.out_dir[o] = dr;
+                if (P.io.out_total_net != nullptr) P.io.out_total_net[o] = P.io.add_net[o] + net;
+            }
+        }
+        if (lane == 0 && P.io.cld_cover != nullptr && HAS_CLD) P.io.cld_cover[col] = FT(n_cloudy) / FT(NGPT);
+        __syncwarp();
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_smem, 512u);
+}
+
+}  // namespace rb
