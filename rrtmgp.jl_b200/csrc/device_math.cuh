@@ -63,13 +63,21 @@ __device__ __forceinline__ float hsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ float hexp(float x) { return expf(x); }
 __device__ __forceinline__ float h_one_minus_exp_neg(float x, float) { return -expm1f(-x); }
 #else
-__device__ __forceinline__ float hdiv(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ float hsqrt(float x) {
+__device__ __forceinline__ float hdiv(float a, float b) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
-__device__ __forceinline__ float hexp(float x) { return __expf(x); }
+__device__ __forceinline__ float hsqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float hexp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
 // 1 - exp(-x), x >= 0, given e = exp(-x): Taylor series below 0.25 (truncation < 2e-9 relative)
 __device__ __forceinline__ float h_one_minus_exp_neg(float x, float e) {
     float p = fmaf(x, -1.0f / 5040.0f, 1.0f / 720.0f);
@@ -96,15 +104,15 @@ template <typename FT> __device__ __forceinline__ void delta_scale(FT& tau, FT& 
     FT ssa_one_minus_g2 = ssa * (FT(1) - g) * (FT(1) + g);
     FT one_minus_wf = (FT(1) - ssa) + ssa_one_minus_g2;
     FT tau_s = one_minus_wf * tau;
-    FT ssa_s = ssa_one_minus_g2 / rmax(Num<FT>::eps(), one_minus_wf);
-    FT g_s = g / rmax(Num<FT>::eps(), FT(1) + g);
+    FT ssa_s = hdiv(ssa_one_minus_g2, rmax(Num<FT>::eps(), one_minus_wf));
+    FT g_s = hdiv(g, rmax(Num<FT>::eps(), FT(1) + g));
     tau = tau_s; ssa = ssa_s; g = g_s;
 }
 // ---- optics_utils.jl:7-14 (equispaced) ----
 template <typename FT> __device__ __forceinline__ int loc_lower_eq(FT xi, FT dx, int n, const FT* __restrict__ x) {
     if (xi <= __ldg(x)) return 1;
     if (xi >= __ldg(x + n - 1)) return n - 1;
-    int j = (int)((xi - __ldg(x)) / dx) + 1;
+    int j = (int)hdiv(xi - __ldg(x), dx) + 1;
     return j < n - 1 ? j : n - 1;
 }
 // ---- optics_utils.jl:34-44 split into "locate" (per level) and "evaluate" (per band) ----
@@ -115,7 +123,7 @@ __device__ __forceinline__ void interp1d_eq_locate(FT xi, const FT* __restrict__
     if (xi > __ldg(x + n - 1)) { loc = n; factor = FT(0); return; }
     FT dx = __ldg(x + 1) - __ldg(x);
     loc = loc_lower_eq(xi, dx, n, x);
-    factor = (xi - __ldg(x + loc - 1)) / dx;
+    factor = hdiv(xi - __ldg(x + loc - 1), dx);
 }
 template <typename FT>
 __device__ __forceinline__ FT interp1d_eq_eval(int loc, FT factor, const FT* __restrict__ y, int n) {
@@ -133,7 +141,7 @@ __device__ __forceinline__ void interp1d_loc_factor(FT xi, const FT* __restrict_
     else
         for (int i = 1; i <= n; ++i)
             if (xi < __ldg(x + i - 1)) { loc = i - 1; break; }
-    factor = (xi - __ldg(x + loc - 1)) / (__ldg(x + loc) - __ldg(x + loc - 1));
+    factor = hdiv(xi - __ldg(x + loc - 1), __ldg(x + loc) - __ldg(x + loc - 1));
 }
 
 // ---- longwave_2stream.jl:149-222 ----

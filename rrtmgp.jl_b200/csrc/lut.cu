@@ -142,15 +142,7 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
     L.nminor_max = nmax;
     for (int tr = 0; tr < 2; ++tr) {
         std::vector<double> kmin = getd(p, pre + tags[tr] + "/kminor");
-        std::vector<FT> dst((size_t)(std::max(nmax, 1) + (sw ? 1 : 0)) * n_t * n_eta * n_gpt, FT(0));
-        if (sw) {   // Rayleigh as the slot after the minors (fast kernels gather it with the same two address registers)
-            std::vector<double> ray = getd(p, pre + (tr == 0 ? "/rayl_lower" : "/rayl_upper"));
-            for (int g = 0; g < n_gpt; ++g)
-                for (int t = 0; t < n_t; ++t)
-                    for (int e = 0; e < n_eta; ++e)
-                        dst[(((size_t)std::max(nmax, 1) * n_t + t) * n_eta + e) * n_gpt + g] =
-                            (FT)ray[e + (size_t)n_eta * (t + (size_t)n_t * g)];
-        }
+        std::vector<FT> dst((size_t)std::max(nmax, 1) * n_t * n_eta * n_gpt, FT(0));
         for (int g = 0; g < n_gpt; ++g) {
             int n = gst[tr][g + 1] - gst[tr][g];
             int b = g2b[g];
@@ -164,6 +156,23 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
             }
         }
         A.add(dst, L.kminor[tr]);
+        {   // 128-bit packed copy for the fast kernels (SW: Rayleigh in slot 0)
+            const int nslots = nmax + (sw ? 1 : 0), ngrp = std::max((nslots + 3) / 4, 1);
+            L.n_minor_groups = ngrp;
+            std::vector<FT> d4((size_t)ngrp * n_t * n_eta * n_gpt * 4, FT(0));
+            std::vector<double> ray;
+            if (sw) ray = getd(p, pre + (tr == 0 ? "/rayl_lower" : "/rayl_upper"));
+            for (int sl = 0; sl < nslots; ++sl)
+                for (int t = 0; t < n_t; ++t)
+                    for (int e = 0; e < n_eta; ++e)
+                        for (int g = 0; g < n_gpt; ++g) {
+                            FT v;
+                            if (sw && sl == 0) v = (FT)ray[e + (size_t)n_eta * (t + (size_t)n_t * g)];
+                            else v = dst[(((size_t)(sl - (sw ? 1 : 0)) * n_t + t) * n_eta + e) * n_gpt + g];
+                            d4[(((((size_t)(sl / 4) * n_t + t) * n_eta + e) * n_gpt + g) * 4) + (sl % 4)] = v;
+                        }
+            A.add(d4, L.kminor4[tr]);
+        }
         std::vector<int> b0 = bst[tr];
         for (auto& v : b0) v -= 1;
         A.add(b0, L.minor_bnd_st[tr]);
@@ -182,8 +191,8 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
                     for (int pp = 0; pp < n_p; ++pp)
                         for (int e = 0; e < n_eta; ++e) {
                             size_t src = e + (size_t)n_eta * (pp + (size_t)n_p * (t + (size_t)n_t * g));
-                            size_t d0 = ((((size_t)pp * n_t + t) * n_eta + e) * 2) * n_gpt + g;
-                            dst[d0] = (FT)km[src]; dst[d0 + n_gpt] = (FT)pfr[src];
+                            size_t d0 = ((((size_t)pp * n_t + t) * n_eta + e) * n_gpt + g) * 2;
+                            dst[d0] = (FT)km[src]; dst[d0 + 1] = (FT)pfr[src];
                         }
             A.add(dst, L.kmaj_pf);
         }

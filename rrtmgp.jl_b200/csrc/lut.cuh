@@ -25,7 +25,7 @@ struct GasLut {
     const int* gpt2bnd;     // [n_gpt], 0-based band
     const FT* kmajor;       // [n_p][n_t][n_eta][n_gpt]
     const FT* pfrac;        // [n_p][n_t][n_eta][n_gpt]          (LW)
-    const FT* kmaj_pf;      // [n_p][n_t][n_eta][2][n_gpt] kmajor | pfrac interleaved (LW; fast kernels)
+    const FT* kmaj_pf;      // [n_p][n_t][n_eta][n_gpt][2] {kmajor, pfrac} pairs (LW; fast kernels: one 64-bit load per corner)
     const FT* t_planck;     // [n_t_plnk]                         (LW)
     const FT* tot_planck;   // [n_bnd][n_t_plnk]                  (LW)
     const FT* rayl;         // [2 (lower, upper)][n_t][n_eta][n_gpt]  (SW)
@@ -33,8 +33,10 @@ struct GasLut {
     // minor absorbers, index 0 = lower atmosphere, 1 = upper (LookUpTables.jl:36-53)
     const int* minor_bnd_st[2];  // [n_bnd+1], 0-based rows of gasdata
     const int* minor_gasdata[2]; // [n_abs][4] (idx_gas, idx_scaling_gas, scales_with_density, scale_by_complement)
-    const FT* kminor[2];         // [slot < nminor_max][n_t][n_eta][n_gpt]; contributor (gpt, slot);
-                                 // SW: one extra slot nminor_max = Rayleigh coefficients of that atmosphere
+    const FT* kminor[2];         // [slot < nminor_max][n_t][n_eta][n_gpt]; contributor (gpt, slot)
+    const FT* kminor4[2];        // fast kernels: [group][n_t][n_eta][n_gpt][4], four slots per 128-bit load;
+                                 // SW: slot 0 = Rayleigh of that atmosphere, minors follow; zero padded
+    int n_minor_groups;          // groups of four slots in kminor4
 };
 
 template <typename FT>

@@ -42,7 +42,7 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
 // Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
 static int plan_smem_fast(SolveParams<float>& P, FastSmem& F) {
     const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
-    P.rec_words = 4 + P.lut.nminor_max + 6;
+    P.rec_words = 4 + 4 * P.lut.n_minor_groups + 6;
     int off = 0;
     P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
     P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(float), 16);
@@ -103,7 +103,7 @@ template <typename FT> static int try_fast(int, SolveParams<FT>&, int, cudaStrea
 template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
     const GasLut<float>& L = P.lut;
     if (!fast_enabled() || P.nlay > 64 || P.nlay < 2 || mode == MODE_LW_NOSCAT || P.io.band_up != nullptr) return -1;
-    if (L.n_eta != 9 || L.n_t != 14 || L.maxb != 2 || L.nminor_max > kFastMaxMinor || (L.n_gpt % 32) != 0) return -1;
+    if (L.n_eta != 9 || L.n_t != 14 || L.maxb != 2 || L.n_minor_groups > 2 || (L.n_gpt % 32) != 0) return -1;
     if (mode == MODE_LW_2STREAM && L.n_gpt == 256 && L.kmaj_pf != nullptr) return launch_fast_flags<MODE_LW_2STREAM, 256>(P, max_smem_optin, s);
     if (mode == MODE_SW_2STREAM && L.n_gpt == 224) return launch_fast_flags<MODE_SW_2STREAM, 224>(P, max_smem_optin, s);
     return -1;

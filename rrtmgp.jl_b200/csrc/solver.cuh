@@ -80,12 +80,12 @@ __device__ __forceinline__ FT get_vmr(const SolveParams<FT>& P, int ig, int lay,
 // cloud_optics.jl:154-192 / :207-244, split into "locate" (per layer) and "evaluate" (per band)
 template <typename FT>
 __device__ __forceinline__ void cld_locate(int nsize, FT lwr, FT upr, FT re, int& loc, FT& fac) {
-    FT dr = (upr - lwr) / FT(nsize - 1);
+    FT dr = hdiv(upr - lwr, FT(nsize - 1));
     re = rmax(rmin(re, upr), lwr);
-    loc = (int)((re - lwr) / dr) + 1;
+    loc = (int)hdiv(re - lwr, dr) + 1;
     loc = loc < nsize - 1 ? loc : nsize - 1;
     loc = loc > 1 ? loc : 1;
-    fac = (re - lwr - (loc - 1) * dr) / dr;
+    fac = hdiv(re - lwr - (loc - 1) * dr, dr);
 }
 template <typename FT>
 __device__ __forceinline__ void cld_eval(int nsize, const FT* __restrict__ tbl, int loc, FT fac, FT path, FT& tau,
@@ -210,17 +210,17 @@ struct Warp {
             int tropo = p_lay > L.p_ref_tropo ? 1 : 2;
             FT dT = __ldg(L.t_ref + 1) - __ldg(L.t_ref);
             int jt = loc_lower_eq(t_lay, dT, n_t, L.t_ref);
-            FT ft = (t_lay - __ldg(L.t_ref + jt - 1)) / dT;
+            FT ft = hdiv(t_lay - __ldg(L.t_ref + jt - 1), dT);
             FT dlnp = __ldg(L.ln_p_ref) - __ldg(L.ln_p_ref + 1);
             FT lp = rlog(p_lay);
-            int jpress = (int)((__ldg(L.ln_p_ref) - lp) / dlnp) + 1;
+            int jpress = (int)hdiv(__ldg(L.ln_p_ref) - lp, dlnp) + 1;
             jpress = jpress > 1 ? jpress : 1;
             jpress = (jpress < L.n_p_ref - 1 ? jpress : L.n_p_ref - 1) + 1;
-            FT fp = (__ldg(L.ln_p_ref + jpress - 2) - lp) / dlnp;
+            FT fp = hdiv(__ldg(L.ln_p_ref + jpress - 2) - lp, dlnp);
             int jp = jpress + tropo - 1;
             FT h2o = get_vmr(P, L.idx_h2o, k, col);
             own_h2o[j] = h2o;
-            own_dens[j] = FT(0.01) * p_lay / t_lay;
+            own_dens[j] = hdiv(FT(0.01) * p_lay, t_lay);
             int aero_on = 0;
             if (use_aero) {   // aerosol_optics.jl:464-483, :438-451, optics_utils.jl:51-62
                 const FT* am = P.io.aero_mass + ((size_t)col * nlay + k) * 15;
@@ -292,7 +292,7 @@ struct Warp {
             const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
             const FT col_dry = colp[4 * k + 2];
             const FT vmr_h2o = own_h2o[j];
-            const FT dry_fact = FT(1) / (FT(1) + vmr_h2o);
+            const FT dry_fact = hdiv(FT(1), FT(1) + vmr_h2o);
             for (int b = 0; b < nb; ++b) {
                 const int ib = b_first + b;
                 FT* r = rec + ((size_t)k * maxb + b) * RW;
@@ -304,16 +304,22 @@ struct Warp {
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
                     const FT* vr = L.vmr_ref + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
-                    FT eta_half = __ldg(vr + 2 * ig1) / __ldg(vr + 2 * ig2);
+                    FT eta_half = hdiv(__ldg(vr + 2 * ig1), __ldg(vr + 2 * ig2));
                     FT col_mix = vmr1 + eta_half * vmr2;
-                    FT eta = vmr1 * (FT(1) / col_mix);
+                    FT eta = vmr1 * hdiv(FT(1), col_mix);
                     if (col_mix <= FT(0)) eta = FT(0.5);
                     FT loc_eta = eta * FT(n_eta - 1);
                     int jj = (int)loc_eta + 1;
                     jj = jj < n_eta - 1 ? jj : n_eta - 1;
-                    je[it] = jj; r[it] = loc_eta - FT(jj - 1); r[2 + it] = col_mix;
+                    je[it] = jj; r[it] = loc_eta - FT(jj - 1);
+                    r[2 + it] = FUSED ? col_mix * col_dry : col_mix;   // fast kernels fold col_dry in here
                 }
-                // gas_optics.jl:344-412: per-absorber scalings
+                // gas_optics.jl:344-412: per-absorber scalings.  Fast kernels (FUSED) gather four slots per
+                // 128-bit load: slots are zero padded to a multiple of four and SW slot 0 is Rayleigh
+                // (gas_optics.jl:430-444: (vmr_h2o + 1) * col_dry).
+                const int soff = (FUSED && !LW) ? 1 : 0;
+                const int nslots = FUSED ? 4 * L.n_minor_groups : L.nminor_max;
+                if (FUSED && !LW) r[4] = (vmr_h2o + FT(1)) * col_dry;
                 const int* bst = L.minor_bnd_st[tropo - 1];
                 const int m0 = __ldg(bst + ib), nmin = __ldg(bst + ib + 1) - m0;
                 for (int i = 0; i < nmin; ++i) {
@@ -330,9 +336,11 @@ struct Warp {
                             }
                         }
                     }
-                    r[4 + i] = scaling;
+                    r[4 + soff + i] = scaling;
                 }
-                FT* rc = r + 4 + L.nminor_max;   // cloud (3) then aerosol (3)  [FUSED: aerosol-only / cloud+aerosol products]
+                if (FUSED)
+                    for (int i = soff + nmin; i < nslots; ++i) r[4 + i] = FT(0);
+                FT* rc = r + 4 + nslots;   // cloud (3) then aerosol (3)  [FUSED: aerosol-only / cloud+aerosol products]
                 FT tc = FT(0), sc = FT(0), gc = FT(0);
                 // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
                 if (use_cloud) {
@@ -349,8 +357,8 @@ struct Warp {
                         } else {
                             tc = tl + ti;
                             sc = tls + tis;
-                            gc = (tlsg + tisg) / rmax(Num<FT>::eps(), sc);
-                            sc /= rmax(Num<FT>::eps(), tc);
+                            gc = hdiv(tlsg + tisg, rmax(Num<FT>::eps(), sc));
+                            sc = hdiv(sc, rmax(Num<FT>::eps(), tc));
                             if (!LW) delta_scale(tc, sc, gc);
                         }
                     }
@@ -366,8 +374,8 @@ struct Warp {
                         if (NOSCAT) {
                             ta = ta - tsa;
                         } else {
-                            ga = tsga / rmax(Num<FT>::eps(), tsa);
-                            sa = tsa / rmax(Num<FT>::eps(), ta);
+                            ga = hdiv(tsga, rmax(Num<FT>::eps(), tsa));
+                            sa = hdiv(tsa, rmax(Num<FT>::eps(), ta));
                             if (!LW) delta_scale(ta, sa, ga);
                         }
                     }
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
             const FT alb_dir = __ldg(P.io.sfc_alb_direct + (size_t)col * L.n_bnd + ibnd);
             const FT alb_dif = __ldg(P.io.sfc_alb_diffuse + (size_t)col * L.n_bnd + ibnd);
             const FT dir_top = toa * __ldg(L.solar_src_scaled + gpt) * mu0;
-            const FT inv_mu0 = FT(1) / rmax(mu0, Num<FT>::eps());
+            const FT inv_mu0 = hdiv(FT(1), rmax(mu0, Num<FT>::eps()));
             FT tau_cum = FT(0), dir_above = dir_top;
             S(nlay, 4) = dir_top;
             for (int k = nlay - 1; k >= 0; --k) {   // direct beam + layer coefficients, top down

@@ -12,8 +12,9 @@
 //    allocates all 512 columns; the three warps that share a lane quadrant get 170 columns
 //    each: (A, B) of 64 levels + the albedo of the lowest 42 levels; the other 22 albedos sit
 //    in shared memory.
-//  * COMPILE-TIME TABLE STRIDES: the 16 (LW: kmajor + Planck fraction, interleaved) + 4 n_minor
-//    (+ 4 Rayleigh) gathers of a cell use four address registers and immediate offsets.
+//  * COMPILE-TIME TABLE STRIDES and PACKED TABLES: a cell gathers its 8 {kmajor, Planck fraction}
+//    corners with 64-bit loads and its minor absorbers (+ Rayleigh) four slots at a time with
+//    128-bit loads: 12 loads from four address registers instead of 28-32 scalar loads.
 //  * G-POINT REDUCTION through a 4 KB shared staging tile read transposed (lane = level),
 //    ~2 instructions per (level, quantity) instead of a 10-instruction shuffle tree.
 //  * SW adding marched from the TOP (reflectance/source of everything ABOVE a level),
@@ -51,6 +52,16 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& a) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#ifdef RB_TEST_NO_TMEM   // SASS experiments only
+#define tmem_alloc(a, b) (*(a) = 0)
+#define tmem_dealloc(a, b)
+#define tmem_st2(t, a, b) (stage[(t) & 1023] = (a) + (b))
+#define tmem_st1(t, a) (stage[(t) & 1023] = (a))
+#define tmem_ld2(t, a, b) (a = stage[(t) & 1023], b = a)
+#define tmem_ld1(t, a) (a = stage[(t) & 1023])
+#define tmem_wait_ld()
+#define tmem_wait_st()
+#endif
 
 constexpr int kFastWarps = 12;        // warps per CTA = per SM
 constexpr int kFastColsPerWarp = 170; // TMEM columns per warp (3 warps share the 512 columns of a lane quadrant)
@@ -69,9 +80,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     __shared__ uint32_t tmem_base_smem;
     constexpr bool LW = MODE == MODE_LW_2STREAM;
     constexpr int NETA = 9, NT = 14;
-    constexpr int NW = LW ? 2 : 1;                                   // kmajor (+ Planck fraction) interleave
-    constexpr int KE = NW * NGPT, KT = NETA * KE, KP = NT * KT;      // major-table strides: eta, T, p
-    constexpr int ME = NGPT, MT = NETA * NGPT, MS = NT * MT;         // minor-table strides: eta, T, slot
+    constexpr int KE = NGPT, KT = NETA * KE, KP = NT * KT;           // major-table strides (LW: in float2): eta, T, p
+    constexpr int ME = NGPT, MT = NETA * NGPT, MS = NT * MT;         // minor-table strides in float4: eta, T, group
     constexpr int UP = 0, DN = 1, DIR = 2;
 
     const int lane = threadIdx.x & 31;
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     const int nlay = P.nlay, nlev = nlay + 1;
     const FT* major = LW ? L.kmaj_pf : L.kmajor;
     const int RW = P.rec_words;
-    const int rayl_slot = L.nminor_max > 0 ? L.nminor_max : 1;
+    const int n_groups = L.n_minor_groups;
 
     for (long long col = (long long)blockIdx.x * kFastWarps + warp; col < P.ncol; col += (long long)gridDim.x * kFastWarps) {
         Warp<FT, MODE, 2, true> W(P, wbase, lane, col);
@@ -133,58 +143,83 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
             const FT on = W.lane_on ? 1.f : 0.f;
 
-            // ---- gas + cloud + aerosol optics of layer k, compile-time strides ----
+            // ---- gas + cloud + aerosol optics of layer k: compile-time strides, 64/128-bit gathers ----
+            // gas_optics.jl:176-320 with the (layer, band) work read from the band record
             auto optics = [&](int k, FT& tau, FT& ssa, FT& g, FT& pfrac) {
                 const int cj = W.colj[k];
                 const int jt = cj & 0xff, jp = (cj >> 8) & 0xff, tr = (cj >> 16) & 1;
-                const float4 cp = reinterpret_cast<const float4*>(W.colp)[k];   // ft, fp, col_dry, vmr_h2o + 1
-                const FT ft = cp.x, fp = cp.y, col_dry = cp.z;
+                const float2 cp = reinterpret_cast<const float2*>(W.colp)[2 * k];   // ft, fp
+                const FT ft = cp.x, fp = cp.y;
                 const int rj = W.recj[k * 2 + bl];
-                const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf, nmin = rj >> 8;
+                const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf;
                 const FT* r = W.rec + (k * 2 + bl) * RW;
                 const FT fe1 = r[0], fe2 = r[1];
-                const FT omfe1 = 1.f - fe1, omfe2 = 1.f - fe2, omft = 1.f - ft, omfp = 1.f - fp;
-                const FT* pa = major + ((jp - 2) * KP + (jt - 1) * KT + (je1 - 1) * KE + gpt);   // (jp-1, jt,   je1)
-                const FT* pb = major + ((jp - 2) * KP + jt * KT + (je2 - 1) * KE + gpt);         // (jp-1, jt+1, je2)
-                {
-                    FT c000 = __ldg(pa), c100 = __ldg(pa + KE), c010 = __ldg(pa + KP), c110 = __ldg(pa + KP + KE);
-                    FT c001 = __ldg(pb), c101 = __ldg(pb + KE), c011 = __ldg(pb + KP), c111 = __ldg(pb + KP + KE);
-                    tau = (r[2] * (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
-                           r[3] * (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)))) * col_dry;
+                const FT omft = 1.f - ft, omfp = 1.f - fp;
+                const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
+                const int ia = (jp - 2) * KP + (jt - 1) * KT + (je1 - 1) * KE + gpt;   // (jp-1, jt,   je1)
+                const int ib = (jp - 2) * KP + jt * KT + (je2 - 1) * KE + gpt;         // (jp-1, jt+1, je2)
+                if (LW) {   // {kmajor, planck_fraction} pairs
+                    const float2* pa = reinterpret_cast<const float2*>(major) + ia;
+                    const float2* pb = reinterpret_cast<const float2*>(major) + ib;
+                    const float2 c000 = __ldg(pa), c100 = __ldg(pa + KE), c010 = __ldg(pa + KP), c110 = __ldg(pa + KP + KE);
+                    const float2 c001 = __ldg(pb), c101 = __ldg(pb + KE), c011 = __ldg(pb + KP), c111 = __ldg(pb + KP + KE);
+                    const FT ka0 = fmaf(fe1, c100.x - c000.x, c000.x), ka1 = fmaf(fe1, c110.x - c010.x, c010.x);
+                    const FT kb0 = fmaf(fe2, c101.x - c001.x, c001.x), kb1 = fmaf(fe2, c111.x - c011.x, c011.x);
+                    tau = r[2] * (wa0 * ka0 + wa1 * ka1) + r[3] * (wb0 * kb0 + wb1 * kb1);
+                    const FT pa0 = fmaf(fe1, c100.y - c000.y, c000.y), pa1 = fmaf(fe1, c110.y - c010.y, c010.y);
+                    const FT pb0 = fmaf(fe2, c101.y - c001.y, c001.y), pb1 = fmaf(fe2, c111.y - c011.y, c011.y);
+                    pfrac = (wa0 * pa0 + wa1 * pa1) + (wb0 * pb0 + wb1 * pb1);
+                } else {
+                    const FT* pa = major + ia;
+                    const FT* pb = major + ib;
+                    const FT c000 = __ldg(pa), c100 = __ldg(pa + KE), c010 = __ldg(pa + KP), c110 = __ldg(pa + KP + KE);
+                    const FT c001 = __ldg(pb), c101 = __ldg(pb + KE), c011 = __ldg(pb + KP), c111 = __ldg(pb + KP + KE);
+                    const FT ka0 = fmaf(fe1, c100 - c000, c000), ka1 = fmaf(fe1, c110 - c010, c010);
+                    const FT kb0 = fmaf(fe2, c101 - c001, c001), kb1 = fmaf(fe2, c111 - c011, c011);
+                    tau = r[2] * (wa0 * ka0 + wa1 * ka1) + r[3] * (wb0 * kb0 + wb1 * kb1);
+                    pfrac = 0.f;
                 }
-                const FT w11 = omfe1 * omft, w21 = fe1 * omft, w12 = omfe2 * ft, w22 = fe2 * ft;
-                const FT* ma = L.kminor[tr] + ((jt - 1) * MT + (je1 - 1) * ME + gpt);
-                const FT* mb = L.kminor[tr] + (jt * MT + (je2 - 1) * ME + gpt);
+                // minor absorbers (+ Rayleigh in SW slot 0): four slots per 128-bit load (optics_utils.jl:85-98)
+                const FT w11 = (1.f - fe1) * omft, w21 = fe1 * omft, w12 = (1.f - fe2) * ft, w22 = fe2 * ft;
+                const float4* ma = reinterpret_cast<const float4*>(L.kminor4[tr]) + ((jt - 1) * MT + (je1 - 1) * ME + gpt);
+                const float4* mb = reinterpret_cast<const float4*>(L.kminor4[tr]) + (jt * MT + (je2 - 1) * ME + gpt);
+                FT tau_ray = 0.f;
                 {
-                    FT tau_minor = 0.f;
-#pragma unroll
-                    for (int i = 0; i < kFastMaxMinor; ++i) {
-                        if (i >= nmin) break;
-                        FT v = w11 * __ldg(ma + i * MS) + w21 * __ldg(ma + i * MS + ME) + w12 * __ldg(mb + i * MS) + w22 * __ldg(mb + i * MS + ME);
-                        tau_minor += v * r[4 + i];
+                    const float4 m11 = __ldg(ma), m21 = __ldg(ma + ME), m12 = __ldg(mb), m22 = __ldg(mb + ME);
+                    const FT v0 = w11 * m11.x + w21 * m21.x + w12 * m12.x + w22 * m22.x;
+                    const FT v1 = w11 * m11.y + w21 * m21.y + w12 * m12.y + w22 * m22.y;
+                    const FT v2 = w11 * m11.z + w21 * m21.z + w12 * m12.z + w22 * m22.z;
+                    const FT v3 = w11 * m11.w + w21 * m21.w + w12 * m12.w + w22 * m22.w;
+                    if (LW) {
+                        tau += v0 * r[4] + v1 * r[5] + v2 * r[6] + v3 * r[7];
+                    } else {
+                        tau_ray = v0 * r[4];
+                        tau += v1 * r[5] + v2 * r[6] + v3 * r[7];
                     }
-                    tau += tau_minor;
+                }
+                if (n_groups > 1) {   // warp-uniform; real tables with more than four (three in SW) minors per band
+                    for (int gi = 1; gi < n_groups; ++gi) {
+                        const float4 m11 = __ldg(ma + gi * MS), m21 = __ldg(ma + gi * MS + ME), m12 = __ldg(mb + gi * MS), m22 = __ldg(mb + gi * MS + ME);
+                        const FT* sc = r + 4 + 4 * gi;
+                        tau += (w11 * m11.x + w21 * m21.x + w12 * m12.x + w22 * m22.x) * sc[0] +
+                               (w11 * m11.y + w21 * m21.y + w12 * m12.y + w22 * m22.y) * sc[1] +
+                               (w11 * m11.z + w21 * m21.z + w12 * m12.z + w22 * m22.z) * sc[2] +
+                               (w11 * m11.w + w21 * m21.w + w12 * m12.w + w22 * m22.w) * sc[3];
+                    }
                 }
                 if (LW) {
-                    FT c000 = __ldg(pa + NGPT), c100 = __ldg(pa + KE + NGPT), c010 = __ldg(pa + KP + NGPT), c110 = __ldg(pa + KP + KE + NGPT);
-                    FT c001 = __ldg(pb + NGPT), c101 = __ldg(pb + KE + NGPT), c011 = __ldg(pb + KP + NGPT), c111 = __ldg(pb + KP + KE + NGPT);
-                    pfrac = (omfp * (omft * (omfe1 * c000 + fe1 * c100)) + fp * (omft * (omfe1 * c010 + fe1 * c110))) +
-                            (omfp * (ft * (omfe2 * c001 + fe2 * c101)) + fp * (ft * (omfe2 * c011 + fe2 * c111)));
                     tau = rmax(tau, 0.f);
                     ssa = 0.f; g = 0.f;
                 } else {
-                    const FT* ra = ma + rayl_slot * MS;
-                    const FT* rb = mb + rayl_slot * MS;
-                    FT tau_ray = (w11 * __ldg(ra) + w21 * __ldg(ra + ME) + w12 * __ldg(rb) + w22 * __ldg(rb + ME)) * cp.w * col_dry;
                     tau = rmax(tau + tau_ray, 0.f);
                     ssa = tau > 0.f ? hdiv(tau_ray, tau) : 0.f;
-                    g = 0.f; pfrac = 0.f;
+                    g = 0.f;
                 }
                 // one fused increment (optics_utils.jl:189-202 is additive in tau, tau ssa, tau ssa g)
                 const bool cb = HAS_CLD && W.mask_bit(k);
                 const bool ab = HAS_AER && ((cj >> 17) & 1);
                 if (cb || ab) {
-                    const FT* x = r + 4 + L.nminor_max + (cb ? 3 : 0);
+                    const FT* x = r + 4 + 4 * n_groups + (cb ? 3 : 0);
                     const FT tn = tau + x[0];
                     const FT w = tau * ssa + x[1];
                     const FT h = tau * ssa * g + x[2];
@@ -276,7 +311,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 const FT alb_dir = __ldg(P.io.sfc_alb_direct + (size_t)col * L.n_bnd + ibnd);
                 const FT alb_dif = __ldg(P.io.sfc_alb_diffuse + (size_t)col * L.n_bnd + ibnd);
                 const FT dir_top = toa * __ldg(L.solar_src_scaled + gpt) * mu0;
-                const FT inv_mu0 = 1.f / rmax(mu0, FLT_EPSILON);
+                const FT inv_mu0 = hdiv(1.f, rmax(mu0, FLT_EPSILON));
                 FT tau_cum = 0.f, dir = dir_top;
                 FT beta = 0.f, d = 0.f;   // reflectance / downward diffuse source of everything above the level
                 {
@@ -358,7 +393,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 if (P.io.out_total_net != nullptr) P.io.out_total_net[o] = P.io.add_net[o] + net;
             }
         }
-        if (lane == 0 && P.io.cld_cover != nullptr && HAS_CLD) P.io.cld_cover[col] = FT(n_cloudy) / FT(NGPT);
+        if (lane == 0 && P.io.cld_cover != nullptr && HAS_CLD) P.io.cld_cover[col] = __fdiv_rn(FT(n_cloudy), FT(NGPT));
         __syncwarp();
     }
 
