@@ -160,17 +160,16 @@ __device__ __forceinline__ void lw_2stream_coeffs(FT tau, FT ssa, FT g, FT lev_s
     FT RT_term = hdiv(FT(1), k * (FT(1) + coeff) + g1 * one_minus_e2kt);
     Rdif = RT_term * g2 * one_minus_e2kt;
     Tdif = RT_term * FT(2) * k * e1;
-    if (tau > FT(0)) {
-        FT dB = lev_src_bot - lev_src_top;
-        FT g_sum = g1 + g2;
-        FT one_p_e1 = FT(1) + e1;
-        FT emis_fac = om1 * (k * om1 + lw_diff_sec * (FT(1) - ssa) * one_p_e1) * RT_term;
-        FT dBz = hdiv(dB * hdiv(om1, tau) * (k * om1 + g_sum * one_p_e1) * RT_term, rmax(g_sum, Num<FT>::eps()));
-        src_up = Num<FT>::pi() * (lev_src_top * emis_fac - Tdif * dB + dBz);
-        src_dn = Num<FT>::pi() * (lev_src_bot * emis_fac + Tdif * dB - dBz);
-    } else {
-        src_up = FT(0); src_dn = FT(0);
-    }
+    // branch-free: a genuinely empty layer (tau = 0) emits nothing (longwave_2stream.jl:202-220)
+    FT dB = lev_src_bot - lev_src_top;
+    FT g_sum = g1 + g2;
+    FT one_p_e1 = FT(1) + e1;
+    FT emis_fac = om1 * (k * om1 + lw_diff_sec * (FT(1) - ssa) * one_p_e1) * RT_term;
+    FT dBz = hdiv(dB * hdiv(om1, tau) * (k * om1 + g_sum * one_p_e1) * RT_term, rmax(g_sum, Num<FT>::eps()));
+    FT su = Num<FT>::pi() * (lev_src_top * emis_fac - Tdif * dB + dBz);
+    FT sd = Num<FT>::pi() * (lev_src_bot * emis_fac + Tdif * dB - dBz);
+    src_up = tau > FT(0) ? su : FT(0);
+    src_dn = tau > FT(0) ? sd : FT(0);
 }
 
 // ---- shortwave_2stream.jl:189-279 ----
@@ -197,9 +196,11 @@ __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, 
     FT k_mu2 = k_mu * k_mu;
     FT diff = FT(1) - k_mu2;
     const FT win = Num<FT>::k_min();                    // resonance_window = sqrt(eps) (Numerics.jl:49)
-    if (rabs(diff) < win) {
-        k_mu2 = diff >= FT(0) ? FT(1) - win : FT(1) + win;
-        k_mu = hsqrt(k_mu2);
+    {   // nudge k mu0 off the removable singularity (branch-free select)
+        const bool res = rabs(diff) < win;
+        const FT k_mu2_n = diff >= FT(0) ? FT(1) - win : FT(1) + win;
+        k_mu2 = res ? k_mu2_n : k_mu2;
+        k_mu = res ? hsqrt(k_mu2_n) : k_mu;
     }
     FT k_g3 = k * g3, k_g4 = k * g4;
     RT_term = hdiv(ssa * RT_term, FT(1) - k_mu2);
@@ -211,8 +212,9 @@ __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, 
     Tdir = rmax(FT(0), Tdir_u);
     FT av_energy = rmax(FT(0), FT(1) - T0);
     FT tot_dir = Rdir + Tdir;
-    if (tot_dir > av_energy) {
+    {
         FT scale = hdiv(av_energy, rmax(Num<FT>::eps(), tot_dir));
+        scale = tot_dir > av_energy ? scale : FT(1);
         Rdir *= scale; Tdir *= scale;
     }
 }

@@ -50,9 +50,9 @@ static int plan_smem_fast(SolveParams<float>& P, FastSmem& F) {
     P.off_rec = off;  off = align_up(off + nlay * maxb * P.rec_words * (int)sizeof(float), 16);
     P.off_plk = off;  off = align_up(off + maxb * 2 * nlev * (int)sizeof(float), 16);
     P.off_store = off;
-    const int n_hi = nlay > kAlphaTmemLevels ? nlay - kAlphaTmemLevels : 0;
+    const int n_hi = (nlay > kAlphaTmemLevels ? nlay - kAlphaTmemLevels : 0) + 1;   // + dummy slot
     F.off_alpha = off; off = align_up(off + n_hi * 32 * (int)sizeof(float), 128);
-    F.off_stage = off; off = align_up(off + 32 * 32 * (int)sizeof(float), 16);
+    F.off_stage = off; off = align_up(off + 32 * kStageStride * (int)sizeof(float), 16);
     F.off_acc = off;   off = align_up(off + 3 * kAccStride * (int)sizeof(float), 128);
     P.warp_bytes = off;
     return off;

@@ -77,6 +77,10 @@ __device__ __forceinline__ FT get_vmr(const SolveParams<FT>& P, int ig, int lay,
     return __ldg(P.io.vmr + k * P.ngas + ig - 1);
 }
 
+template <typename FT> __device__ __forceinline__ FT int_as_ft(int i);
+template <> __device__ __forceinline__ float int_as_ft<float>(int i) { return __int_as_float(i); }
+template <> __device__ __forceinline__ double int_as_ft<double>(int i) { return (double)i; }
+
 // cloud_optics.jl:154-192 / :207-244, split into "locate" (per layer) and "evaluate" (per band)
 template <typename FT>
 __device__ __forceinline__ void cld_locate(int nsize, FT lwr, FT upr, FT re, int& loc, FT& fac) {
@@ -257,7 +261,9 @@ struct Warp {
                 if (NOSCAT) interp1d_eq_locate(t_lay, L.t_planck, L.n_t_plnk, own_py_loc[j], own_py_f[j]);
             }
             colj[k] = jt | (jp << 8) | ((tropo - 1) << 16) | (aero_on << 17);
-            colp[4 * k + 0] = ft; colp[4 * k + 1] = fp; colp[4 * k + 2] = col_dry; colp[4 * k + 3] = h2o + FT(1);
+            colp[4 * k + 0] = ft; colp[4 * k + 1] = fp; colp[4 * k + 2] = col_dry;
+            // fast kernels: element offset of the (jp-1, jt) node row of the major table instead of vmr_h2o + 1
+            colp[4 * k + 3] = FUSED ? int_as_ft<FT>(((jp - 2) * n_t + (jt - 1)) * L.n_eta * L.n_gpt) : h2o + FT(1);
         }
         p0_loc = psfc_loc = 0; p0_f = psfc_f = FT(0);
         if (LW && lane == 0) {
@@ -390,7 +396,8 @@ struct Warp {
                     if (use_cloud) { rc[0] = tc; rc[1] = sc; rc[2] = gc; }
                     if (use_aero) { rc[3] = ta; rc[4] = sa; rc[5] = ga; }
                 }
-                recj[k * maxb + b] = je[0] | (je[1] << 4) | (nmin << 8);
+                recj[k * maxb + b] = FUSED ? (((je[0] - 1) * L.n_gpt) | (((je[1] - 1) * L.n_gpt) << 16))   // eta offsets
+                                           : (je[0] | (je[1] << 4) | (nmin << 8));
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {
                     const FT* totplnk = L.tot_planck + (size_t)L.n_t_plnk * ib;

@@ -65,7 +65,8 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 constexpr int kFastWarps = 12;        // warps per CTA = per SM
 constexpr int kFastColsPerWarp = 170; // TMEM columns per warp (3 warps share the 512 columns of a lane quadrant)
-constexpr int kAlphaTmemLevels = kFastColsPerWarp - 128;   // 42 albedos in TMEM, the rest in shared memory
+constexpr int kAlphaTmemLevels = kFastColsPerWarp - 128 - 1;   // 41 albedos in TMEM (+1 dummy column), the rest in shared memory
+constexpr int kStageStride = 33;     // padded row stride of the staging tile
 constexpr int kAccStride = 68;        // per-quantity stride of the shared broadband accumulators
 constexpr int kFastMaxMinor = 8;
 
@@ -147,17 +148,17 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             // gas_optics.jl:176-320 with the (layer, band) work read from the band record
             auto optics = [&](int k, FT& tau, FT& ssa, FT& g, FT& pfrac) {
                 const int cj = W.colj[k];
-                const int jt = cj & 0xff, jp = (cj >> 8) & 0xff, tr = (cj >> 16) & 1;
-                const float2 cp = reinterpret_cast<const float2*>(W.colp)[2 * k];   // ft, fp
+                const int jt = cj & 0xff, tr = (cj >> 16) & 1;
+                const float4 cp = reinterpret_cast<const float4*>(W.colp)[k];   // ft, fp, col_dry, major-table row offset
                 const FT ft = cp.x, fp = cp.y;
                 const int rj = W.recj[k * 2 + bl];
-                const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf;
+                const int e1 = rj & 0xffff, e2 = rj >> 16;                     // (je - 1) * NGPT
                 const FT* r = W.rec + (k * 2 + bl) * RW;
                 const FT fe1 = r[0], fe2 = r[1];
                 const FT omft = 1.f - ft, omfp = 1.f - fp;
                 const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
-                const int ia = (jp - 2) * KP + (jt - 1) * KT + (je1 - 1) * KE + gpt;   // (jp-1, jt,   je1)
-                const int ib = (jp - 2) * KP + jt * KT + (je2 - 1) * KE + gpt;         // (jp-1, jt+1, je2)
+                const int ia = __float_as_int(cp.w) + e1 + gpt;               // (jp-1, jt,   je1)
+                const int ib = __float_as_int(cp.w) + KT + e2 + gpt;          // (jp-1, jt+1, je2)
                 if (LW) {   // {kmajor, planck_fraction} pairs
                     const float2* pa = reinterpret_cast<const float2*>(major) + ia;
                     const float2* pb = reinterpret_cast<const float2*>(major) + ib;
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 }
                 // minor absorbers (+ Rayleigh in SW slot 0): four slots per 128-bit load (optics_utils.jl:85-98)
                 const FT w11 = (1.f - fe1) * omft, w21 = fe1 * omft, w12 = (1.f - fe2) * ft, w22 = fe2 * ft;
-                const float4* ma = reinterpret_cast<const float4*>(L.kminor4[tr]) + ((jt - 1) * MT + (je1 - 1) * ME + gpt);
-                const float4* mb = reinterpret_cast<const float4*>(L.kminor4[tr]) + (jt * MT + (je2 - 1) * ME + gpt);
+                const float4* ma = reinterpret_cast<const float4*>(L.kminor4[tr]) + ((jt - 1) * MT + e1 + gpt);
+                const float4* mb = reinterpret_cast<const float4*>(L.kminor4[tr]) + (jt * MT + e2 + gpt);
                 FT tau_ray = 0.f;
                 {
                     const float4 m11 = __ldg(ma), m21 = __ldg(ma + ME), m12 = __ldg(mb), m22 = __ldg(mb + ME);
@@ -228,18 +229,20 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     tau = tn;
                 }
             };
+            // albedo of level k: TMEM for k < 41 (column 41 is a dummy), shared memory above (slot 0 is a dummy);
+            // branch-free so the level loops stay single basic blocks
             auto st_alpha = [&](int k, FT v) {
-                if (k < kAlphaTmemLevels) tmem_st1(tAl + k, v); else alpha_hi[(k - kAlphaTmemLevels) * 32 + lane] = v;
+                tmem_st1(tAl + (k < kAlphaTmemLevels ? k : kAlphaTmemLevels), v);
+                alpha_hi[(k < kAlphaTmemLevels ? 0 : k - kAlphaTmemLevels + 1) * 32 + lane] = v;
             };
-            auto ld_alpha = [&](int k, FT& v) {
-                if (k < kAlphaTmemLevels) tmem_ld1(tAl + k, v); else v = alpha_hi[(k - kAlphaTmemLevels) * 32 + lane];
-            };
+            auto ld_alpha_t = [&](int k, FT& v) { tmem_ld1(tAl + (k < kAlphaTmemLevels ? k : kAlphaTmemLevels), v); };
+            auto ld_alpha_s = [&](int k) -> FT { return alpha_hi[(k < kAlphaTmemLevels ? 0 : k - kAlphaTmemLevels + 1) * 32 + lane]; };
             // transposed row sum of the staging tile: lane <-> row
             auto row_sum = [&]() -> FT {
                 FT s = 0.f;
-                const FT* row = stage + lane * 32;
-#pragma unroll 8
-                for (int j = 0; j < 32; ++j) s += row[(lane + j) & 31];
+                const FT* row = stage + lane * kStageStride;   // stride 33: conflict-free, immediate offsets
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s += row[j];
                 return s;
             };
 
@@ -253,33 +256,32 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 FT lev_bot = pbk[0] * pf;
                 FT albedo = 1.f - emis;
                 FT src = Num<FT>::pi() * emis * (pbk[nlev + nlay] * pf);
-                for (int k = 0; k < nlay; ++k) {
-                    FT tau_n = 0.f, ssa_n = 0.f, g_n = 0.f, pf_n = 0.f, lev_top;
-                    FT inc_k = pbk[k + 1] * pf;
-                    if (k + 1 < nlay) {
-                        optics(k + 1, tau_n, ssa_n, g_n, pf_n);
-                        lev_top = hsqrt(inc_k * (pbk[k + 1] * pf_n));
-                    } else {
-                        lev_top = inc_k;
+                for (int kc = 0; kc < nlay; kc += 32) {              // 32 levels per reduction tile
+                    const int kend = kc + 32 < nlay ? kc + 32 : nlay;
+                    for (int k = kc; k < kend; ++k) {
+                        FT tau_n, ssa_n, g_n, pf_n;
+                        const bool last = k + 1 >= nlay;
+                        optics(last ? k : k + 1, tau_n, ssa_n, g_n, pf_n);   // next layer (recomputed once at the top)
+                        const FT inc_k = pbk[k + 1] * pf;
+                        const FT lev_top = last ? inc_k : hsqrt(inc_k * (pbk[k + 1] * pf_n));
+                        FT Rdif, Tdif, su, sd;
+                        lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
+                        const FT denom = hdiv(1.f, 1.f - Rdif * albedo);
+                        // level k: F_dn(k) = A_k F_dn(k+1) + B_k ; F_up(k) = albedo_k F_dn(k) + src_k
+                        tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * src + sd) * denom);
+                        st_alpha(k, albedo);
+                        stage[(k - kc) * kStageStride + lane] = src * on;
+                        const FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
+                        src = su + Tdif * denom * (src + albedo * sd);
+                        albedo = albedo_n;
+                        lev_bot = lev_top; tau = tau_n; ssa = ssa_n; g = g_n; pf = pf_n;
                     }
-                    FT Rdif, Tdif, su, sd;
-                    lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
-                    FT denom = hdiv(1.f, 1.f - Rdif * albedo);
-                    // level k: F_dn(k) = A_k F_dn(k+1) + B_k ; F_up(k) = albedo_k F_dn(k) + src_k
-                    tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * src + sd) * denom);
-                    st_alpha(k, albedo);
-                    stage[(k & 31) * 32 + lane] = src * on;
-                    if ((k & 31) == 31 || k == nlay - 1) {       // sum_g src_k for up to 32 levels
-                        __syncwarp();
-                        const int kb = k & ~31;
-                        FT s = row_sum();
-                        if (kb + lane <= k) accs[UP * kAccStride + kb + lane] += s;
-                        __syncwarp();
+                    __syncwarp();                                     // sum_g src_k for this tile
+                    {
+                        const FT sum = row_sum();
+                        if (kc + lane < kend) accs[UP * kAccStride + kc + lane] += sum;
                     }
-                    FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
-                    src = su + Tdif * denom * (src + albedo * sd);
-                    albedo = albedo_n;
-                    lev_bot = lev_top; tau = tau_n; ssa = ssa_n; g = g_n; pf = pf_n;
+                    __syncwarp();
                 }
                 FT dn = inc;
                 {
@@ -289,22 +291,28 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 tmem_wait_st();
                 FT A, B, al;
                 tmem_ld2(tA + 2 * (nlay - 1), A, B);
-                ld_alpha(nlay - 1, al);
+                ld_alpha_t(nlay - 1, al);
                 tmem_wait_ld();
-                for (int k = nlay - 1; k >= 0; --k) {
-                    const FT Ak = A, Bk = B, alk = al;
-                    if (k > 0) { tmem_ld2(tA + 2 * (k - 1), A, B); ld_alpha(k - 1, al); }   // prefetch
-                    dn = Ak * dn + Bk;
-                    stage[((k & 15) * 2 + 0) * 32 + lane] = dn * on;
-                    stage[((k & 15) * 2 + 1) * 32 + lane] = alk * dn * on;
-                    if ((k & 15) == 0) {                          // 16 levels x (dn, albedo*dn)
-                        __syncwarp();
-                        const int lev = k + (lane >> 1);
-                        FT s = row_sum();
-                        if (lev < nlay) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += s;
-                        __syncwarp();
+                for (int kc = (nlay - 1) & ~15; kc >= 0; kc -= 16) {   // 16 levels x (dn, albedo * dn) per tile
+                    const int ktop = kc + 15 < nlay - 1 ? kc + 15 : nlay - 1;
+                    for (int k = ktop; k >= kc; --k) {
+                        const FT Ak = A, Bk = B;
+                        const FT alk = k < kAlphaTmemLevels ? al : ld_alpha_s(k);
+                        const int kn = k > 0 ? k - 1 : 0;                // prefetch the next level (harmless reload at k = 0)
+                        tmem_ld2(tA + 2 * kn, A, B);
+                        ld_alpha_t(kn, al);
+                        dn = Ak * dn + Bk;
+                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = dn * on;
+                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = alk * dn * on;
+                        tmem_wait_ld();
                     }
-                    tmem_wait_ld();
+                    __syncwarp();
+                    {
+                        const int lev = kc + (lane >> 1);
+                        const FT sum = row_sum();
+                        if (lev <= ktop) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += sum;
+                    }
+                    __syncwarp();
                 }
             } else {
                 // shortwave_2stream.jl:300-392 with the adding marched from the top
@@ -315,35 +323,39 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 FT tau_cum = 0.f, dir = dir_top;
                 FT beta = 0.f, d = 0.f;   // reflectance / downward diffuse source of everything above the level
                 {
-                    FT s = warp_sum(dir_top * on);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
-                    if (lane == 0) { accs[DIR * kAccStride + nlay] += s; accs[DN * kAccStride + nlay] += s; }
+                    FT sum = warp_sum(dir_top * on);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
+                    if (lane == 0) { accs[DIR * kAccStride + nlay] += sum; accs[DN * kAccStride + nlay] += sum; }
                 }
-                for (int k = nlay - 1; k >= 0; --k) {
-                    FT tau, ssa, g, pf;
-                    optics(k, tau, ssa, g, pf);
-                    FT Rdir, Tdir, Rdif, Tdif;
-                    sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
-                    const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
-                    const FT denom = hdiv(1.f, 1.f - Rdif * beta);
-                    // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
-                    tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
-                    st_alpha(k, beta);
-                    stage[((k & 15) * 2 + 0) * 32 + lane] = d * on;  // d_{k+1}
-                    d = sd + Tdif * denom * (d + beta * su);
-                    beta = Rdif + Tdif * Tdif * beta * denom;
-                    tau_cum += tau;
-                    dir = dir_top * hexp(-tau_cum * inv_mu0);         // direct flux at level k
-                    stage[((k & 15) * 2 + 1) * 32 + lane] = dir * on;
-                    if ((k & 15) == 0) {                              // 16 levels x (d_{k+1}, dir_k)
-                        __syncwarp();
-                        const int kk = k + (lane >> 1);
-                        FT s = row_sum();
-                        if (kk < nlay) {
-                            if (lane & 1) { accs[DN * kAccStride + kk] += s; accs[DIR * kAccStride + kk] += s; }
-                            else accs[DN * kAccStride + kk + 1] += s;
-                        }
-                        __syncwarp();
+                for (int kc = (nlay - 1) & ~15; kc >= 0; kc -= 16) {   // 16 levels x (d_{k+1}, dir_k) per tile
+                    const int ktop = kc + 15 < nlay - 1 ? kc + 15 : nlay - 1;
+                    for (int k = ktop; k >= kc; --k) {
+                        FT tau, ssa, g, pf;
+                        optics(k, tau, ssa, g, pf);
+                        FT Rdir, Tdir, Rdif, Tdif;
+                        sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
+                        const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
+                        const FT denom = hdiv(1.f, 1.f - Rdif * beta);
+                        // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
+                        tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
+                        st_alpha(k, beta);
+                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = d * on;   // d_{k+1}
+                        d = sd + Tdif * denom * (d + beta * su);
+                        beta = Rdif + Tdif * Tdif * beta * denom;
+                        tau_cum += tau;
+                        dir = dir_top * hexp(-tau_cum * inv_mu0);         // direct flux at level k
+                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = dir * on;
                     }
+                    __syncwarp();
+                    {
+                        const int kk = kc + (lane >> 1);
+                        const FT sum = row_sum();
+                        // d_{kk+1} (even lanes) and dir_kk (odd lanes) both feed F_dn: two ordered steps,
+                        // never two lanes read-modify-writing one accumulator in the same instruction
+                        if (kk <= ktop && (lane & 1)) { accs[DN * kAccStride + kk] += sum; accs[DIR * kAccStride + kk] += sum; }
+                        __syncwarp();
+                        if (kk <= ktop && !(lane & 1)) accs[DN * kAccStride + kk + 1] += sum;
+                    }
+                    __syncwarp();
                 }
                 // surface: F_up(0) = alb_dif F_dn_dif(0) + alb_dir dir(0) ; F_dn_dif(0) = d_0 + beta_0 F_up(0)
                 FT up = hdiv(alb_dif * d + alb_dir * dir, 1.f - alb_dif * beta);
@@ -354,22 +366,28 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 tmem_wait_st();
                 FT A, B, be;
                 tmem_ld2(tA, A, B);
-                ld_alpha(0, be);
+                ld_alpha_t(0, be);
                 tmem_wait_ld();
-                for (int k = 0; k < nlay; ++k) {
-                    const FT Ak = A, Bk = B, bek = be;
-                    if (k + 1 < nlay) { tmem_ld2(tA + 2 * (k + 1), A, B); ld_alpha(k + 1, be); }
-                    up = Ak * up + Bk;                                  // F_up(k+1)
-                    stage[((k & 15) * 2 + 0) * 32 + lane] = up * on;
-                    stage[((k & 15) * 2 + 1) * 32 + lane] = bek * up * on;
-                    if ((k & 15) == 15 || k == nlay - 1) {
-                        __syncwarp();
-                        const int kk = (k & ~15) + (lane >> 1);
-                        FT s = row_sum();
-                        if (kk <= k) accs[((lane & 1) ? DN : UP) * kAccStride + kk + 1] += s;
-                        __syncwarp();
+                for (int kc = 0; kc < nlay; kc += 16) {               // 16 levels x (F_up, beta * F_up) per tile
+                    const int kend = kc + 16 < nlay ? kc + 16 : nlay;
+                    for (int k = kc; k < kend; ++k) {
+                        const FT Ak = A, Bk = B;
+                        const FT bek = k < kAlphaTmemLevels ? be : ld_alpha_s(k);
+                        const int kn = k + 1 < nlay ? k + 1 : k;
+                        tmem_ld2(tA + 2 * kn, A, B);
+                        ld_alpha_t(kn, be);
+                        up = Ak * up + Bk;                                  // F_up(k+1)
+                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = up * on;
+                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = bek * up * on;
+                        tmem_wait_ld();
                     }
-                    tmem_wait_ld();
+                    __syncwarp();
+                    {
+                        const int kk = kc + (lane >> 1);
+                        const FT sum = row_sum();
+                        if (kk < kend) accs[((lane & 1) ? DN : UP) * kAccStride + kk + 1] += sum;
+                    }
+                    __syncwarp();
                 }
             }
         }
