@@ -1,0 +1,37 @@
+"""Committed golden vectors (tests/golden/make_golden.py): the oracle on CPU, the engine on GPU."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import rrtmgp_b200 as R
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(_HERE, "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+GOLD = np.load(os.path.join(_HERE, "golden", "allsky_real_dims.npz"))
+
+
+def test_oracle_reproduces_golden(real_pack):
+    from oracle import Oracle
+    r = Oracle(real_pack, np.float64).update_fluxes(mg.inputs(), seed=mg.CASE["seed_mcica"], method="all_sky_with_clear")
+    for k in GOLD.files:
+        np.testing.assert_allclose(r[k], GOLD[k], rtol=1e-12, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,rel", [(np.float64, 1e-9), (np.float32, None)])
+def test_engine_reproduces_golden(real_pack, dtype, rel):
+    from helpers import run_engine
+    e = run_engine(real_pack, mg.inputs(), dtype, seed=mg.CASE["seed_mcica"], method="all_sky_with_clear")
+    tol32 = {"lw_up": 1e-3, "lw_dn": 1e-3, "clear_lw_up": 1e-3, "sw_up": 1.2e-1, "sw_dn": 1.2e-1, "sw_dir": 1.2e-1,
+             "clear_sw_dn": 1.2e-1, "net": 1.2e-1}
+    for k in GOLD.files:
+        if k.startswith(("cld_cover", "aod")):
+            np.testing.assert_allclose(e[k], GOLD[k], rtol=1e-12 if dtype == np.float64 else 3e-5)
+            continue
+        err = float(np.abs(e[k].astype(np.float64) - GOLD[k]).max())
+        bar = rel * max(1.0, float(np.abs(GOLD[k]).max())) if rel else tol32[k]
+        assert err <= bar, (k, err)
