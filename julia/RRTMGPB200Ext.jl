@@ -1,0 +1,138 @@
+# RRTMGPB200Ext.jl -- reference-side binding of librrtmgp_b200.so (include/rrtmgp_b200.h).
+#
+# UNTESTED HERE: this image has no Julia.  The same C ABI is exercised through ctypes by
+# rrtmgp.jl_b200/_lib.py + solver.py, from which this file is mechanically derived.
+#
+# Drop-in seam: the same methods `ext/RRTMGPCUDAExt.jl:33-45` specialises on the CUDA device,
+# plus the Layer-2 orchestration of `src/api/update_fluxes.jl:223-281`.  A host keeps its
+# `RRTMGPSolver` (all arrays stay owned by Julia, `src/api/solver.jl:216-272`); `B200Engine`
+# wraps one library handle bound to the `CuPtr`s of those arrays.  After `bind!`, replace
+#     RRTMGP.update_fluxes!(solver, seed)      by      update_fluxes!(engine, seed)
+# and keep reading results through the usual getters (`net_flux(solver)`, ...): the engine
+# writes straight into the `(nlev, ncol)` presentation arrays the getters expose
+# (`src/optics/Fluxes.jl:355-374`), so the `(ncol, nlev)` compute buffers, the transposed
+# state cache and the presentation copies of the reference are simply unused.
+module RRTMGPB200Ext
+
+using CUDA
+import RRTMGP
+import RRTMGP: RRTMGPSolver
+
+const LIB = get(ENV, "RRTMGP_B200_LIB", "librrtmgp_b200.so")
+
+# rrtmgp_b200_config_t (include/rrtmgp_b200.h)
+struct Config
+    abi_version::Int32; device::Int32; dtype::Int32; ncol::Int32; nlay::Int32; ngas::Int32
+    vmr_kind::Int32; method::Int32; aerosol_radiation::Int32; op_lw::Int32; n_gauss_angles::Int32
+    ice_rgh::Int32; spectral_fluxes::Int32; isothermal_boundary_layer::Int32
+    col_offset::Int64
+    grav::Float64; molmass_dryair::Float64; molmass_water::Float64; avogad::Float64
+end
+
+# rrtmgp_b200_buffers_t: 48 device pointers in header order
+const NBUF = 48
+mutable struct Buffers
+    p::NTuple{NBUF, CuPtr{Cvoid}}
+end
+
+mutable struct B200Engine
+    handle::Ptr{Cvoid}
+end
+
+check(st::Cint) = st == 0 || error(unsafe_string(ccall((:rrtmgp_b200_strerror, LIB), Cstring, (Cint,), st)))
+
+devptr(::Nothing) = CuPtr{Cvoid}(0)
+devptr(a) = reinterpret(CuPtr{Cvoid}, pointer(parent(a)))   # parent(): getters hand out SubArray views
+
+method_code(::RRTMGP.ClearSkyRadiation) = 0
+method_code(::RRTMGP.AllSkyRadiation) = 1
+method_code(::RRTMGP.AllSkyRadiationWithClearSkyDiagnostics) = 2
+
+"""
+    B200Engine(s::RRTMGPSolver, lut_pack::Vector{UInt8}; col_offset = 0)
+
+`lut_pack` is the flat table pack; produce it once from `Adapt.adapt(Array, s.lookups)` with
+`write_lut_pack` below (array-by-array dump in the post-load layouts of `src/optics/LookUpTables.jl`).
+"""
+function B200Engine(s::RRTMGPSolver, lut_pack::Vector{UInt8}; col_offset = 0)
+    FT = eltype(s.grid_params)
+    as = s.as
+    rm = s.radiation_method
+    vmr = as.vmr
+    cfg = Config(1, CUDA.deviceid(), FT === Float64 ? 1 : 0, s.grid_params.ncol, s.grid_params.nlay,
+                 vmr isa RRTMGP.VolumeMixingRatios.VmrGM ? length(vmr.vmr) : size(vmr.vmr, 1),
+                 vmr isa RRTMGP.VolumeMixingRatios.VmrGM ? 0 : 1, method_code(rm), rm.aerosol_radiation ? 1 : 0,
+                 s.lws.op isa RRTMGP.Optics.OneScalar ? 1 : 0,
+                 s.lws isa RRTMGP.RTE.NoScatLWRTE ? s.lws.angle_disc.n_gauss_angles : 1,
+                 isnothing(as.cloud_state) ? 2 : as.cloud_state.ice_rgh,
+                 (hasproperty(s.lws, :band_flux) && !isnothing(s.lws.band_flux)) ? 1 : 0, s.grid_params.isothermal_boundary_layer ? 1 : 0,
+                 col_offset, s.params.grav, s.params.molmass_dryair, s.params.molmass_water, s.params.avogad)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rrtmgp_b200_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h))
+    check(ccall((:rrtmgp_b200_load_luts, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t), h[], lut_pack, length(lut_pack)))
+    e = B200Engine(h[])
+    finalizer(x -> ccall((:rrtmgp_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), e)
+    bind!(e, s)
+    return e
+end
+
+function bind!(e::B200Engine, s::RRTMGPSolver)
+    as = s.as; cs = as.cloud_state; ae = as.aerosol_state
+    gm = as.vmr isa RRTMGP.VolumeMixingRatios.VmrGM
+    pf, cf = s.presented_flux_lw, s.presented_flux_sw
+    clw, csw = s.clear_flux_lw, s.clear_flux_sw                  # `nothing` unless WithClearSkyDiagnostics
+    bl = hasproperty(s.lws, :band_flux) ? s.lws.band_flux : nothing
+    bs = s.sws.band_flux
+    f(x, name) = isnothing(x) ? nothing : getfield(x, name)
+    ptrs = (
+        devptr(as.layerdata), devptr(as.p_lev), devptr(as.t_lev), devptr(as.t_sfc),
+        devptr(gm ? as.vmr.vmr_h2o : nothing), devptr(gm ? as.vmr.vmr_o3 : nothing), devptr(as.vmr.vmr), devptr(as.lat),
+        devptr(f(cs, :cld_r_eff_liq)), devptr(f(cs, :cld_r_eff_ice)), devptr(f(cs, :cld_path_liq)), devptr(f(cs, :cld_path_ice)),
+        devptr(f(cs, :cld_frac)), devptr(f(cs, :cld_cover_lw)), devptr(f(cs, :cld_cover_sw)),
+        devptr(f(ae, :aero_mass)), devptr(f(ae, :aero_size)), devptr(f(ae, :aod_sw_ext)), devptr(f(ae, :aod_sw_sca)),
+        devptr(s.lws.bcs.sfc_emis), devptr(s.lws.bcs.inc_flux), devptr(s.sws.bcs.cos_zenith), devptr(s.sws.bcs.toa_flux),
+        devptr(s.sws.bcs.sfc_alb_direct), devptr(s.sws.bcs.sfc_alb_diffuse), devptr(s.deep_atmosphere_inverse_scaling),
+        devptr(pf.flux_up), devptr(pf.flux_dn), devptr(pf.flux_net),
+        devptr(cf.flux_up), devptr(cf.flux_dn), devptr(cf.flux_net), devptr(cf.flux_dn_dir), devptr(s.net_flux_buffer),
+        devptr(f(clw, :flux_up)), devptr(f(clw, :flux_dn)), devptr(f(clw, :flux_net)),
+        devptr(f(csw, :flux_up)), devptr(f(csw, :flux_dn)), devptr(f(csw, :flux_net)), devptr(f(csw, :flux_dn_dir)),
+        devptr(s.clear_net_flux_buffer),
+        devptr(f(bl, :flux_up)), devptr(f(bl, :flux_dn)), devptr(f(bl, :flux_net)),
+        devptr(f(bs, :flux_up)), devptr(f(bs, :flux_dn)), devptr(f(bs, :flux_net)),
+    )
+    check(ccall((:rrtmgp_b200_bind, LIB), Cint, (Ptr{Cvoid}, Ref{Buffers}), e.handle, Buffers(ptrs)))
+end
+
+# update_fluxes!(s, seedval) (src/api/update_fluxes.jl:223-233): async on the task-local CUDA stream,
+# no allocation, no host sync, returns nothing.
+function update_fluxes!(e::B200Engine, seedval = nothing)
+    st = CUDA.stream().handle
+    check(ccall((:rrtmgp_b200_update_fluxes, LIB), Cint, (Ptr{Cvoid}, UInt64, Cint, Ptr{Cvoid}),
+                e.handle, isnothing(seedval) ? UInt64(0) : UInt64(seedval), isnothing(seedval) ? 0 : 1, st))
+    return nothing
+end
+prepare_atmosphere!(e::B200Engine) =
+    (check(ccall((:rrtmgp_b200_prepare_atmosphere, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, CUDA.stream().handle)); nothing)
+
+# LUT pack writer: name -> Array in the post-load layouts of src/optics/LookUpTables.jl
+# (format: rrtmgp.jl_b200/lutpack.py; names: rrtmgp.jl_b200/synthetic.py `make_lut_arrays`).
+function write_lut_pack(arrays::Vector{Pair{String, Array}})
+    io = IOBuffer()
+    n = length(arrays)
+    off = cld(32 + 80n, 64) * 64
+    entries = IOBuffer(); blobs = IOBuffer()
+    for (name, a) in arrays
+        isint = eltype(a) <: Integer
+        data = isint ? Int32.(a) : Float64.(a)
+        write(entries, rpad(name, 32, '\0')); write(entries, UInt32(isint ? 1 : 0), UInt32(ndims(a)))
+        write(entries, UInt32.(vcat(collect(size(a)), ones(Int, 6 - ndims(a)))))
+        write(entries, UInt64(off), UInt64(sizeof(data)))
+        write(blobs, data); pad = mod(-sizeof(data), 64); write(blobs, zeros(UInt8, pad))
+        off += sizeof(data) + pad
+    end
+    write(io, "RRTMGPB200LUT\0\0\0"); write(io, UInt32(1), UInt32(n), UInt64(off))
+    write(io, take!(entries)); write(io, zeros(UInt8, mod(-position(io), 64))); write(io, take!(blobs))
+    return take!(io)
+end
+
+end # module
