@@ -148,6 +148,13 @@ int rrtmgp_b200_update_net_fluxes(rrtmgp_b200_handle_t* h, void* stream);
 /* update_fluxes!(s, seedval) (update_fluxes.jl:223-233) = prepare + lw + sw + net, async on `stream`. */
 int rrtmgp_b200_update_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream);
 
+/* The same update restricted to columns [col_begin, col_begin + col_count): lets a host pipeline
+ * H2D copy / compute / D2H copy of column chunks on several streams (the reference has no such call; its
+ * columns are independent, ext/cuda/rte_longwave_2stream.jl:101).  Requires an explicit seed so that all
+ * chunks of one step sample consistently; results are identical to one full-range call. */
+int rrtmgp_b200_update_fluxes_range(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, int64_t col_begin,
+                                    int32_t col_count, void* stream);
+
 /* compute_relative_humidity!(...) (src/optics/column_amounts.jl:52-76, gas_optics.jl:58-80): a host
  * duty in the reference (grid_adaptation.jl:267-270); writes layerdata[..][3]. */
 int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream);

@@ -51,6 +51,7 @@ class LutInfo(C.Structure):
 EXPORTS = ("rrtmgp_b200_create", "rrtmgp_b200_destroy", "rrtmgp_b200_load_luts", "rrtmgp_b200_lut_info",
            "rrtmgp_b200_bind", "rrtmgp_b200_prepare_atmosphere", "rrtmgp_b200_update_lw_fluxes",
            "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_net_fluxes", "rrtmgp_b200_update_fluxes",
+           "rrtmgp_b200_update_fluxes_range",
            "rrtmgp_b200_compute_relative_humidity", "rrtmgp_b200_last_launch_count",
            "rrtmgp_b200_last_cuda_error", "rrtmgp_b200_strerror", "rrtmgp_b200_abi_version")
 
@@ -84,6 +85,7 @@ def lib():
         for n in ("rrtmgp_b200_update_lw_fluxes", "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_fluxes"):
             getattr(L, n).argtypes = [H, C.c_uint64, C.c_int, C.c_void_p]
         L.rrtmgp_b200_update_net_fluxes.argtypes = [H, C.c_void_p]
+        L.rrtmgp_b200_update_fluxes_range.argtypes = [H, C.c_uint64, C.c_int, C.c_int64, C.c_int32, C.c_void_p]
         L.rrtmgp_b200_compute_relative_humidity.argtypes = [H, C.c_void_p]
         L.rrtmgp_b200_last_launch_count.argtypes = [H]
         L.rrtmgp_b200_last_cuda_error.argtypes = [H]

@@ -31,9 +31,10 @@ namespace {
 // ------------------------------------------------------------------------------------
 // add_isothermal_boundary_layer! (grid_adaptation.jl:135-150,176-214); one thread per column
 template <typename FT>
-__global__ void boundary_layer_kernel(rrtmgp_b200_buffers_t B, int ncol, int nlay, int ngas, int vmr_kind, FT p_min) {
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void boundary_layer_kernel(rrtmgp_b200_buffers_t B, long long col0, int ncol, int nlay, int ngas, int vmr_kind, FT p_min) {
+    long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncol) return;
+    col += col0;
     const int nlev = nlay + 1, top = nlay - 1;
     FT* ld = (FT*)B.layerdata + (size_t)col * nlay * 4;
     FT* p_lev = (FT*)B.p_lev + (size_t)col * nlev;
@@ -63,12 +64,14 @@ __global__ void boundary_layer_kernel(rrtmgp_b200_buffers_t B, int ncol, int nla
 
 // clip! (grid_adaptation.jl:232-258) + compute_col_gas_kernel! (gas_optics.jl:16-41); thread per (col, level)
 template <typename FT>
-__global__ void prepare_kernel(rrtmgp_b200_buffers_t B, int ncol, int nlay, int ngas, int vmr_kind, int idx_h2o, FT p_min,
+__global__ void prepare_kernel(rrtmgp_b200_buffers_t B, long long col0, int ncol, int nlay, int ngas, int vmr_kind, int idx_h2o, FT p_min,
                                FT t_min, FT t_max, FT grav, FT m_dry, FT m_h2o, FT avogad) {
     const int nlev = nlay + 1;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)ncol * nlev) return;
-    const int col = (int)(idx / nlev), lev = (int)(idx - (long long)col * nlev);
+    const long long lcol = idx / nlev;
+    const int lev = (int)(idx - lcol * nlev);
+    const long long col = col0 + lcol;
     FT* p_lev = (FT*)B.p_lev + (size_t)col * nlev;
     FT* t_lev = (FT*)B.t_lev + (size_t)col * nlev;
     const FT p_here = rmax(p_lev[lev], p_min);
@@ -123,21 +126,26 @@ template <typename FT> const Luts<FT>& luts_of(const rrtmgp_b200_handle* h);
 template <> const Luts<float>& luts_of<float>(const rrtmgp_b200_handle* h) { return h->luts.f32; }
 template <> const Luts<double>& luts_of<double>(const rrtmgp_b200_handle* h) { return h->luts.f64; }
 
+// Typed view of the bound buffers, advanced to column `c0` (all arrays are [ncol][...] except
+// inc_flux_lw [n_gpt][ncol] and the band fluxes [n_bnd][ncol][nlev], which keep the full column stride).
 template <typename FT>
-void fill_io(const rrtmgp_b200_handle* h, ColumnIO<FT>& io) {
+void fill_io(const rrtmgp_b200_handle* h, ColumnIO<FT>& io, long long c0) {
     const rrtmgp_b200_buffers_t& B = h->buf;
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const long long nlay = c.nlay, nlev = c.nlay + 1;
+    auto adv = [&](void* p, long long per_col) -> FT* { return p ? (FT*)p + c0 * per_col : nullptr; };
     std::memset(&io, 0, sizeof(io));
-    io.layerdata = (const FT*)B.layerdata; io.p_lev = (const FT*)B.p_lev; io.t_lev = (const FT*)B.t_lev;
-    io.t_sfc = (const FT*)B.t_sfc; io.vmr_h2o = (const FT*)B.vmr_h2o; io.vmr_o3 = (const FT*)B.vmr_o3;
-    io.vmr = (const FT*)B.vmr;
-    io.cld_r_eff_liq = (const FT*)B.cld_r_eff_liq; io.cld_r_eff_ice = (const FT*)B.cld_r_eff_ice;
-    io.cld_path_liq = (const FT*)B.cld_path_liq; io.cld_path_ice = (const FT*)B.cld_path_ice;
-    io.cld_frac = (const FT*)B.cld_frac;
-    io.aero_mass = (const FT*)B.aero_mass; io.aero_size = (const FT*)B.aero_size;
-    io.sfc_emis = (const FT*)B.sfc_emis; io.inc_flux_lw = (const FT*)B.inc_flux_lw;
-    io.cos_zenith = (const FT*)B.cos_zenith; io.toa_flux = (const FT*)B.toa_flux;
-    io.sfc_alb_direct = (const FT*)B.sfc_alb_direct; io.sfc_alb_diffuse = (const FT*)B.sfc_alb_diffuse;
-    io.metric_scaling = (const FT*)B.metric_scaling;
+    io.layerdata = adv(B.layerdata, nlay * 4); io.p_lev = adv(B.p_lev, nlev); io.t_lev = adv(B.t_lev, nlev);
+    io.t_sfc = adv(B.t_sfc, 1); io.vmr_h2o = adv(B.vmr_h2o, nlay); io.vmr_o3 = adv(B.vmr_o3, nlay);
+    io.vmr = c.vmr_kind == RRTMGP_B200_VMR_GM ? (const FT*)B.vmr : adv(B.vmr, nlay * c.ngas);
+    io.cld_r_eff_liq = adv(B.cld_r_eff_liq, nlay); io.cld_r_eff_ice = adv(B.cld_r_eff_ice, nlay);
+    io.cld_path_liq = adv(B.cld_path_liq, nlay); io.cld_path_ice = adv(B.cld_path_ice, nlay);
+    io.cld_frac = adv(B.cld_frac, nlay);
+    io.aero_mass = adv(B.aero_mass, nlay * 15); io.aero_size = adv(B.aero_size, nlay * 15);
+    io.sfc_emis = adv(B.sfc_emis, h->luts.n_bnd_lw); io.inc_flux_lw = adv(B.inc_flux_lw, 1);
+    io.cos_zenith = adv(B.cos_zenith, 1); io.toa_flux = adv(B.toa_flux, 1);
+    io.sfc_alb_direct = adv(B.sfc_alb_direct, h->luts.n_bnd_sw); io.sfc_alb_diffuse = adv(B.sfc_alb_diffuse, h->luts.n_bnd_sw);
+    io.metric_scaling = adv(B.metric_scaling, nlev);
 }
 
 // src/optics/AngularDiscretizations.jl:34-63
@@ -155,19 +163,19 @@ template <typename FT> void gauss_angles(int n, FT* Ds, FT* wts) {
 }
 
 template <typename FT>
-void base_params(const rrtmgp_b200_handle* h, SolveParams<FT>& P, bool sw, bool clouds, unsigned long long seed) {
+void base_params(const rrtmgp_b200_handle* h, SolveParams<FT>& P, bool sw, bool clouds, unsigned long long seed, long long c0, int count) {
     const rrtmgp_b200_config_t& c = h->cfg;
     const Luts<FT>& L = luts_of<FT>(h);
     std::memset(&P, 0, sizeof(P));
-    fill_io(h, P.io);
+    fill_io(h, P.io, c0);
     P.lut = sw ? L.sw : L.lw;
     P.cld = sw ? L.cld_sw : L.cld_lw;
     P.aero = sw ? L.aero_sw : L.aero_lw;
-    P.ncol = c.ncol; P.nlay = c.nlay; P.ngas = c.ngas; P.vmr_kind = c.vmr_kind; P.ice_rgh = c.ice_rgh;
+    P.ncol = count; P.ncol_total = c.ncol; P.nlay = c.nlay; P.ngas = c.ngas; P.vmr_kind = c.vmr_kind; P.ice_rgh = c.ice_rgh;
     P.use_cloud = clouds && h->buf.cld_frac != nullptr;
     P.use_aero = c.aerosol_radiation && h->buf.aero_mass != nullptr;
     P.n_mu = c.op_lw == RRTMGP_B200_ONE_SCALAR ? c.n_gauss_angles : 1;
-    P.col_offset = c.col_offset;
+    P.col_offset = c.col_offset + c0;
     P.seed = seed;
     gauss_angles<FT>(P.n_mu, P.Ds, P.wts);
 }
@@ -178,25 +186,29 @@ unsigned long long effective_seed(rrtmgp_b200_handle* h, uint64_t seed, int have
     return have_seed ? (unsigned long long)seed : 0xA5A5F00DULL + (++h->call_counter) * 0x632BE59BD9B4E019ULL;
 }
 
+// output arrays advanced to column c0: [ncol][nlev] (and band arrays, whose column stride stays ncol) / [ncol]
+#define OFFL(T, p) ((p) ? (T*)(p) + c0 * (long long)(h->cfg.nlay + 1) : (T*)nullptr)
+#define OFFC(T, p) ((p) ? (T*)(p) + c0 : (T*)nullptr)
+
 template <typename FT>
-int solve_lw_t(rrtmgp_b200_handle* h, unsigned long long seed, cudaStream_t s) {
+int solve_lw_t(rrtmgp_b200_handle* h, unsigned long long seed, long long c0, int count, cudaStream_t s) {
     const rrtmgp_b200_config_t& c = h->cfg;
     const rrtmgp_b200_buffers_t& B = h->buf;
     const int mode = c.op_lw == RRTMGP_B200_ONE_SCALAR ? MODE_LW_NOSCAT : MODE_LW_2STREAM;
     const size_t nb = (size_t)h->luts.n_bnd_lw * c.ncol * (c.nlay + 1) * sizeof(FT);
     SolveParams<FT> P;
     if (c.method == RRTMGP_B200_ALL_SKY_WITH_CLEAR) {   // update_fluxes.jl:39-65
-        base_params<FT>(h, P, false, false, seed);
-        P.io.out_up = (FT*)B.clear_lw_flux_up; P.io.out_dn = (FT*)B.clear_lw_flux_dn; P.io.out_net = (FT*)B.clear_lw_flux_net;
+        base_params<FT>(h, P, false, false, seed, c0, count);
+        P.io.out_up = OFFL(FT, B.clear_lw_flux_up); P.io.out_dn = OFFL(FT, B.clear_lw_flux_dn); P.io.out_net = OFFL(FT, B.clear_lw_flux_net);
         int e = launch_solve<FT>(mode, P, h->max_smem_optin, s);
         if (e) return fail_cuda(h, (cudaError_t)e);
         ++h->last_launches;
     }
-    base_params<FT>(h, P, false, c.method >= RRTMGP_B200_ALL_SKY, seed);
-    P.io.out_up = (FT*)B.lw_flux_up; P.io.out_dn = (FT*)B.lw_flux_dn; P.io.out_net = (FT*)B.lw_flux_net;
-    P.io.cld_cover = (FT*)B.cld_cover_lw;
+    base_params<FT>(h, P, false, c.method >= RRTMGP_B200_ALL_SKY, seed, c0, count);
+    P.io.out_up = OFFL(FT, B.lw_flux_up); P.io.out_dn = OFFL(FT, B.lw_flux_dn); P.io.out_net = OFFL(FT, B.lw_flux_net);
+    P.io.cld_cover = OFFC(FT, B.cld_cover_lw);
     if (c.spectral_fluxes && mode == MODE_LW_2STREAM) {
-        P.io.band_up = (FT*)B.lw_band_flux_up; P.io.band_dn = (FT*)B.lw_band_flux_dn; P.io.band_net = (FT*)B.lw_band_flux_net;
+        P.io.band_up = OFFL(FT, B.lw_band_flux_up); P.io.band_dn = OFFL(FT, B.lw_band_flux_dn); P.io.band_net = OFFL(FT, B.lw_band_flux_net);
         cudaError_t e = cudaMemsetAsync(B.lw_band_flux_up, 0, nb, s);   // set_band_flux_to_zero! (Fluxes.jl:191-197)
         if (e == cudaSuccess) e = cudaMemsetAsync(B.lw_band_flux_dn, 0, nb, s);
         if (e != cudaSuccess) return fail_cuda(h, e);
@@ -208,29 +220,29 @@ int solve_lw_t(rrtmgp_b200_handle* h, unsigned long long seed, cudaStream_t s) {
 }
 
 template <typename FT>
-int solve_sw_t(rrtmgp_b200_handle* h, unsigned long long seed, bool fuse_net, cudaStream_t s) {
+int solve_sw_t(rrtmgp_b200_handle* h, unsigned long long seed, bool fuse_net, long long c0, int count, cudaStream_t s) {
     const rrtmgp_b200_config_t& c = h->cfg;
     const rrtmgp_b200_buffers_t& B = h->buf;
     const size_t nb = (size_t)h->luts.n_bnd_sw * c.ncol * (c.nlay + 1) * sizeof(FT);
     SolveParams<FT> P;
     if (c.method == RRTMGP_B200_ALL_SKY_WITH_CLEAR) {   // update_fluxes.jl:101-128
-        base_params<FT>(h, P, true, false, seed);
-        P.io.out_up = (FT*)B.clear_sw_flux_up; P.io.out_dn = (FT*)B.clear_sw_flux_dn; P.io.out_net = (FT*)B.clear_sw_flux_net;
-        P.io.out_dir = (FT*)B.clear_sw_flux_dn_dir;
-        P.io.aod_ext = (FT*)B.aod_sw_ext; P.io.aod_sca = (FT*)B.aod_sw_sca;
-        if (fuse_net && B.clear_net_flux) { P.io.add_net = (const FT*)B.clear_lw_flux_net; P.io.out_total_net = (FT*)B.clear_net_flux; }
+        base_params<FT>(h, P, true, false, seed, c0, count);
+        P.io.out_up = OFFL(FT, B.clear_sw_flux_up); P.io.out_dn = OFFL(FT, B.clear_sw_flux_dn); P.io.out_net = OFFL(FT, B.clear_sw_flux_net);
+        P.io.out_dir = OFFL(FT, B.clear_sw_flux_dn_dir);
+        P.io.aod_ext = OFFC(FT, B.aod_sw_ext); P.io.aod_sca = OFFC(FT, B.aod_sw_sca);
+        if (fuse_net && B.clear_net_flux) { P.io.add_net = OFFL(const FT, B.clear_lw_flux_net); P.io.out_total_net = OFFL(FT, B.clear_net_flux); }
         int e = launch_solve<FT>(MODE_SW_2STREAM, P, h->max_smem_optin, s);
         if (e) return fail_cuda(h, (cudaError_t)e);
         ++h->last_launches;
     }
-    base_params<FT>(h, P, true, c.method >= RRTMGP_B200_ALL_SKY, seed);
-    P.io.out_up = (FT*)B.sw_flux_up; P.io.out_dn = (FT*)B.sw_flux_dn; P.io.out_net = (FT*)B.sw_flux_net;
-    P.io.out_dir = (FT*)B.sw_flux_dn_dir;
-    P.io.cld_cover = (FT*)B.cld_cover_sw;
-    P.io.aod_ext = (FT*)B.aod_sw_ext; P.io.aod_sca = (FT*)B.aod_sw_sca;
-    if (fuse_net && B.net_flux) { P.io.add_net = (const FT*)B.lw_flux_net; P.io.out_total_net = (FT*)B.net_flux; }
+    base_params<FT>(h, P, true, c.method >= RRTMGP_B200_ALL_SKY, seed, c0, count);
+    P.io.out_up = OFFL(FT, B.sw_flux_up); P.io.out_dn = OFFL(FT, B.sw_flux_dn); P.io.out_net = OFFL(FT, B.sw_flux_net);
+    P.io.out_dir = OFFL(FT, B.sw_flux_dn_dir);
+    P.io.cld_cover = OFFC(FT, B.cld_cover_sw);
+    P.io.aod_ext = OFFC(FT, B.aod_sw_ext); P.io.aod_sca = OFFC(FT, B.aod_sw_sca);
+    if (fuse_net && B.net_flux) { P.io.add_net = OFFL(const FT, B.lw_flux_net); P.io.out_total_net = OFFL(FT, B.net_flux); }
     if (c.spectral_fluxes) {
-        P.io.band_up = (FT*)B.sw_band_flux_up; P.io.band_dn = (FT*)B.sw_band_flux_dn; P.io.band_net = (FT*)B.sw_band_flux_net;
+        P.io.band_up = OFFL(FT, B.sw_band_flux_up); P.io.band_dn = OFFL(FT, B.sw_band_flux_dn); P.io.band_net = OFFL(FT, B.sw_band_flux_net);
         cudaError_t e = cudaMemsetAsync(B.sw_band_flux_up, 0, nb, s);
         if (e == cudaSuccess) e = cudaMemsetAsync(B.sw_band_flux_dn, 0, nb, s);
         if (e != cudaSuccess) return fail_cuda(h, e);
@@ -241,16 +253,16 @@ int solve_sw_t(rrtmgp_b200_handle* h, unsigned long long seed, bool fuse_net, cu
     return RRTMGP_B200_OK;
 }
 
-template <typename FT> int prepare_t(rrtmgp_b200_handle* h, cudaStream_t s) {
+template <typename FT> int prepare_t(rrtmgp_b200_handle* h, long long c0, int count, cudaStream_t s) {
     const rrtmgp_b200_config_t& c = h->cfg;
     const LutStore& L = h->luts;
     const int idx_h2o = luts_of<FT>(h).lw.idx_h2o;
     if (c.isothermal_boundary_layer) {
-        boundary_layer_kernel<FT><<<(c.ncol + 127) / 128, 128, 0, s>>>(h->buf, c.ncol, c.nlay, c.ngas, c.vmr_kind, (FT)L.p_ref_min);
+        boundary_layer_kernel<FT><<<(count + 127) / 128, 128, 0, s>>>(h->buf, c0, count, c.nlay, c.ngas, c.vmr_kind, (FT)L.p_ref_min);
         ++h->last_launches;
     }
-    const long long n = (long long)c.ncol * (c.nlay + 1);
-    prepare_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->buf, c.ncol, c.nlay, c.ngas, c.vmr_kind, idx_h2o,
+    const long long n = (long long)count * (c.nlay + 1);
+    prepare_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->buf, c0, count, c.nlay, c.ngas, c.vmr_kind, idx_h2o,
                                                                   luts_of<FT>(h).lw.p_ref_min, luts_of<FT>(h).lw.t_ref_min,
                                                                   luts_of<FT>(h).lw.t_ref_max, (FT)c.grav, (FT)c.molmass_dryair,
                                                                   (FT)c.molmass_water, (FT)c.avogad);
@@ -394,7 +406,7 @@ int rrtmgp_b200_prepare_atmosphere(rrtmgp_b200_handle_t* h, void* stream) {
     if (st) return st;
     DeviceGuard g(h->cfg.device);
     h->last_launches = 0;
-    return h->cfg.dtype == 1 ? prepare_t<double>(h, (cudaStream_t)stream) : prepare_t<float>(h, (cudaStream_t)stream);
+    return h->cfg.dtype == 1 ? prepare_t<double>(h, 0, h->cfg.ncol, (cudaStream_t)stream) : prepare_t<float>(h, 0, h->cfg.ncol, (cudaStream_t)stream);
 }
 
 int rrtmgp_b200_update_lw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {
@@ -403,7 +415,7 @@ int rrtmgp_b200_update_lw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int hav
     DeviceGuard g(h->cfg.device);
     h->last_launches = 0;
     unsigned long long s = effective_seed(h, seed, have_seed);
-    return h->cfg.dtype == 1 ? solve_lw_t<double>(h, s, (cudaStream_t)stream) : solve_lw_t<float>(h, s, (cudaStream_t)stream);
+    return h->cfg.dtype == 1 ? solve_lw_t<double>(h, s, 0, h->cfg.ncol, (cudaStream_t)stream) : solve_lw_t<float>(h, s, 0, h->cfg.ncol, (cudaStream_t)stream);
 }
 
 int rrtmgp_b200_update_sw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {
@@ -412,8 +424,8 @@ int rrtmgp_b200_update_sw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int hav
     DeviceGuard g(h->cfg.device);
     h->last_launches = 0;
     unsigned long long s = effective_seed(h, seed, have_seed);
-    return h->cfg.dtype == 1 ? solve_sw_t<double>(h, s, false, (cudaStream_t)stream)
-                             : solve_sw_t<float>(h, s, false, (cudaStream_t)stream);
+    return h->cfg.dtype == 1 ? solve_sw_t<double>(h, s, false, 0, h->cfg.ncol, (cudaStream_t)stream)
+                             : solve_sw_t<float>(h, s, false, 0, h->cfg.ncol, (cudaStream_t)stream);
 }
 
 int rrtmgp_b200_update_net_fluxes(rrtmgp_b200_handle_t* h, void* stream) {
@@ -424,20 +436,34 @@ int rrtmgp_b200_update_net_fluxes(rrtmgp_b200_handle_t* h, void* stream) {
     return h->cfg.dtype == 1 ? net_t<double>(h, (cudaStream_t)stream) : net_t<float>(h, (cudaStream_t)stream);
 }
 
+static int update_range(rrtmgp_b200_handle_t* h, unsigned long long sd, long long c0, int count, cudaStream_t s) {
+    const bool f64 = h->cfg.dtype == 1;
+    int st = f64 ? prepare_t<double>(h, c0, count, s) : prepare_t<float>(h, c0, count, s);
+    if (st) return st;
+    st = f64 ? solve_lw_t<double>(h, sd, c0, count, s) : solve_lw_t<float>(h, sd, c0, count, s);
+    if (st) return st;
+    // net = lw_net + sw_net is folded into the shortwave epilogue (update_fluxes.jl:165-194)
+    return f64 ? solve_sw_t<double>(h, sd, true, c0, count, s) : solve_sw_t<float>(h, sd, true, c0, count, s);
+}
+
 int rrtmgp_b200_update_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {
     int st = ready(h);
     if (st) return st;
     DeviceGuard g(h->cfg.device);
     h->last_launches = 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long sd = effective_seed(h, seed, have_seed);
-    const bool f64 = h->cfg.dtype == 1;
-    st = f64 ? prepare_t<double>(h, s) : prepare_t<float>(h, s);
+    return update_range(h, effective_seed(h, seed, have_seed), 0, h->cfg.ncol, (cudaStream_t)stream);
+}
+
+int rrtmgp_b200_update_fluxes_range(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, int64_t col_begin,
+                                    int32_t col_count, void* stream) {
+    int st = ready(h);
     if (st) return st;
-    st = f64 ? solve_lw_t<double>(h, sd, s) : solve_lw_t<float>(h, sd, s);
-    if (st) return st;
-    // net = lw_net + sw_net is folded into the shortwave epilogue (update_fluxes.jl:165-194)
-    return f64 ? solve_sw_t<double>(h, sd, true, s) : solve_sw_t<float>(h, sd, true, s);
+    if (col_begin < 0 || col_count <= 0 || col_begin + col_count > h->cfg.ncol) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (!have_seed) return RRTMGP_B200_ERR_INVALID_ARG;          // every range of one step must share the seed
+    if (h->cfg.spectral_fluxes) return RRTMGP_B200_ERR_UNSUPPORTED;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 0;
+    return update_range(h, (unsigned long long)seed, col_begin, col_count, (cudaStream_t)stream);
 }
 
 int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream) {

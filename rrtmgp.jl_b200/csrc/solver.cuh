@@ -53,6 +53,7 @@ struct SolveParams {
     CldLut<FT> cld;
     AeroLut<FT> aero;
     int ncol, nlay, ngas, vmr_kind, ice_rgh;
+    int ncol_total;   // column stride of the [n_gpt][ncol] / [n_bnd][ncol][nlev] arrays (>= ncol for column ranges)
     int use_cloud, use_aero, n_mu;
     long long col_offset;
     unsigned long long seed;
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
             // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding
             const FT* pb = W.plk + bl * 2 * nlev;
             const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
-            const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : FT(0);
+            const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : FT(0);
             FT tau, ssa, g, pf;
             W.optics(0, tau, ssa, g, pf);
             FT lev_bot = pb[0] * pf;
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
             const FT* pb = W.plk + bl * 2 * nlev;
             const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
             const bool has_inc = P.io.inc_flux_lw != nullptr;
-            const FT inc = has_inc ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : FT(0);
+            const FT inc = has_inc ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : FT(0);
             FT sfc_source = FT(0), inc_prev = FT(0);
             for (int k = 0; k < nlay; ++k) {
                 FT tau, ssa, g, pf;
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
                                 const int l2 = (lane + j) & 31;
                                 if (g0 + l2 < n_gpt && __ldg(L.gpt2bnd + g0 + l2) == W.b_first + b) { bu += su[l2]; bd += sd[l2]; }
                             }
-                            size_t o = ((size_t)(W.b_first + b) * P.ncol + col) * nlev + lev;
+                            size_t o = ((size_t)(W.b_first + b) * P.ncol_total + col) * nlev + lev;
                             P.io.band_up[o] += bu; P.io.band_dn[o] += bd;
                         }
                     }
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
             if (P.io.out_total_net != nullptr) P.io.out_total_net[o] = P.io.add_net[o] + net;   // Fluxes.jl:423-435
             if (P.io.band_up != nullptr) {
                 for (int b = 0; b < L.n_bnd; ++b) {
-                    size_t ob = ((size_t)b * P.ncol + col) * nlev + lev;
+                    size_t ob = ((size_t)b * P.ncol_total + col) * nlev + lev;
                     FT bu = P.io.band_up[ob], bd = P.io.band_dn[ob];
                     if (!day) { bu = FT(0); bd = FT(0); }
                     if (P.io.metric_scaling != nullptr) { FT sc = __ldg(P.io.metric_scaling + o); bu *= sc; bd *= sc; }

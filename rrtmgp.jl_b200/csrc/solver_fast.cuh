@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom)
                 const FT* pbk = W.plk + bl * 2 * nlev;
                 const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
-                const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol + col) : 0.f;
+                const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : 0.f;
                 FT tau, ssa, g, pf;
                 optics(0, tau, ssa, g, pf);
                 FT lev_bot = pbk[0] * pf;

@@ -239,6 +239,77 @@ def update_fluxes(s: RRTMGPSolver, seedval=None) -> None:
     check(lib().rrtmgp_b200_update_fluxes(s._h, seed, have, s._stream()), s._h)
 
 
+def update_fluxes_range(s: RRTMGPSolver, seedval: int, col_begin: int, col_count: int, stream=None) -> None:
+    """`update_fluxes!` restricted to columns [col_begin, col_begin + col_count) on `stream` (a
+    `torch.cuda.Stream`; default: the current one).  Columns are independent, so any partition of the
+    column range gives the same result as one full call with the same seed."""
+    st = C.c_void_p((stream or torch.cuda.current_stream(s.device)).cuda_stream)
+    check(lib().rrtmgp_b200_update_fluxes_range(s._h, C.c_uint64(int(seedval) & (2 ** 64 - 1)), 1, col_begin,
+                                                col_count, st), s._h)
+
+
+INPUT_KEYS = ("layerdata", "p_lev", "t_lev", "t_sfc", "vmr_h2o", "vmr_o3", "cld_r_eff_liq", "cld_r_eff_ice",
+              "cld_path_liq", "cld_path_ice", "cld_frac", "aero_mass", "aero_size", "sfc_emis", "cos_zenith", "toa_flux",
+              "sfc_alb_direct", "sfc_alb_diffuse", "lat", "metric_scaling")
+OUTPUT_KEYS = ("lw_flux_up", "lw_flux_dn", "lw_flux_net", "sw_flux_up", "sw_flux_dn", "sw_flux_net", "sw_flux_dn_dir",
+               "net_flux", "cld_cover_lw", "cld_cover_sw", "aod_sw_ext", "aod_sw_sca")
+
+
+class HostPipeline:
+    """Host-resident driving of one solver: per step, every per-column input is copied from pinned host memory,
+    `update_fluxes!` runs, and every flux / diagnostic is copied back -- as column chunks on a few CUDA streams so
+    that the H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe and the
+    SMs are otherwise idle in turn).  This is the end-to-end call for a host whose state lives in host memory;
+    a GPU-resident host (the CliMA case) calls `update_fluxes` directly."""
+
+    def __init__(self, s: RRTMGPSolver, n_chunks: int = 8, n_streams: int = 3):
+        self.s = s
+        ncol = s.grid_params.ncol
+        n_chunks = max(1, min(n_chunks, ncol))
+        step = -(-ncol // n_chunks)
+        # whole "waves" of the persistent kernels (one 12-warp CTA per SM) per chunk avoid a ragged tail per chunk
+        wave = 12 * torch.cuda.get_device_properties(s.device).multi_processor_count
+        if step > 2 * wave:
+            step = max(wave, (step // wave) * wave)
+        self.chunks = [(a, min(step, ncol - a)) for a in range(0, ncol, step)]
+        self.streams = [torch.cuda.Stream(device=s.device) for _ in range(max(1, n_streams))]
+        full = lambda k: (k == "vmr" and s.config.vmr_kind == _lib.VMR_FULL)
+        self.in_keys = [k for k in INPUT_KEYS + ("vmr",) if s.buffers.get(k) is not None and (k != "vmr" or full(k))]
+        self.out_keys = [k for k in OUTPUT_KEYS if s.buffers.get(k) is not None]
+        if s.config.method == _lib.ALL_SKY_WITH_CLEAR:
+            self.out_keys += [k for k in s.buffers if k.startswith("clear_") and s.buffers[k] is not None]
+        self.host_in = {k: torch.empty_like(s.buffers[k], device="cpu").pin_memory() for k in self.in_keys}
+        self.host_out = {k: torch.empty_like(s.buffers[k], device="cpu").pin_memory() for k in self.out_keys}
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host_in.values())
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out.values())
+
+    def load_host_inputs(self, arrays) -> None:
+        alias = {"vmr_full": "vmr"}
+        for k, v in arrays.items():
+            k = alias.get(k, k)
+            if k in self.host_in:
+                self.host_in[k].copy_(torch.as_tensor(np.ascontiguousarray(v, dtype=self.s.dtype)))
+            elif k == "vmr" and self.s.config.vmr_kind == _lib.VMR_GM:
+                self.s.buffers["vmr"].copy_(torch.as_tensor(np.ascontiguousarray(v, dtype=self.s.dtype)))
+
+    def update_fluxes(self, seedval: int = 0) -> None:
+        """One end-to-end step; returns after the results are in `self.host_out` (pinned host tensors)."""
+        s = self.s
+        cur = torch.cuda.current_stream(s.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        for i, (a, n) in enumerate(self.chunks):
+            st = self.streams[i % len(self.streams)]
+            with torch.cuda.stream(st):
+                for k in self.in_keys:
+                    s.buffers[k][a:a + n].copy_(self.host_in[k][a:a + n], non_blocking=True)
+                update_fluxes_range(s, seedval, a, n, st)
+                for k in self.out_keys:
+                    self.host_out[k][a:a + n].copy_(s.buffers[k][a:a + n], non_blocking=True)
+        for st in self.streams:
+            st.synchronize()
+
+
 def prepare_atmosphere(s: RRTMGPSolver) -> None:
     check(lib().rrtmgp_b200_prepare_atmosphere(s._h, s._stream()), s._h)
 

@@ -259,3 +259,29 @@ def test_constructor_guards(real_pack):
     with pytest.raises(R.RRTMGPB200Error):   # nlev > 96 is outside the kernel's register tiling
         R.RRTMGPSolver(R.RRTMGPGridParams(FT=np.float32, domain_nlay=120, ncol=4), R.ClearSkyRadiation(),
                        R.default_parameters(), real_pack)
+
+
+def test_column_range_and_host_pipeline_match_full_call(real_pack):
+    """Any partition of the columns gives bit-identical results (columns are independent); the pipelined
+    host-buffer path (H2D -> update_fluxes_range -> D2H per chunk) returns the same fluxes."""
+    import torch
+    from helpers import make_solver
+    st = R.synthetic.make_atmosphere(700, 64, cld_frac=None, cos_zenith=None)
+    s = make_solver(real_pack, st, np.float32, method="all_sky", aerosols=True)
+    R.update_fluxes(s, 31)
+    torch.cuda.synchronize()
+    full = {k: s.buffers[k].clone() for k in R.solver.OUTPUT_KEYS}
+    s2 = make_solver(real_pack, st, np.float32, method="all_sky", aerosols=True)
+    for a, n in ((0, 100), (100, 333), (433, 267)):
+        R.update_fluxes_range(s2, 31, a, n)
+    torch.cuda.synchronize()
+    for k, v in full.items():
+        assert torch.equal(v, s2.buffers[k]), k
+    s3 = make_solver(real_pack, st, np.float32, method="all_sky", aerosols=True)
+    pipe = R.HostPipeline(s3, n_chunks=5)
+    pipe.load_host_inputs(st)
+    pipe.update_fluxes(31)
+    for k, v in full.items():
+        assert torch.equal(v.cpu(), pipe.host_out[k]), k
+    with pytest.raises(R.RRTMGPB200Error):
+        R.update_fluxes_range(s2, 31, 650, 100)
