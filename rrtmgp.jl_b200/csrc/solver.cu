@@ -42,17 +42,18 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
 // Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
 static int plan_smem_fast(SolveParams<float>& P, FastSmem& F) {
     const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
+    const int nrec = nlay < 32 ? nlay : 32;                    // band records cover half a column at a time
     P.rec_words = 4 + 4 * P.lut.n_minor_groups + 6;
     int off = 0;
     P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
     P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(float), 16);
-    P.off_recj = off; off = align_up(off + nlay * maxb * (int)sizeof(int), 16);
-    P.off_rec = off;  off = align_up(off + nlay * maxb * P.rec_words * (int)sizeof(float), 16);
+    P.off_recj = off; off = align_up(off + nrec * maxb * (int)sizeof(int), 16);
+    P.off_rec = off;  off = align_up(off + nrec * maxb * P.rec_words * (int)sizeof(float), 16);
     P.off_plk = off;  off = align_up(off + maxb * 2 * nlev * (int)sizeof(float), 16);
     P.off_store = off;
     const int n_hi = (nlay > kAlphaTmemLevels ? nlay - kAlphaTmemLevels : 0) + 1;   // + dummy slot
     F.off_alpha = off; off = align_up(off + n_hi * 32 * (int)sizeof(float), 128);
-    F.off_stage = off; off = align_up(off + 32 * kStageStride * (int)sizeof(float), 16);
+    F.off_stage = off; off = align_up(off + 16 * kStageStride * (int)sizeof(float), 16);
     F.off_acc = off;   off = align_up(off + 3 * kAccStride * (int)sizeof(float), 128);
     P.warp_bytes = off;
     return off;

@@ -287,14 +287,17 @@ struct Warp {
 
     // ---------------- phase 1: band records of this block ----------------
     // returns this lane's partial (aod_ext, aod_sca) of the 550 nm band if it is in the block
-    __device__ __forceinline__ void phase1(FT& aod_e, FT& aod_s) {
+    // `half` >= 0 (fast kernels): only the layers [32 half, 32 half + 32) and records indexed by (k & 31),
+    // so the band records of half a column fit in 3.6 KB; `half` < 0: all layers
+    __device__ __forceinline__ void phase1(FT& aod_e, FT& aod_s, int half = -1) {
         const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
         const int n_eta = L.n_eta;
         aod_e = aod_s = FT(0);
 #pragma unroll
         for (int j = 0; j < NOWN; ++j) {
             const int k = lane + 32 * j;
-            if (k >= nlay) continue;
+            if (k >= nlay || (half >= 0 && j != half)) continue;
+            const int kr = half >= 0 ? lane : k;   // record row
             const int cj = colj[k];
             const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
             const FT col_dry = colp[4 * k + 2];
@@ -302,7 +305,7 @@ struct Warp {
             const FT dry_fact = hdiv(FT(1), FT(1) + vmr_h2o);
             for (int b = 0; b < nb; ++b) {
                 const int ib = b_first + b;
-                FT* r = rec + ((size_t)k * maxb + b) * RW;
+                FT* r = rec + ((size_t)kr * maxb + b) * RW;
                 // gas_optics.jl:129-170
                 const int ig1 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib));
                 const int ig2 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib) + 1);
@@ -397,7 +400,7 @@ struct Warp {
                     if (use_cloud) { rc[0] = tc; rc[1] = sc; rc[2] = gc; }
                     if (use_aero) { rc[3] = ta; rc[4] = sa; rc[5] = ga; }
                 }
-                recj[k * maxb + b] = FUSED ? (((je[0] - 1) * L.n_gpt) | (((je[1] - 1) * L.n_gpt) << 16))   // eta offsets
+                recj[kr * maxb + b] = FUSED ? (((je[0] - 1) * L.n_gpt) | (((je[1] - 1) * L.n_gpt) << 16))   // eta offsets
                                            : (je[0] | (je[1] << 4) | (nmin << 8));
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {

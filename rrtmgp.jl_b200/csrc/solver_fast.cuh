@@ -131,15 +131,26 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
         for (int g0 = 0; g0 < NGPT; g0 += 32) {
             W.set_block(g0);
             __syncwarp();
-            FT aod_e, aod_s;
-            W.phase1(aod_e, aod_s);
-            if (!LW && HAS_AER && P.io.aod_ext != nullptr && P.aero.iband_550nm >= W.b_first + 1 &&
-                P.aero.iband_550nm <= W.b_first + W.nb) {
-                aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
-                if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
-            }
             if (HAS_CLD) n_cloudy += W.mcica(col_key, cld_start, cld_finish);
-            if (!day) continue;
+            // band records are built half a column (32 layers) at a time, just before the sweep needs them
+            FT aod_e = 0.f, aod_s = 0.f;
+            const bool aod_here = !LW && HAS_AER && P.io.aod_ext != nullptr && P.aero.iband_550nm >= W.b_first + 1 &&
+                                  P.aero.iband_550nm <= W.b_first + W.nb;
+            auto build_records = [&](int half) {
+                __syncwarp();
+                FT e, sc;
+                W.phase1(e, sc, half);
+                aod_e += e; aod_s += sc;
+            };
+            if (!day) {   // night: AOD and masks only (shortwave_2stream.jl:66-102)
+                if (aod_here) {
+                    build_records(0);
+                    if (nlay > 32) build_records(1);
+                    aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
+                    if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
+                }
+                continue;
+            }
 
             const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
             const FT on = W.lane_on ? 1.f : 0.f;
@@ -151,9 +162,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 const int jt = cj & 0xff, tr = (cj >> 16) & 1;
                 const float4 cp = reinterpret_cast<const float4*>(W.colp)[k];   // ft, fp, col_dry, major-table row offset
                 const FT ft = cp.x, fp = cp.y;
-                const int rj = W.recj[k * 2 + bl];
+                const int rj = W.recj[(k & 31) * 2 + bl];
                 const int e1 = rj & 0xffff, e2 = rj >> 16;                     // (je - 1) * NGPT
-                const FT* r = W.rec + (k * 2 + bl) * RW;
+                const FT* r = W.rec + ((k & 31) * 2 + bl) * RW;
                 const FT fe1 = r[0], fe2 = r[1];
                 const FT omft = 1.f - ft, omfp = 1.f - fp;
                 const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
@@ -240,48 +251,50 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             // transposed row sum of the staging tile: lane <-> row
             auto row_sum = [&]() -> FT {
                 FT s = 0.f;
-                const FT* row = stage + lane * kStageStride;   // stride 33: conflict-free, immediate offsets
+                const FT* row = stage + (lane & 15) * kStageStride;   // 16 rows, stride 33: conflict-free, immediate offsets
 #pragma unroll
                 for (int j = 0; j < 32; ++j) s += row[j];
                 return s;
             };
 
             if (LW) {
-                // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom)
+                // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom).
+                // Iteration k gathers layer k and finishes layer k-1 (its top-level source needs pfrac of layer k).
                 const FT* pbk = W.plk + bl * 2 * nlev;
                 const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
                 const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : 0.f;
+                build_records(0);
                 FT tau, ssa, g, pf;
                 optics(0, tau, ssa, g, pf);
                 FT lev_bot = pbk[0] * pf;
                 FT albedo = 1.f - emis;
                 FT src = Num<FT>::pi() * emis * (pbk[nlev + nlay] * pf);
-                for (int kc = 0; kc < nlay; kc += 32) {              // 32 levels per reduction tile
-                    const int kend = kc + 32 < nlay ? kc + 32 : nlay;
-                    for (int k = kc; k < kend; ++k) {
-                        FT tau_n, ssa_n, g_n, pf_n;
-                        const bool last = k + 1 >= nlay;
-                        optics(last ? k : k + 1, tau_n, ssa_n, g_n, pf_n);   // next layer (recomputed once at the top)
-                        const FT inc_k = pbk[k + 1] * pf;
-                        const FT lev_top = last ? inc_k : hsqrt(inc_k * (pbk[k + 1] * pf_n));
-                        FT Rdif, Tdif, su, sd;
-                        lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
-                        const FT denom = hdiv(1.f, 1.f - Rdif * albedo);
-                        // level k: F_dn(k) = A_k F_dn(k+1) + B_k ; F_up(k) = albedo_k F_dn(k) + src_k
-                        tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * src + sd) * denom);
-                        st_alpha(k, albedo);
-                        stage[(k - kc) * kStageStride + lane] = src * on;
-                        const FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
-                        src = su + Tdif * denom * (src + albedo * sd);
-                        albedo = albedo_n;
-                        lev_bot = lev_top; tau = tau_n; ssa = ssa_n; g = g_n; pf = pf_n;
-                    }
-                    __syncwarp();                                     // sum_g src_k for this tile
-                    {
+                for (int k = 1; k <= nlay; ++k) {
+                    if (k == 32) build_records(1);
+                    const bool has = k < nlay;
+                    FT tau_n, ssa_n, g_n, pf_n;
+                    optics(has ? k : nlay - 1, tau_n, ssa_n, g_n, pf_n);       // (recomputed once at the top)
+                    const FT inc_k = pbk[k] * pf;
+                    const FT lev_top = has ? hsqrt(inc_k * (pbk[k] * pf_n)) : inc_k;
+                    FT Rdif, Tdif, su, sd;
+                    lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
+                    const FT denom = hdiv(1.f, 1.f - Rdif * albedo);
+                    const int kl = k - 1;                                         // the layer / level being finished
+                    // level kl: F_dn(kl) = A F_dn(kl+1) + B ; F_up(kl) = albedo F_dn(kl) + src
+                    tmem_st2(tA + 2 * kl, Tdif * denom, (Rdif * src + sd) * denom);
+                    st_alpha(kl, albedo);
+                    stage[(kl & 15) * kStageStride + lane] = src * on;
+                    const FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
+                    src = su + Tdif * denom * (src + albedo * sd);
+                    albedo = albedo_n;
+                    lev_bot = lev_top; tau = tau_n; ssa = ssa_n; g = g_n; pf = pf_n;
+                    if ((kl & 15) == 15 || k == nlay) {                           // sum_g src for <= 16 levels
+                        __syncwarp();
+                        const int lev = (kl & ~15) + lane;
                         const FT sum = row_sum();
-                        if (kc + lane < kend) accs[UP * kAccStride + kc + lane] += sum;
+                        if (lane < 16 && lev <= kl) accs[UP * kAccStride + lev] += sum;
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
                 FT dn = inc;
                 {
@@ -293,8 +306,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 tmem_ld2(tA + 2 * (nlay - 1), A, B);
                 ld_alpha_t(nlay - 1, al);
                 tmem_wait_ld();
-                for (int kc = (nlay - 1) & ~15; kc >= 0; kc -= 16) {   // 16 levels x (dn, albedo * dn) per tile
-                    const int ktop = kc + 15 < nlay - 1 ? kc + 15 : nlay - 1;
+                for (int kc = (nlay - 1) & ~7; kc >= 0; kc -= 8) {     // 8 levels x (dn, albedo * dn) per tile
+                    const int ktop = kc + 7 < nlay - 1 ? kc + 7 : nlay - 1;
                     for (int k = ktop; k >= kc; --k) {
                         const FT Ak = A, Bk = B;
                         const FT alk = k < kAlphaTmemLevels ? al : ld_alpha_s(k);
@@ -310,7 +323,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     {
                         const int lev = kc + (lane >> 1);
                         const FT sum = row_sum();
-                        if (lev <= ktop) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += sum;
+                        if (lane < 16 && lev <= ktop) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += sum;
                     }
                     __syncwarp();
                 }
@@ -326,8 +339,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     FT sum = warp_sum(dir_top * on);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
                     if (lane == 0) { accs[DIR * kAccStride + nlay] += sum; accs[DN * kAccStride + nlay] += sum; }
                 }
-                for (int kc = (nlay - 1) & ~15; kc >= 0; kc -= 16) {   // 16 levels x (d_{k+1}, dir_k) per tile
-                    const int ktop = kc + 15 < nlay - 1 ? kc + 15 : nlay - 1;
+                build_records(nlay > 32 ? 1 : 0);
+                for (int kc = (nlay - 1) & ~7; kc >= 0; kc -= 8) {     // 8 levels x (d_{k+1}, dir_k) per tile
+                    if (kc == 24 && nlay > 32) build_records(0);
+                    const int ktop = kc + 7 < nlay - 1 ? kc + 7 : nlay - 1;
                     for (int k = ktop; k >= kc; --k) {
                         FT tau, ssa, g, pf;
                         optics(k, tau, ssa, g, pf);
@@ -349,13 +364,18 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     {
                         const int kk = kc + (lane >> 1);
                         const FT sum = row_sum();
+                        const bool ok = lane < 16 && kk <= ktop;
                         // d_{kk+1} (even lanes) and dir_kk (odd lanes) both feed F_dn: two ordered steps,
                         // never two lanes read-modify-writing one accumulator in the same instruction
-                        if (kk <= ktop && (lane & 1)) { accs[DN * kAccStride + kk] += sum; accs[DIR * kAccStride + kk] += sum; }
+                        if (ok && (lane & 1)) { accs[DN * kAccStride + kk] += sum; accs[DIR * kAccStride + kk] += sum; }
                         __syncwarp();
-                        if (kk <= ktop && !(lane & 1)) accs[DN * kAccStride + kk + 1] += sum;
+                        if (ok && !(lane & 1)) accs[DN * kAccStride + kk + 1] += sum;
                     }
                     __syncwarp();
+                }
+                if (aod_here) {
+                    aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
+                    if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
                 }
                 // surface: F_up(0) = alb_dif F_dn_dif(0) + alb_dir dir(0) ; F_dn_dif(0) = d_0 + beta_0 F_up(0)
                 FT up = hdiv(alb_dif * d + alb_dir * dir, 1.f - alb_dif * beta);
@@ -368,8 +388,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 tmem_ld2(tA, A, B);
                 ld_alpha_t(0, be);
                 tmem_wait_ld();
-                for (int kc = 0; kc < nlay; kc += 16) {               // 16 levels x (F_up, beta * F_up) per tile
-                    const int kend = kc + 16 < nlay ? kc + 16 : nlay;
+                for (int kc = 0; kc < nlay; kc += 8) {                // 8 levels x (F_up, beta * F_up) per tile
+                    const int kend = kc + 8 < nlay ? kc + 8 : nlay;
                     for (int k = kc; k < kend; ++k) {
                         const FT Ak = A, Bk = B;
                         const FT bek = k < kAlphaTmemLevels ? be : ld_alpha_s(k);
@@ -385,7 +405,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     {
                         const int kk = kc + (lane >> 1);
                         const FT sum = row_sum();
-                        if (kk < kend) accs[((lane & 1) ? DN : UP) * kAccStride + kk + 1] += sum;
+                        if (lane < 16 && kk < kend) accs[((lane & 1) ? DN : UP) * kAccStride + kk + 1] += sum;
                     }
                     __syncwarp();
                 }
