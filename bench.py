@@ -95,6 +95,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Host threads this process may use (affinity mask, not the machine total)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def make_state(ncol, nlay, rank):
     import rrtmgp_b200 as R
     return R.synthetic.make_atmosphere(ncol, nlay, seed=20260101 + rank, cld_frac=1.0, cos_zenith=0.86)
@@ -110,14 +118,14 @@ def run_reference(args, rank, world):
     pack = R.synthetic.make_lut_pack(seed=7)
     st = make_state(ncol_s, args.nlay, 0)
     o = Oracle(pack, np.float32)
+    cores = host_threads()   # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     for _ in range(args.warmup):
-        o.update_fluxes(st, seed=1, params=PARAMS)
+        o.update_fluxes(st, seed=1, params=PARAMS, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.update_fluxes(st, seed=1, params=PARAMS)
+        o.update_fluxes(st, seed=1, params=PARAMS, nthreads=cores)
     dt = (time.perf_counter() - t0) / args.steps
     v = ncol_s / dt
-    cores = os.cpu_count()
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "columns/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -268,11 +276,12 @@ def main():
         ncs = min(ncol, args.cpu_sample)
         sub = {k: (v[:ncs] if (v.ndim >= 1 and v.shape[0] == ncol) else v) for k, v in st.items()}
         o = Oracle(pack, np.float32)
-        o.update_fluxes(sub, seed=1, params=PARAMS)
+        cores = host_threads()
+        o.update_fluxes(sub, seed=1, params=PARAMS, nthreads=cores)
         t0 = time.perf_counter()
-        o.update_fluxes(sub, seed=1, params=PARAMS)
+        o.update_fluxes(sub, seed=1, params=PARAMS, nthreads=cores)
         dtc = time.perf_counter() - t0
-        cpu_baseline = {"value": ncs / dtc, "unit": "columns/s", "cores": os.cpu_count(), "kind": "port",
+        cpu_baseline = {"value": ncs / dtc, "unit": "columns/s", "cores": cores, "kind": "port",
                         "sample": f"first {ncs} of {ncol} columns, one update_fluxes (cost is linear in ncol); C++ "
                                   "restatement of the Julia reference CPU path, OpenMP over columns, Float32"}
 

@@ -536,7 +536,9 @@ template <typename FT, int MODE>
 __global__ void __launch_bounds__(256) solve_kernel(const SolveParams<FT> P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle: provably warp-uniform, so everything derived from it (column, shared
+    // memory bases, table descriptors) lives in uniform registers instead of being re-broadcast with R2UR
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int wpc = blockDim.x >> 5;
     const long long col = (long long)blockIdx.x * wpc + warp;
     if (col >= P.ncol) return;   // warp-uniform; no block-level barriers are used below

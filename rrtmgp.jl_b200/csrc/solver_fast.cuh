@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     constexpr int UP = 0, DN = 1, DIR = 2;
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle: provably warp-uniform, so everything derived from it (column, shared
+    // memory bases, table descriptors) lives in uniform registers instead of being re-broadcast with R2UR
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 
     if (warp == 0) tmem_alloc(&tmem_base_smem, 512u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
