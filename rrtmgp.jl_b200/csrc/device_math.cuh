@@ -172,6 +172,35 @@ __device__ __forceinline__ void lw_2stream_coeffs(FT tau, FT ssa, FT g, FT lev_s
     src_dn = tau > FT(0) ? sd : FT(0);
 }
 
+// longwave_2stream.jl:149-222 split for the fast kernels: everything that does not depend on the level sources
+// (so it overlaps the table gathers of the next layer), then the two sources from
+//   src_up = pi (B_top emis_fac - q dB),  src_dn = pi (B_bot emis_fac + q dB),  dB = B_bot - B_top,
+// with q = Tdif - [(1 - e1)/tau (k (1 - e1) + (g1 + g2)(1 + e1)) RT / max(g1 + g2, eps)]; both vanish for tau = 0.
+struct LwCoef { float Rdif, Tdif, emis_fac, q; };
+__device__ __forceinline__ LwCoef lw_2stream_coeffs_nosrc(float tau, float ssa, float g) {
+    const float lw_diff_sec = 1.66f;
+    const float g1 = lw_diff_sec * (1.f - 0.5f * ssa * (1.f + g));
+    const float g2 = lw_diff_sec * 0.5f * ssa * (1.f - g);
+    const float g_sum = g1 + g2;
+    const float k = hsqrt(rmax(lw_diff_sec * (1.f - ssa) * g_sum, Num<float>::k_min()));
+    const float tk = tau * k;
+    const float e1 = hexp(-tk);
+    const float om1 = h_one_minus_exp_neg(tk, e1);
+    const float one_p_e1 = 1.f + e1;
+    const float one_minus_e2kt = om1 * one_p_e1;
+    const float RT_term = hdiv(1.f, k * fmaf(e1, e1, 1.f) + g1 * one_minus_e2kt);
+    LwCoef c;
+    c.Rdif = RT_term * g2 * one_minus_e2kt;
+    c.Tdif = RT_term * 2.f * k * e1;
+    const float kom1 = k * om1;
+    const float ef = om1 * (kom1 + lw_diff_sec * (1.f - ssa) * one_p_e1) * RT_term;
+    const float dBfac = hdiv(hdiv(om1, tau) * (kom1 + g_sum * one_p_e1) * RT_term, rmax(g_sum, Num<float>::eps()));
+    const bool has = tau > 0.f;
+    c.emis_fac = has ? ef : 0.f;
+    c.q = has ? c.Tdif - dBfac : 0.f;
+    return c;
+}
+
 // ---- shortwave_2stream.jl:189-279 ----
 template <typename FT>
 __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, FT inv_mu0, FT& Rdir, FT& Tdir,

@@ -43,11 +43,12 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
 static int plan_smem_fast(SolveParams<float>& P, FastSmem& F) {
     const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
     const int nrec = nlay < 32 ? nlay : 32;                    // band records cover half a column at a time
-    P.rec_words = 4 + 4 * P.lut.n_minor_groups + 6;
+    // record = {fe1, fe2, s1, s2}, 4 slot scalings per group, {aerosol-only products, eta offsets}, {cloud+aerosol, eta offsets}
+    P.rec_words = 4 + 4 * P.lut.n_minor_groups + 8;
     int off = 0;
     P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
     P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(float), 16);
-    P.off_recj = off; off = align_up(off + nrec * maxb * (int)sizeof(int), 16);
+    P.off_recj = off;   // unused by the fast kernels (eta offsets travel in the record)
     P.off_rec = off;  off = align_up(off + nrec * maxb * P.rec_words * (int)sizeof(float), 16);
     P.off_plk = off;  off = align_up(off + maxb * 2 * nlev * (int)sizeof(float), 16);
     P.off_store = off;
@@ -68,13 +69,13 @@ static int sm_count_of_current_device() {
     return cached[dev] > 0 ? cached[dev] : 148;
 }
 
-template <int MODE, int NGPT, bool HAS_CLD, bool HAS_AER>
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER>
 static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
     FastSmem F;
     const int wb = plan_smem_fast(P, F);
     const size_t smem = (size_t)kFastWarps * wb;
     if ((int)smem > max_smem_optin) return -1;   // does not fit: generic kernel
-    auto kern = solve_kernel_fast<MODE, NGPT, HAS_CLD, HAS_AER>;
+    auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int need = (P.ncol + kFastWarps - 1) / kFastWarps;
@@ -84,13 +85,20 @@ static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t
     return (int)cudaGetLastError();
 }
 
+template <int MODE, int NGPT, int NG>
+static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
+    const bool c = P.use_cloud != 0, a = P.use_aero != 0;
+    if (c && a) return launch_fast_t<MODE, NGPT, NG, true, true>(P, max_smem_optin, s);
+    if (c) return launch_fast_t<MODE, NGPT, NG, true, false>(P, max_smem_optin, s);
+    if (a) return launch_fast_t<MODE, NGPT, NG, false, true>(P, max_smem_optin, s);
+    return launch_fast_t<MODE, NGPT, NG, false, false>(P, max_smem_optin, s);
+}
+
+// groups of four minor-absorber slots per band: 1 (synthetic pack) or 2 (up to 8 / 7 + Rayleigh, real tables)
 template <int MODE, int NGPT>
 static int launch_fast_flags(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
-    const bool c = P.use_cloud != 0, a = P.use_aero != 0;
-    if (c && a) return launch_fast_t<MODE, NGPT, true, true>(P, max_smem_optin, s);
-    if (c) return launch_fast_t<MODE, NGPT, true, false>(P, max_smem_optin, s);
-    if (a) return launch_fast_t<MODE, NGPT, false, true>(P, max_smem_optin, s);
-    return launch_fast_t<MODE, NGPT, false, false>(P, max_smem_optin, s);
+    return P.lut.n_minor_groups == 1 ? launch_fast_ng<MODE, NGPT, 1>(P, max_smem_optin, s)
+                                     : launch_fast_ng<MODE, NGPT, 2>(P, max_smem_optin, s);
 }
 
 // RRTMGP_B200_KERNEL=generic forces the shared-memory kernels of solver.cuh (experiments / A-B tests).

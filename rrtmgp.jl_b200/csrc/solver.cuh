@@ -114,49 +114,67 @@ template <typename FT> __device__ __forceinline__ int merra_size_bin(const FT* _
     return bin;
 }
 
-// Per-(column, layer) aerosol bookkeeping: which of the 15 species are present, the MERRA size
-// bin of the ten sized species (dust 1,8..11 then sea salt 2,12..15; 3 bits each) and the RH
-// interval (aerosol_optics.jl:141-235 hoisted out of the band loop).
-struct AeroLayer { unsigned active; unsigned bins; int rh_loc; };
+// Per-(column, layer) aerosol bookkeeping, hoisted out of the band loop (aerosol_optics.jl:141-235): `active` has
+// one bit per species present (mass > 0), in the ORDER the reference sums them -- positions 0-4 dust (species
+// 1, 8..11), 5-9 sea salt (2, 12..15), 10 sulfate, 11 BC-rh, 12 BC, 13 OC-rh, 14 OC -- `bins` the MERRA size bin
+// of the ten sized species (3 bits per position) and `rh_loc` the RH interval.  The usual input has one species
+// per layer, so the table row of the FIRST active species is resolved here once per layer: `off0` = element
+// offset from AeroLut::dust of its (bin, RH interval) row for band 0, `bs0` = band stride | rh-interpolated << 24
+// | 0-based species index << 25.
+struct AeroLayer { unsigned active; unsigned bins; int rh_loc; int off0; int bs0; };
 
-// aerosol_optics.jl:141-235 (+ species functions :243-431); ibnd 0-based
+__device__ __forceinline__ int aero_pos_of_species(int i) {   // 0-based species -> summation position
+    return i == 0 ? 0 : (i == 1 ? 5 : (i <= 6 ? i + 8 : (i <= 10 ? i - 6 : i - 5)));
+}
+
+// table row of the species at summation position `pos` (species functions aerosol_optics.jl:243-431)
+template <typename FT>
+__device__ __forceinline__ void aero_entry(const AeroLut<FT>& A, int pos, unsigned bins, int loc, int& off, int& bs) {
+    const int nrh = A.nrh, nbin = A.nbin;
+    if (pos < 5) {             // dust (3, nbin, nband)
+        const int bin = (int)((bins >> (3 * pos)) & 7u);
+        off = 3 * (bin - 1);
+        bs = (3 * nbin) | ((pos == 0 ? 0 : 6 + pos) << 25);
+    } else if (pos < 10) {     // sea salt (3, nrh, nbin, nband)
+        const int k = pos - 5;
+        const int bin = (int)((bins >> (3 * pos)) & 7u);
+        off = (int)(A.sea_salt - A.dust) + 3 * nrh * (bin - 1) + 3 * (loc - 1);
+        bs = (3 * nrh * nbin) | (1 << 24) | ((k == 0 ? 1 : 10 + k) << 25);
+    } else {
+        const FT* t = pos == 10 ? A.sulfate : (pos == 11 ? A.black_carbon_rh : (pos == 12 ? A.black_carbon
+                                : (pos == 13 ? A.organic_carbon_rh : A.organic_carbon)));
+        const bool rh = pos != 12 && pos != 14;
+        off = (int)(t - A.dust) + (rh ? 3 * (loc - 1) : 0);
+        bs = (rh ? (3 * nrh) | (1 << 24) : 3) | ((pos - 8) << 25);
+    }
+}
+
+// aerosol_optics.jl:141-235; ibnd 0-based.  Dry species read one (ext, ssa, asy) row, RH-dependent ones
+// interpolate between two adjacent rows; one branch-free form serves both (f_eff = 0, second row = first).
 template <typename FT>
 __device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, const FT* __restrict__ mass,
                                                const AeroLayer& al, FT f, FT& tc, FT& tsc, FT& tsgc) {
     tc = tsc = tsgc = FT(0);
-    const int nrh = A.nrh, nbin = A.nbin, loc = al.rh_loc;
-    auto rh_species = [&](const FT* __restrict__ t3, FT m) {   // t3 -> (3, nrh) slice
-        FT t = m * (__ldg(t3 + 3 * (loc - 1)) * (FT(1) - f) + __ldg(t3 + 3 * loc) * f);
-        FT ts = t * (__ldg(t3 + 3 * (loc - 1) + 1) * (FT(1) - f) + __ldg(t3 + 3 * loc + 1) * f);
-        FT tsg = ts * (__ldg(t3 + 3 * (loc - 1) + 2) * (FT(1) - f) + __ldg(t3 + 3 * loc + 2) * f);
+    auto species = [&](int off, int bs) {
+        const FT* __restrict__ p = A.dust + off + (size_t)(bs & 0xffffff) * ibnd;
+        const bool rh = (bs >> 24) & 1;
+        const int d = rh ? 3 : 0;
+        const FT fe = rh ? f : FT(0);
+        const FT m = __ldg(mass + (bs >> 25));
+        FT t = m * (__ldg(p) * (FT(1) - fe) + __ldg(p + d) * fe);
+        FT ts = t * (__ldg(p + 1) * (FT(1) - fe) + __ldg(p + d + 1) * fe);
+        FT tsg = ts * (__ldg(p + 2) * (FT(1) - fe) + __ldg(p + d + 2) * fe);
         tc += t; tsc += ts; tsgc += tsg;
     };
-    auto dry_species = [&](const FT* __restrict__ t3, FT m) {
-        FT t = m * __ldg(t3); FT ts = t * __ldg(t3 + 1); FT tsg = ts * __ldg(t3 + 2);
-        tc += t; tsc += ts; tsgc += tsg;
-    };
-    unsigned act = al.active;
-#pragma unroll 1
-    for (int k = 0; k < 5; ++k) {   // dust: species 1, 8..11
-        int i = k == 0 ? 0 : 6 + k;
-        if ((act >> i) & 1u) {
-            int bin = (int)((al.bins >> (3 * k)) & 7u);
-            dry_species(A.dust + 3 * ((bin - 1) + (size_t)nbin * ibnd), __ldg(mass + i));
-        }
+    species(al.off0, al.bs0);
+    unsigned rest = al.active & (al.active - 1u);
+    while (rest) {   // layers with several species: resolve the remaining rows here
+        const int pos = __ffs((int)rest) - 1;
+        rest &= rest - 1u;
+        int off, bs;
+        aero_entry(A, pos, al.bins, al.rh_loc, off, bs);
+        species(off, bs);
     }
-#pragma unroll 1
-    for (int k = 0; k < 5; ++k) {   // sea salt: species 2, 12..15
-        int i = k == 0 ? 1 : 10 + k;
-        if ((act >> i) & 1u) {
-            int bin = (int)((al.bins >> (15 + 3 * k)) & 7u);
-            rh_species(A.sea_salt + (size_t)3 * nrh * ((bin - 1) + (size_t)nbin * ibnd), __ldg(mass + i));
-        }
-    }
-    if ((act >> 2) & 1u) rh_species(A.sulfate + (size_t)3 * nrh * ibnd, __ldg(mass + 2));
-    if ((act >> 3) & 1u) rh_species(A.black_carbon_rh + (size_t)3 * nrh * ibnd, __ldg(mass + 3));
-    if ((act >> 4) & 1u) dry_species(A.black_carbon + 3 * ibnd, __ldg(mass + 4));
-    if ((act >> 5) & 1u) rh_species(A.organic_carbon_rh + (size_t)3 * nrh * ibnd, __ldg(mass + 5));
-    if ((act >> 6) & 1u) dry_species(A.organic_carbon + 3 * ibnd, __ldg(mass + 6));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -180,7 +198,7 @@ struct Warp {
     FT* plk;     // LW: [maxb][2*nlev] B(t_lev) | B(t_lay) (noscat) | B(t_sfc)
     const int RW, maxb;
     // per-lane registers for the layers this lane owns in phase 0/1: lane, lane+32, lane+64
-    FT own_h2o[NOWN], own_dens[NOWN];
+    FT own_h2o[NOWN], own_dens[NOWN], own_cdry[NOWN];
     AeroLayer own_aero[NOWN];
     FT own_rh_f[NOWN];
     int own_cld[NOWN];          // loc_liq | loc_ice << 8 | cloudy << 16
@@ -207,7 +225,7 @@ struct Warp {
 #pragma unroll
         for (int j = 0; j < NOWN; ++j) {
             const int k = lane + 32 * j;
-            own_h2o[j] = FT(0); own_dens[j] = FT(0); own_aero[j] = AeroLayer{0u, 0u, 1}; own_rh_f[j] = FT(0);
+            own_h2o[j] = FT(0); own_dens[j] = FT(0); own_cdry[j] = FT(0); own_aero[j] = AeroLayer{0u, 0u, 1, 0, 0}; own_rh_f[j] = FT(0);
             own_cld[j] = 0; own_cld_fl[j] = own_cld_fi[j] = FT(0);
             own_pl_loc[j] = own_py_loc[j] = 0; own_pl_f[j] = own_py_f[j] = FT(0);
             if (k >= nlay) continue;
@@ -225,23 +243,24 @@ struct Warp {
             int jp = jpress + tropo - 1;
             FT h2o = get_vmr(P, L.idx_h2o, k, col);
             own_h2o[j] = h2o;
+            own_cdry[j] = col_dry;
             own_dens[j] = hdiv(FT(0.01) * p_lay, t_lay);
             int aero_on = 0;
             if (use_aero) {   // aerosol_optics.jl:464-483, :438-451, optics_utils.jl:51-62
                 const FT* am = P.io.aero_mass + ((size_t)col * nlay + k) * 15;
                 const FT* as = P.io.aero_size + ((size_t)col * nlay + k) * 15;
                 unsigned act = 0u, bins = 0u;
-                for (int i = 0; i < 15; ++i) act |= (__ldg(am + i) > FT(0)) ? (1u << i) : 0u;
+                for (int i = 0; i < 15; ++i) act |= (__ldg(am + i) > FT(0)) ? (1u << aero_pos_of_species(i)) : 0u;
                 if (act) {
-                    for (int s = 0; s < 5; ++s) {
-                        int i = s == 0 ? 0 : 6 + s;
-                        if ((act >> i) & 1u) bins |= (unsigned)merra_size_bin(P.aero.size_bin_limits, P.aero.nbin, __ldg(as + i)) << (3 * s);
-                        i = s == 0 ? 1 : 10 + s;
-                        if ((act >> i) & 1u) bins |= (unsigned)merra_size_bin(P.aero.size_bin_limits, P.aero.nbin, __ldg(as + i)) << (15 + 3 * s);
+                    for (int pos = 0; pos < 10; ++pos) {   // sized species: dust 1, 8..11 then sea salt 2, 12..15
+                        const int i = pos < 5 ? (pos == 0 ? 0 : 6 + pos) : (pos == 5 ? 1 : 5 + pos);
+                        if ((act >> pos) & 1u) bins |= (unsigned)merra_size_bin(P.aero.size_bin_limits, P.aero.nbin, __ldg(as + i)) << (3 * pos);
                     }
                     int loc; FT f;
                     interp1d_loc_factor(__ldg(ld + 4 * k + 3), P.aero.rh_levels, P.aero.nrh, loc, f);
-                    own_aero[j] = AeroLayer{act, bins, loc};
+                    int off0, bs0;
+                    aero_entry(P.aero, __ffs((int)act) - 1, bins, loc, off0, bs0);
+                    own_aero[j] = AeroLayer{act, bins, loc, off0, bs0};
                     own_rh_f[j] = f;
                     aero_on = 1;
                 }
@@ -262,9 +281,17 @@ struct Warp {
                 if (NOSCAT) interp1d_eq_locate(t_lay, L.t_planck, L.n_t_plnk, own_py_loc[j], own_py_f[j]);
             }
             colj[k] = jt | (jp << 8) | ((tropo - 1) << 16) | (aero_on << 17);
-            colp[4 * k + 0] = ft; colp[4 * k + 1] = fp; colp[4 * k + 2] = col_dry;
-            // fast kernels: element offset of the (jp-1, jt) node row of the major table instead of vmr_h2o + 1
-            colp[4 * k + 3] = FUSED ? int_as_ft<FT>(((jp - 2) * n_t + (jt - 1)) * L.n_eta * L.n_gpt) : h2o + FT(1);
+            colp[4 * k + 0] = ft; colp[4 * k + 1] = fp;
+            if (FUSED) {
+                // fast kernels: element offsets of the (jt) node row of the packed minor table (float4 units, both
+                // tropospheres in one arena) and of the (jp-1, jt) node row of the major table
+                const int tr_off = tropo == 2 ? (int)((L.kminor4[1] - L.kminor4[0]) >> 2) : 0;
+                colp[4 * k + 2] = int_as_ft<FT>(tr_off + (jt - 1) * L.n_eta * L.n_gpt);
+                colp[4 * k + 3] = int_as_ft<FT>(((jp - 2) * n_t + (jt - 1)) * L.n_eta * L.n_gpt);
+            } else {
+                colp[4 * k + 2] = col_dry;
+                colp[4 * k + 3] = h2o + FT(1);
+            }
         }
         p0_loc = psfc_loc = 0; p0_f = psfc_f = FT(0);
         if (LW && lane == 0) {
@@ -300,7 +327,7 @@ struct Warp {
             const int kr = half >= 0 ? lane : k;   // record row
             const int cj = colj[k];
             const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
-            const FT col_dry = colp[4 * k + 2];
+            const FT col_dry = own_cdry[j];
             const FT vmr_h2o = own_h2o[j];
             const FT dry_fact = hdiv(FT(1), FT(1) + vmr_h2o);
             for (int b = 0; b < nb; ++b) {
@@ -392,16 +419,17 @@ struct Warp {
                 }
                 if (FUSED) {
                     // increment_2stream (optics_utils.jl:189-202) is additive in (tau, tau ssa, tau ssa g):
-                    // store those products for "aerosol only" and "cloud + aerosol"; one increment per lane
+                    // store those products for "aerosol only" and "cloud + aerosol" as two 16-byte groups whose
+                    // fourth word is the pair of eta offsets, so a cell needs one 128-bit load for both
                     const FT a0 = ta, a1 = ta * sa, a2 = ta * sa * ga;
-                    rc[0] = a0; rc[1] = a1; rc[2] = a2;
-                    rc[3] = a0 + tc; rc[4] = a1 + tc * sc; rc[5] = a2 + tc * sc * gc;
+                    const FT rj = int_as_ft<FT>(((je[0] - 1) * L.n_gpt) | (((je[1] - 1) * L.n_gpt) << 16));
+                    rc[0] = a0; rc[1] = a1; rc[2] = a2; rc[3] = rj;
+                    rc[4] = a0 + tc; rc[5] = a1 + tc * sc; rc[6] = a2 + tc * sc * gc; rc[7] = rj;
                 } else {
                     if (use_cloud) { rc[0] = tc; rc[1] = sc; rc[2] = gc; }
                     if (use_aero) { rc[3] = ta; rc[4] = sa; rc[5] = ga; }
+                    recj[kr * maxb + b] = je[0] | (je[1] << 4) | (nmin << 8);
                 }
-                recj[kr * maxb + b] = FUSED ? (((je[0] - 1) * L.n_gpt) | (((je[1] - 1) * L.n_gpt) << 16))   // eta offsets
-                                           : (je[0] | (je[1] << 4) | (nmin << 8));
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {
                     const FT* totplnk = L.tot_planck + (size_t)L.n_t_plnk * ib;

@@ -52,34 +52,34 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& a) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-#ifdef RB_TEST_NO_TMEM   // SASS experiments only
-#define tmem_alloc(a, b) (*(a) = 0)
-#define tmem_dealloc(a, b)
-#define tmem_st2(t, a, b) (stage[(t) & 1023] = (a) + (b))
-#define tmem_st1(t, a) (stage[(t) & 1023] = (a))
-#define tmem_ld2(t, a, b) (a = stage[(t) & 1023], b = a)
-#define tmem_ld1(t, a) (a = stage[(t) & 1023])
-#define tmem_wait_ld()
-#define tmem_wait_st()
-#endif
-
 constexpr int kFastWarps = 12;        // warps per CTA = per SM
 constexpr int kFastColsPerWarp = 170; // TMEM columns per warp (3 warps share the 512 columns of a lane quadrant)
 constexpr int kAlphaTmemLevels = kFastColsPerWarp - 128 - 1;   // 41 albedos in TMEM (+1 dummy column), the rest in shared memory
-constexpr int kStageStride = 33;     // padded row stride of the staging tile
+constexpr int kStageStride = 36;      // staging-tile row stride: 16-byte aligned rows, conflict-free 128-bit row reads
 constexpr int kAccStride = 68;        // per-quantity stride of the shared broadband accumulators
-constexpr int kFastMaxMinor = 8;
 
 struct FastSmem {   // byte offsets from the warp's base, extending SolveParams' layout
     int off_alpha, off_stage, off_acc;
 };
 
-template <int MODE, int NGPT, bool HAS_CLD, bool HAS_AER>
+// Raw table corners and band-record words of one (layer, g-point) cell: the loads are issued together
+// (fast_gather) and consumed later (fast_finish), with independent arithmetic of the previous layer in between.
+template <bool LW, int NG> struct FastCell {
+    float2 c2[LW ? 8 : 1];   // LW: {kmajor, planck_fraction} corners
+    float c1[LW ? 1 : 8];    // SW: kmajor corners
+    float4 m[4 * NG];        // per group: four minor-absorber slots (SW slot 0 = Rayleigh) at the four (T, eta) corners
+    float4 r0, x;            // band record: {fe1, fe2, s1, s2}, increment products
+    float4 r1[NG];           // slot scalings
+    float ft, fp;
+};
+
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER>
 __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const SolveParams<float> P, const FastSmem F) {
     using FT = float;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_smem;
     constexpr bool LW = MODE == MODE_LW_2STREAM;
+    constexpr bool INCR = HAS_CLD || HAS_AER;
     constexpr int NETA = 9, NT = 14;
     constexpr int KE = NGPT, KT = NETA * KE, KP = NT * KT;           // major-table strides (LW: in float2): eta, T, p
     constexpr int ME = NGPT, MT = NETA * NGPT, MS = NT * MT;         // minor-table strides in float4: eta, T, group
@@ -99,14 +99,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     const uint32_t tAl = tA + 128u;
 
     unsigned char* wbase = smem_raw + (size_t)warp * P.warp_bytes;
-    FT* alpha_hi = reinterpret_cast<FT*>(wbase + F.off_alpha);   // [nlay - 42][32]
-    FT* stage = reinterpret_cast<FT*>(wbase + F.off_stage);      // [32][32]
+    FT* alpha_hi = reinterpret_cast<FT*>(wbase + F.off_alpha);   // [nlay - 41 + 1][32]
+    FT* stage = reinterpret_cast<FT*>(wbase + F.off_stage);      // [16][kStageStride]
     FT* accs = reinterpret_cast<FT*>(wbase + F.off_acc);         // [3][kAccStride]
     const GasLut<FT>& L = P.lut;
     const int nlay = P.nlay, nlev = nlay + 1;
     const FT* major = LW ? L.kmaj_pf : L.kmajor;
+    const float4* minor4 = reinterpret_cast<const float4*>(L.kminor4[0]);
     const int RW = P.rec_words;
-    const int n_groups = L.n_minor_groups;
 
     for (long long col = (long long)blockIdx.x * kFastWarps + warp; col < P.ncol; col += (long long)gridDim.x * kFastWarps) {
         Warp<FT, MODE, 2, true> W(P, wbase, lane, col);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
         int n_cloudy = 0;
         __syncwarp();
 
-        for (int g0 = 0; g0 < NGPT; g0 += 32) {
+        for (int g0 = 0; g0 < NGPT; g0 += 32) {   // NGPT is a multiple of 32: every lane owns a g-point
             W.set_block(g0);
             __syncwarp();
             if (HAS_CLD) n_cloudy += W.mcica(col_key, cld_start, cld_finish);
@@ -155,70 +155,79 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             }
 
             const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
-            const FT on = W.lane_on ? 1.f : 0.f;
+            const FT* rec_lane = W.rec + bl * RW;          // this lane's band within a record row pair
+            const unsigned mask0 = W.mask[0], mask1 = W.mask[1];
 
-            // ---- gas + cloud + aerosol optics of layer k: compile-time strides, 64/128-bit gathers ----
-            // gas_optics.jl:176-320 with the (layer, band) work read from the band record
-            auto optics = [&](int k, FT& tau, FT& ssa, FT& g, FT& pfrac) {
-                const int cj = W.colj[k];
-                const int jt = cj & 0xff, tr = (cj >> 16) & 1;
-                const float4 cp = reinterpret_cast<const float4*>(W.colp)[k];   // ft, fp, col_dry, major-table row offset
-                const FT ft = cp.x, fp = cp.y;
-                const int rj = W.recj[(k & 31) * 2 + bl];
-                const int e1 = rj & 0xffff, e2 = rj >> 16;                     // (je - 1) * NGPT
-                const FT* r = W.rec + ((k & 31) * 2 + bl) * RW;
-                const FT fe1 = r[0], fe2 = r[1];
-                const FT omft = 1.f - ft, omfp = 1.f - fp;
-                const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
-                const int ia = __float_as_int(cp.w) + e1 + gpt;               // (jp-1, jt,   je1)
-                const int ib = __float_as_int(cp.w) + KT + e2 + gpt;          // (jp-1, jt+1, je2)
+            // ---- issue every load of cell (layer k, this g-point): compile-time strides, 64/128-bit gathers ----
+            auto gather = [&](int k, FastCell<LW, NG>& G) {
+                const float4 cp = reinterpret_cast<const float4*>(W.colp)[k];   // ft, fp, minor row, major row
+                const FT* r = rec_lane + (k & 31) * 2 * RW;
+                bool cb = false;
+                if (HAS_CLD) cb = ((k < 32 ? mask0 : mask1) >> (k & 31)) & 1u;
+                G.r0 = *reinterpret_cast<const float4*>(r);
+                G.x = *reinterpret_cast<const float4*>(r + 4 + 4 * NG + (cb ? 4 : 0));
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) G.r1[gi] = *reinterpret_cast<const float4*>(r + 4 + 4 * gi);
+                G.ft = cp.x; G.fp = cp.y;
+                const int rj = __float_as_int(G.x.w);
+                const int e1 = (rj & 0xffff) + gpt, e2 = (rj >> 16) + gpt;     // (je - 1) * NGPT + gpt
+                const int ia = __float_as_int(cp.w) + e1;                       // (jp-1, jt,   je1)
+                const int ib = __float_as_int(cp.w) + KT + e2;                  // (jp-1, jt+1, je2)
                 if (LW) {   // {kmajor, planck_fraction} pairs
                     const float2* pa = reinterpret_cast<const float2*>(major) + ia;
                     const float2* pb = reinterpret_cast<const float2*>(major) + ib;
-                    const float2 c000 = __ldg(pa), c100 = __ldg(pa + KE), c010 = __ldg(pa + KP), c110 = __ldg(pa + KP + KE);
-                    const float2 c001 = __ldg(pb), c101 = __ldg(pb + KE), c011 = __ldg(pb + KP), c111 = __ldg(pb + KP + KE);
-                    const FT ka0 = fmaf(fe1, c100.x - c000.x, c000.x), ka1 = fmaf(fe1, c110.x - c010.x, c010.x);
-                    const FT kb0 = fmaf(fe2, c101.x - c001.x, c001.x), kb1 = fmaf(fe2, c111.x - c011.x, c011.x);
-                    tau = r[2] * (wa0 * ka0 + wa1 * ka1) + r[3] * (wb0 * kb0 + wb1 * kb1);
-                    const FT pa0 = fmaf(fe1, c100.y - c000.y, c000.y), pa1 = fmaf(fe1, c110.y - c010.y, c010.y);
-                    const FT pb0 = fmaf(fe2, c101.y - c001.y, c001.y), pb1 = fmaf(fe2, c111.y - c011.y, c011.y);
-                    pfrac = (wa0 * pa0 + wa1 * pa1) + (wb0 * pb0 + wb1 * pb1);
+                    G.c2[0] = __ldg(pa); G.c2[1] = __ldg(pa + KE); G.c2[2] = __ldg(pa + KP); G.c2[3] = __ldg(pa + KP + KE);
+                    G.c2[4] = __ldg(pb); G.c2[5] = __ldg(pb + KE); G.c2[6] = __ldg(pb + KP); G.c2[7] = __ldg(pb + KP + KE);
                 } else {
                     const FT* pa = major + ia;
                     const FT* pb = major + ib;
-                    const FT c000 = __ldg(pa), c100 = __ldg(pa + KE), c010 = __ldg(pa + KP), c110 = __ldg(pa + KP + KE);
-                    const FT c001 = __ldg(pb), c101 = __ldg(pb + KE), c011 = __ldg(pb + KP), c111 = __ldg(pb + KP + KE);
-                    const FT ka0 = fmaf(fe1, c100 - c000, c000), ka1 = fmaf(fe1, c110 - c010, c010);
-                    const FT kb0 = fmaf(fe2, c101 - c001, c001), kb1 = fmaf(fe2, c111 - c011, c011);
-                    tau = r[2] * (wa0 * ka0 + wa1 * ka1) + r[3] * (wb0 * kb0 + wb1 * kb1);
+                    G.c1[0] = __ldg(pa); G.c1[1] = __ldg(pa + KE); G.c1[2] = __ldg(pa + KP); G.c1[3] = __ldg(pa + KP + KE);
+                    G.c1[4] = __ldg(pb); G.c1[5] = __ldg(pb + KE); G.c1[6] = __ldg(pb + KP); G.c1[7] = __ldg(pb + KP + KE);
+                }
+                const float4* ma = minor4 + (__float_as_int(cp.z) + e1);        // (jt,   je1)
+                const float4* mb = minor4 + (__float_as_int(cp.z) + MT + e2);   // (jt+1, je2)
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {
+                    G.m[4 * gi + 0] = __ldg(ma + gi * MS); G.m[4 * gi + 1] = __ldg(ma + gi * MS + ME);
+                    G.m[4 * gi + 2] = __ldg(mb + gi * MS); G.m[4 * gi + 3] = __ldg(mb + gi * MS + ME);
+                }
+            };
+            // ---- gas + cloud + aerosol optics of the gathered cell (gas_optics.jl:176-320, optics_utils.jl:85-181) ----
+            auto finish = [&](int k, const FastCell<LW, NG>& G, FT& tau, FT& ssa, FT& g, FT& pfrac) {
+                const FT ft = G.ft, fp = G.fp, fe1 = G.r0.x, fe2 = G.r0.y;
+                const FT omft = 1.f - ft, omfp = 1.f - fp;
+                const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
+                if (LW) {
+                    const float2 *c = G.c2;
+                    const FT ka0 = fmaf(fe1, c[1].x - c[0].x, c[0].x), ka1 = fmaf(fe1, c[3].x - c[2].x, c[2].x);
+                    const FT kb0 = fmaf(fe2, c[5].x - c[4].x, c[4].x), kb1 = fmaf(fe2, c[7].x - c[6].x, c[6].x);
+                    tau = G.r0.z * (wa0 * ka0 + wa1 * ka1) + G.r0.w * (wb0 * kb0 + wb1 * kb1);
+                    const FT pa0 = fmaf(fe1, c[1].y - c[0].y, c[0].y), pa1 = fmaf(fe1, c[3].y - c[2].y, c[2].y);
+                    const FT pb0 = fmaf(fe2, c[5].y - c[4].y, c[4].y), pb1 = fmaf(fe2, c[7].y - c[6].y, c[6].y);
+                    pfrac = (wa0 * pa0 + wa1 * pa1) + (wb0 * pb0 + wb1 * pb1);
+                } else {
+                    const FT* c = G.c1;
+                    const FT ka0 = fmaf(fe1, c[1] - c[0], c[0]), ka1 = fmaf(fe1, c[3] - c[2], c[2]);
+                    const FT kb0 = fmaf(fe2, c[5] - c[4], c[4]), kb1 = fmaf(fe2, c[7] - c[6], c[6]);
+                    tau = G.r0.z * (wa0 * ka0 + wa1 * ka1) + G.r0.w * (wb0 * kb0 + wb1 * kb1);
                     pfrac = 0.f;
                 }
                 // minor absorbers (+ Rayleigh in SW slot 0): four slots per 128-bit load (optics_utils.jl:85-98)
                 const FT w11 = (1.f - fe1) * omft, w21 = fe1 * omft, w12 = (1.f - fe2) * ft, w22 = fe2 * ft;
-                const float4* ma = reinterpret_cast<const float4*>(L.kminor4[tr]) + ((jt - 1) * MT + e1 + gpt);
-                const float4* mb = reinterpret_cast<const float4*>(L.kminor4[tr]) + (jt * MT + e2 + gpt);
                 FT tau_ray = 0.f;
-                {
-                    const float4 m11 = __ldg(ma), m21 = __ldg(ma + ME), m12 = __ldg(mb), m22 = __ldg(mb + ME);
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {   // real tables can have more than four (three in SW) minors per band
+                    const float4 m11 = G.m[4 * gi], m21 = G.m[4 * gi + 1], m12 = G.m[4 * gi + 2], m22 = G.m[4 * gi + 3];
+                    const float4 sc = G.r1[gi];
                     const FT v0 = w11 * m11.x + w21 * m21.x + w12 * m12.x + w22 * m22.x;
                     const FT v1 = w11 * m11.y + w21 * m21.y + w12 * m12.y + w22 * m22.y;
                     const FT v2 = w11 * m11.z + w21 * m21.z + w12 * m12.z + w22 * m22.z;
                     const FT v3 = w11 * m11.w + w21 * m21.w + w12 * m12.w + w22 * m22.w;
-                    if (LW) {
-                        tau += v0 * r[4] + v1 * r[5] + v2 * r[6] + v3 * r[7];
+                    if (!LW && gi == 0) {
+                        tau_ray = v0 * sc.x;
+                        tau += v1 * sc.y + v2 * sc.z + v3 * sc.w;
                     } else {
-                        tau_ray = v0 * r[4];
-                        tau += v1 * r[5] + v2 * r[6] + v3 * r[7];
-                    }
-                }
-                if (n_groups > 1) {   // warp-uniform; real tables with more than four (three in SW) minors per band
-                    for (int gi = 1; gi < n_groups; ++gi) {
-                        const float4 m11 = __ldg(ma + gi * MS), m21 = __ldg(ma + gi * MS + ME), m12 = __ldg(mb + gi * MS), m22 = __ldg(mb + gi * MS + ME);
-                        const FT* sc = r + 4 + 4 * gi;
-                        tau += (w11 * m11.x + w21 * m21.x + w12 * m12.x + w22 * m22.x) * sc[0] +
-                               (w11 * m11.y + w21 * m21.y + w12 * m12.y + w22 * m22.y) * sc[1] +
-                               (w11 * m11.z + w21 * m21.z + w12 * m12.z + w22 * m22.z) * sc[2] +
-                               (w11 * m11.w + w21 * m21.w + w12 * m12.w + w22 * m22.w) * sc[3];
+                        tau += v0 * sc.x + v1 * sc.y + v2 * sc.z + v3 * sc.w;
                     }
                 }
                 if (LW) {
@@ -229,14 +238,12 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     ssa = tau > 0.f ? hdiv(tau_ray, tau) : 0.f;
                     g = 0.f;
                 }
-                // one fused increment (optics_utils.jl:189-202 is additive in tau, tau ssa, tau ssa g)
-                const bool cb = HAS_CLD && W.mask_bit(k);
-                const bool ab = HAS_AER && ((cj >> 17) & 1);
-                if (cb || ab) {
-                    const FT* x = r + 4 + 4 * n_groups + (cb ? 3 : 0);
-                    const FT tn = tau + x[0];
-                    const FT w = tau * ssa + x[1];
-                    const FT h = tau * ssa * g + x[2];
+                // one fused, unconditional increment (optics_utils.jl:189-202 is additive in tau, tau ssa, tau ssa g;
+                // the record holds zeros where neither cloud nor aerosol is present)
+                if (INCR) {
+                    const FT tn = tau + G.x.x;
+                    const FT w = LW ? G.x.y : tau * ssa + G.x.y;       // LW gas: ssa = 0
+                    const FT h = G.x.z;                                  // gas: g = 0 in both
                     g = hdiv(h, rmax(FLT_EPSILON, w));
                     ssa = hdiv(w, rmax(FLT_EPSILON, tn));
                     tau = tn;
@@ -250,15 +257,16 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             };
             auto ld_alpha_t = [&](int k, FT& v) { tmem_ld1(tAl + (k < kAlphaTmemLevels ? k : kAlphaTmemLevels), v); };
             auto ld_alpha_s = [&](int k) -> FT { return alpha_hi[(k < kAlphaTmemLevels ? 0 : k - kAlphaTmemLevels + 1) * 32 + lane]; };
-            // transposed row sum of the staging tile: lane <-> row
+            // g-point sum of the staging tile, read transposed: lane r and lane r + 16 each add half of row r
+            // (128-bit reads), one shuffle joins the halves; every lane ends with the total of row (lane & 15)
             auto row_sum = [&]() -> FT {
-                FT s = 0.f;
-                const FT* row = stage + (lane & 15) * kStageStride;   // 16 rows, stride 33: conflict-free, immediate offsets
-#pragma unroll
-                for (int j = 0; j < 32; ++j) s += row[j];
-                return s;
+                const float4* row = reinterpret_cast<const float4*>(stage + (lane & 15) * kStageStride + (lane >> 4) * 16);
+                const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+                FT s = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+                return s + __shfl_xor_sync(0xffffffffu, s, 16);
             };
 
+            FastCell<LW, NG> G;
             if (LW) {
                 // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom).
                 // Iteration k gathers layer k and finishes layer k-1 (its top-level source needs pfrac of layer k).
@@ -267,40 +275,55 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : 0.f;
                 build_records(0);
                 FT tau, ssa, g, pf;
-                optics(0, tau, ssa, g, pf);
+                gather(0, G);
+                finish(0, G, tau, ssa, g, pf);
                 FT lev_bot = pbk[0] * pf;
                 FT albedo = 1.f - emis;
                 FT src = Num<FT>::pi() * emis * (pbk[nlev + nlay] * pf);
-                for (int k = 1; k <= nlay; ++k) {
-                    if (k == 32) build_records(1);
-                    const bool has = k < nlay;
-                    FT tau_n, ssa_n, g_n, pf_n;
-                    optics(has ? k : nlay - 1, tau_n, ssa_n, g_n, pf_n);       // (recomputed once at the top)
-                    const FT inc_k = pbk[k] * pf;
-                    const FT lev_top = has ? hsqrt(inc_k * (pbk[k] * pf_n)) : inc_k;
-                    FT Rdif, Tdif, su, sd;
-                    lw_2stream_coeffs(tau, ssa, g, lev_bot, lev_top, Rdif, Tdif, su, sd);
-                    const FT denom = hdiv(1.f, 1.f - Rdif * albedo);
-                    const int kl = k - 1;                                         // the layer / level being finished
+                // finishes layer kl = k - 1 given the Planck source at its top
+                auto close_layer = [&](int kl, const LwCoef& C, FT denom, FT lev_top) {
+                    const FT dB = lev_bot - lev_top;
+                    const FT su = Num<FT>::pi() * (lev_top * C.emis_fac - C.q * dB);
+                    const FT sd = Num<FT>::pi() * (lev_bot * C.emis_fac + C.q * dB);
                     // level kl: F_dn(kl) = A F_dn(kl+1) + B ; F_up(kl) = albedo F_dn(kl) + src
-                    tmem_st2(tA + 2 * kl, Tdif * denom, (Rdif * src + sd) * denom);
+                    tmem_st2(tA + 2 * kl, C.Tdif * denom, (C.Rdif * src + sd) * denom);
                     st_alpha(kl, albedo);
-                    stage[(kl & 15) * kStageStride + lane] = src * on;
-                    const FT albedo_n = Rdif + Tdif * Tdif * albedo * denom;
-                    src = su + Tdif * denom * (src + albedo * sd);
-                    albedo = albedo_n;
-                    lev_bot = lev_top; tau = tau_n; ssa = ssa_n; g = g_n; pf = pf_n;
-                    if ((kl & 15) == 15 || k == nlay) {                           // sum_g src for <= 16 levels
-                        __syncwarp();
-                        const int lev = (kl & ~15) + lane;
-                        const FT sum = row_sum();
-                        if (lane < 16 && lev <= kl) accs[UP * kAccStride + lev] += sum;
-                        __syncwarp();
+                    const FT src_lev = src;
+                    src = su + C.Tdif * denom * (src + albedo * sd);
+                    albedo = C.Rdif + C.Tdif * C.Tdif * albedo * denom;
+                    lev_bot = lev_top;
+                    return src_lev;
+                };
+                for (int k0 = 0; k0 < nlay; k0 += 16) {                 // tiles of <= 16 interfaces k
+                    const int ks = k0 > 0 ? k0 : 1, ke = k0 + 16 < nlay ? k0 + 16 : nlay;
+                    if (k0 == 32) build_records(1);
+                    for (int k = ks; k < ke; ++k) {                       // single basic block
+                        gather(k, G);
+                        const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
+                        const FT denom = hdiv(1.f, 1.f - C.Rdif * albedo);
+                        const FT bk = pbk[k];
+                        const FT inc_k = bk * pf;
+                        finish(k, G, tau, ssa, g, pf);
+                        const FT lev_top = hsqrt(inc_k * (bk * pf));
+                        stage[(k - ks) * kStageStride + lane] = close_layer(k - 1, C, denom, lev_top);
                     }
+                    __syncwarp();
+                    {                                                     // sum_g src of levels ks-1 .. ke-2
+                        const FT sum = row_sum();
+                        if (lane < 16 && lane < ke - ks) accs[UP * kAccStride + ks - 1 + lane] += sum;
+                    }
+                    __syncwarp();
+                }
+                {   // top layer: its upper source is its own increment (compute_optical_props.jl:193-195)
+                    const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
+                    const FT denom = hdiv(1.f, 1.f - C.Rdif * albedo);
+                    const FT s_top = close_layer(nlay - 1, C, denom, pbk[nlay] * pf);
+                    const FT ssum = warp_sum(s_top);
+                    if (lane == 0) accs[UP * kAccStride + nlay - 1] += ssum;
                 }
                 FT dn = inc;
                 {
-                    FT u = warp_sum((dn * albedo + src) * on), d = warp_sum(dn * on);
+                    FT u = warp_sum(dn * albedo + src), d = warp_sum(dn);
                     if (lane == 0) { accs[UP * kAccStride + nlay] += u; accs[DN * kAccStride + nlay] += d; }
                 }
                 tmem_wait_st();
@@ -317,56 +340,68 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                         tmem_ld2(tA + 2 * kn, A, B);
                         ld_alpha_t(kn, al);
                         dn = Ak * dn + Bk;
-                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = dn * on;
-                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = alk * dn * on;
+                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = dn;
+                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = alk * dn;
                         tmem_wait_ld();
                     }
                     __syncwarp();
                     {
-                        const int lev = kc + (lane >> 1);
+                        const int lev = kc + ((lane & 15) >> 1);
                         const FT sum = row_sum();
                         if (lane < 16 && lev <= ktop) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += sum;
                     }
                     __syncwarp();
                 }
             } else {
-                // shortwave_2stream.jl:300-392 with the adding marched from the top
+                // shortwave_2stream.jl:300-392 with the adding marched from the top.  Iteration j gathers layer j
+                // and processes layer j + 1 with the optics finished one iteration earlier.
                 const FT alb_dir = __ldg(P.io.sfc_alb_direct + (size_t)col * L.n_bnd + ibnd);
                 const FT alb_dif = __ldg(P.io.sfc_alb_diffuse + (size_t)col * L.n_bnd + ibnd);
                 const FT dir_top = toa * __ldg(L.solar_src_scaled + gpt) * mu0;
                 const FT inv_mu0 = hdiv(1.f, rmax(mu0, FLT_EPSILON));
+                const FT neg_inv_mu0_l2e = -inv_mu0 * 1.4426950408889634f;
                 FT tau_cum = 0.f, dir = dir_top;
                 FT beta = 0.f, d = 0.f;   // reflectance / downward diffuse source of everything above the level
                 {
-                    FT sum = warp_sum(dir_top * on);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
+                    FT sum = warp_sum(dir_top);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
                     if (lane == 0) { accs[DIR * kAccStride + nlay] += sum; accs[DN * kAccStride + nlay] += sum; }
                 }
                 build_records(nlay > 32 ? 1 : 0);
-                for (int kc = (nlay - 1) & ~7; kc >= 0; kc -= 8) {     // 8 levels x (d_{k+1}, dir_k) per tile
-                    if (kc == 24 && nlay > 32) build_records(0);
-                    const int ktop = kc + 7 < nlay - 1 ? kc + 7 : nlay - 1;
-                    for (int k = ktop; k >= kc; --k) {
-                        FT tau, ssa, g, pf;
-                        optics(k, tau, ssa, g, pf);
-                        FT Rdir, Tdir, Rdif, Tdif;
-                        sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
-                        const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
-                        const FT denom = hdiv(1.f, 1.f - Rdif * beta);
-                        // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
-                        tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
-                        st_alpha(k, beta);
-                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = d * on;   // d_{k+1}
-                        d = sd + Tdif * denom * (d + beta * su);
-                        beta = Rdif + Tdif * Tdif * beta * denom;
-                        tau_cum += tau;
-                        dir = dir_top * hexp(-tau_cum * inv_mu0);         // direct flux at level k
-                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = dir * on;
+                FT tau, ssa, g, pf;
+                gather(nlay - 1, G);
+                finish(nlay - 1, G, tau, ssa, g, pf);
+                // layer k: coefficients, TMEM store, marching update; returns d_{k+1} (before the update)
+                auto march = [&](int k) -> FT {
+                    FT Rdir, Tdir, Rdif, Tdif;
+                    sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
+                    const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
+                    const FT denom = hdiv(1.f, 1.f - Rdif * beta);
+                    // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
+                    tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
+                    st_alpha(k, beta);
+                    const FT d_above = d;
+                    d = sd + Tdif * denom * (d + beta * su);
+                    beta = Rdif + Tdif * Tdif * beta * denom;
+                    tau_cum += tau;
+                    float ex;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(tau_cum * neg_inv_mu0_l2e));
+                    dir = dir_top * ex;                               // direct flux at level k
+                    return d_above;
+                };
+                for (int jc = (nlay - 2) & ~7; jc >= 0; jc -= 8) {     // 8 layers x (d_{k+1}, dir_k) per tile, k = j + 1
+                    if (jc == 24 && nlay > 32) build_records(0);
+                    const int jtop = jc + 7 < nlay - 2 ? jc + 7 : nlay - 2;
+                    for (int j = jtop; j >= jc; --j) {                  // single basic block
+                        gather(j, G);
+                        stage[((j - jc) * 2 + 0) * kStageStride + lane] = march(j + 1);
+                        stage[((j - jc) * 2 + 1) * kStageStride + lane] = dir;
+                        finish(j, G, tau, ssa, g, pf);
                     }
                     __syncwarp();
                     {
-                        const int kk = kc + (lane >> 1);
+                        const int kk = jc + 1 + ((lane & 15) >> 1);
                         const FT sum = row_sum();
-                        const bool ok = lane < 16 && kk <= ktop;
+                        const bool ok = lane < 16 && kk <= jtop + 1;
                         // d_{kk+1} (even lanes) and dir_kk (odd lanes) both feed F_dn: two ordered steps,
                         // never two lanes read-modify-writing one accumulator in the same instruction
                         if (ok && (lane & 1)) { accs[DN * kAccStride + kk] += sum; accs[DIR * kAccStride + kk] += sum; }
@@ -375,6 +410,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     }
                     __syncwarp();
                 }
+                {   // lowest layer
+                    const FT d1 = warp_sum(march(0)), dir0 = warp_sum(dir);
+                    if (lane == 0) { accs[DN * kAccStride + 1] += d1; accs[DN * kAccStride] += dir0; accs[DIR * kAccStride] += dir0; }
+                }
                 if (aod_here) {
                     aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
                     if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
@@ -382,7 +421,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 // surface: F_up(0) = alb_dif F_dn_dif(0) + alb_dir dir(0) ; F_dn_dif(0) = d_0 + beta_0 F_up(0)
                 FT up = hdiv(alb_dif * d + alb_dir * dir, 1.f - alb_dif * beta);
                 {
-                    FT u = warp_sum(up * on), dd = warp_sum((d + beta * up) * on);
+                    FT u = warp_sum(up), dd = warp_sum(d + beta * up);
                     if (lane == 0) { accs[UP * kAccStride] += u; accs[DN * kAccStride] += dd; }
                 }
                 tmem_wait_st();
@@ -399,13 +438,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                         tmem_ld2(tA + 2 * kn, A, B);
                         ld_alpha_t(kn, be);
                         up = Ak * up + Bk;                                  // F_up(k+1)
-                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = up * on;
-                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = bek * up * on;
+                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = up;
+                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = bek * up;
                         tmem_wait_ld();
                     }
                     __syncwarp();
                     {
-                        const int kk = kc + (lane >> 1);
+                        const int kk = kc + ((lane & 15) >> 1);
                         const FT sum = row_sum();
                         if (lane < 16 && kk < kend) accs[((lane & 1) ? DN : UP) * kAccStride + kk + 1] += sum;
                     }
