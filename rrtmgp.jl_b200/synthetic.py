@@ -51,6 +51,10 @@ class LutDims:
     nrghice: int = 3
     nbin: int = 5
     nrh: int = 36
+    # minor absorbers per band in the lower atmosphere (real tables have up to ~6; more than 4 LW / 3 SW
+    # exercises the second 128-bit slot group of the fast kernels)
+    minor_lower_lw: int = 3
+    minor_lower_sw: int = 2
     # optional explicit g-points per band (lists) for reduced-resolution style tables
     gpts_lw: Optional[List[int]] = None
     gpts_sw: Optional[List[int]] = None
@@ -188,10 +192,10 @@ def _band_tables(rng, d: LutDims, n_bnd, gpts, lw: bool):
     templ_upper = [(2, 0, 0, 0), (3, 0, 0, 0), (7, 8, 1, 0), (4, 0, 0, 0), (9, 0, 0, 0),
                    (7, 0, 1, 0), (5, 0, 0, 0)]
     if lw:
-        cl = [3] * n_bnd
+        cl = [d.minor_lower_lw] * n_bnd
         cu = [1 + (b % 2) for b in range(n_bnd)]
     else:
-        cl = [2] * n_bnd
+        cl = [d.minor_lower_sw] * n_bnd
         cu = [1] * n_bnd
     if n_bnd > 2:
         cu[-1] = 0  # one band without upper-atmosphere minors (n == 0 path)

@@ -285,3 +285,42 @@ def test_column_range_and_host_pipeline_match_full_call(real_pack):
         assert torch.equal(v.cpu(), pipe.host_out[k]), k
     with pytest.raises(R.RRTMGPB200Error):
         R.update_fluxes_range(s2, 31, 650, 100)
+
+
+@pytest.mark.parametrize("nlay", [8, 17, 32, 33, 40, 63])
+def test_fast_path_runtime_nlay_f32(real_pack, nlay):
+    """The Float32 fast kernels (TMEM level store, tiled level loops, half-column band records) at layer counts
+    that hit every tile / record-half boundary: Float32 engine vs Float64 oracle, all-sky with aerosols."""
+    st = R.synthetic.make_atmosphere(96, nlay, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, seed=99)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+    np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(np.float32))
+    np.testing.assert_allclose(e["aod_sw_ext"], o["aod_sw_ext"], rtol=2e-5)
+
+
+def test_fast_path_two_minor_groups_f32():
+    """Tables with more than four minor absorbers per band (as the real rrtmgp-data files have) select the
+    two-group instantiation of the fast kernels (two 128-bit slot groups per cell)."""
+    dims = R.synthetic.LutDims(minor_lower_lw=6, minor_lower_sw=5)
+    pack = R.synthetic.make_lut_pack(seed=7, dims=dims)
+    st = R.synthetic.make_atmosphere(192, 64, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, seed=5)
+    e, o = run_engine(pack, st, np.float32, **kw), run_oracle(pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(pack, st, np.float32, **kw))
+
+
+def test_fast_path_several_aerosol_species_per_layer(real_pack):
+    """Layers holding several aerosol species at once (the compact per-layer species list: first species
+    resolved per layer, the rest per band), Float32 fast kernels and Float64 generic kernels."""
+    st = R.synthetic.make_atmosphere(64, 64, cld_frac=None)
+    rng = np.random.default_rng(3)
+    extra = rng.random(st["aero_mass"].shape) < 0.3
+    st["aero_mass"] = np.where(extra, 10.0 ** rng.uniform(-6, -4, st["aero_mass"].shape), st["aero_mass"]).astype(st["aero_mass"].dtype)
+    st["aero_size"] = rng.uniform(0.1, 10.0, st["aero_size"].shape).astype(st["aero_size"].dtype)
+    kw = dict(method="all_sky", aerosols=True, seed=17)
+    o = run_oracle(real_pack, st, np.float64, **kw)
+    e32 = run_engine(real_pack, st, np.float32, **kw)
+    _check_f32(e32, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+    np.testing.assert_allclose(e32["aod_sw_ext"], o["aod_sw_ext"], rtol=2e-5)
+    _check_f64(run_engine(real_pack, st, np.float64, **kw), o)   # set_state casts the host arrays
