@@ -108,40 +108,46 @@ template <typename FT> __device__ __forceinline__ void delta_scale(FT& tau, FT& 
     FT g_s = hdiv(g, rmax(Num<FT>::eps(), FT(1) + g));
     tau = tau_s; ssa = ssa_s; g = g_s;
 }
+// Small-table load: S = false reads global memory through the read-only path; S = true dereferences the pointer as
+// it is (the fast kernels pass pointers into their shared-memory copy of the small tables).
+template <bool S, typename T> __device__ __forceinline__ T ldt(const T* p) {
+    if (S) return *p;
+    return __ldg(p);
+}
 // ---- optics_utils.jl:7-14 (equispaced) ----
-template <typename FT> __device__ __forceinline__ int loc_lower_eq(FT xi, FT dx, int n, const FT* __restrict__ x) {
-    if (xi <= __ldg(x)) return 1;
-    if (xi >= __ldg(x + n - 1)) return n - 1;
-    int j = (int)hdiv(xi - __ldg(x), dx) + 1;
+template <bool S = false, typename FT> __device__ __forceinline__ int loc_lower_eq(FT xi, FT dx, int n, const FT* __restrict__ x) {
+    if (xi <= ldt<S>(x)) return 1;
+    if (xi >= ldt<S>(x + n - 1)) return n - 1;
+    int j = (int)hdiv(xi - ldt<S>(x), dx) + 1;
     return j < n - 1 ? j : n - 1;
 }
 // ---- optics_utils.jl:34-44 split into "locate" (per level) and "evaluate" (per band) ----
 // loc = 0 encodes "below range -> y[0]", loc = n encodes "above range -> y[n-1]"
-template <typename FT>
+template <bool S = false, typename FT>
 __device__ __forceinline__ void interp1d_eq_locate(FT xi, const FT* __restrict__ x, int n, int& loc, FT& factor) {
-    if (xi < __ldg(x)) { loc = 0; factor = FT(0); return; }
-    if (xi > __ldg(x + n - 1)) { loc = n; factor = FT(0); return; }
-    FT dx = __ldg(x + 1) - __ldg(x);
-    loc = loc_lower_eq(xi, dx, n, x);
-    factor = hdiv(xi - __ldg(x + loc - 1), dx);
+    if (xi < ldt<S>(x)) { loc = 0; factor = FT(0); return; }
+    if (xi > ldt<S>(x + n - 1)) { loc = n; factor = FT(0); return; }
+    FT dx = ldt<S>(x + 1) - ldt<S>(x);
+    loc = loc_lower_eq<S>(xi, dx, n, x);
+    factor = hdiv(xi - ldt<S>(x + loc - 1), dx);
 }
-template <typename FT>
+template <bool S = false, typename FT>
 __device__ __forceinline__ FT interp1d_eq_eval(int loc, FT factor, const FT* __restrict__ y, int n) {
-    if (loc == 0) return __ldg(y);
-    if (loc == n) return __ldg(y + n - 1);
-    return __ldg(y + loc - 1) * (FT(1) - factor) + __ldg(y + loc) * factor;
+    if (loc == 0) return ldt<S>(y);
+    if (loc == n) return ldt<S>(y + n - 1);
+    return ldt<S>(y + loc - 1) * (FT(1) - factor) + ldt<S>(y + loc) * factor;
 }
 // ---- optics_utils.jl:51-62 + :21-27 (non-uniform x) ----
-template <typename FT>
+template <bool S = false, typename FT>
 __device__ __forceinline__ void interp1d_loc_factor(FT xi, const FT* __restrict__ x, int n, int& loc, FT& factor) {
-    if (xi < __ldg(x)) { loc = 1; factor = FT(0); return; }
-    if (xi > __ldg(x + n - 1)) { loc = n - 1; factor = FT(1); return; }
+    if (xi < ldt<S>(x)) { loc = 1; factor = FT(0); return; }
+    if (xi > ldt<S>(x + n - 1)) { loc = n - 1; factor = FT(1); return; }
     loc = n - 1;
-    if (xi <= __ldg(x)) loc = 1;
+    if (xi <= ldt<S>(x)) loc = 1;
     else
         for (int i = 1; i <= n; ++i)
-            if (xi < __ldg(x + i - 1)) { loc = i - 1; break; }
-    factor = hdiv(xi - __ldg(x + loc - 1), __ldg(x + loc) - __ldg(x + loc - 1));
+            if (xi < ldt<S>(x + i - 1)) { loc = i - 1; break; }
+    factor = hdiv(xi - ldt<S>(x + loc - 1), ldt<S>(x + loc) - ldt<S>(x + loc - 1));
 }
 
 // ---- longwave_2stream.jl:149-222 ----

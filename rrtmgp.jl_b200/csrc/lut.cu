@@ -71,6 +71,29 @@ struct Arena {
         if (!v.empty()) std::memcpy(buf.data() + off, v.data(), v.size() * sizeof(T));
         fixes.push_back({(void**)&field, off});
     }
+    // Small tables of one sweep (group 0 = LW, 1 = SW) are collected and laid out contiguously by finalize().
+    struct Small { std::vector<unsigned char> buf; std::vector<Fix> fixes; };
+    Small small[2];
+    template <class T, class P> void add_small(int grp, const std::vector<T>& v, P*& field) {
+        Small& S = small[grp];
+        size_t off = (S.buf.size() + 15) / 16 * 16;
+        S.buf.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
+        if (!v.empty()) std::memcpy(S.buf.data() + off, v.data(), v.size() * sizeof(T));
+        S.fixes.push_back({(void**)&field, off});
+    }
+    template <class P> void finalize_small(int grp, P*& blob, int& blob_bytes, int& n_cut, int* cut) {
+        Small& S = small[grp];
+        S.buf.resize((S.buf.size() + 15) / 16 * 16);
+        n_cut = 0;
+        for (size_t i = 1; i < S.fixes.size() && n_cut < 31; ++i) cut[n_cut++] = (int)S.fixes[i].off;   // table starts
+        cut[n_cut++] = (int)S.buf.size();
+        size_t off = (buf.size() + 255) / 256 * 256;
+        buf.resize(off + S.buf.size());
+        std::memcpy(buf.data() + off, S.buf.data(), S.buf.size());
+        for (auto& f : S.fixes) fixes.push_back({f.where, off + f.off});
+        fixes.push_back({(void**)&blob, off});
+        blob_bytes = (int)S.buf.size();
+    }
     void patch(unsigned char* base) {
         for (auto& f : fixes) *f.where = base + f.off;
     }
@@ -84,6 +107,7 @@ template <class FT> std::vector<FT> cast(const std::vector<double>& v) {
 
 template <class FT>
 void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Arena& A) {
+    const int grp = sw ? 1 : 0;
     const Entry& km = get(p, pre + "/kmajor", 0);
     if (km.ndim != 4) throw Missing{pre + "/kmajor (ndim)"};
     const int n_eta = km.dims[0], n_p = km.dims[1], n_t = km.dims[2], n_gpt = km.dims[3];
@@ -99,7 +123,7 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
     std::vector<int> ks = geti(p, pre + "/key_species");
     for (size_t i = 0; i + 1 < ks.size(); i += 2)
         if (ks[i] == 0 && ks[i + 1] == 0) ks[i] = ks[i + 1] = 2;
-    A.add(ks, L.key_species);
+    A.add_small(grp, ks, L.key_species);
 
     std::vector<int> g2b = geti(p, pre + "/major_gpt2bnd");
     for (auto& b : g2b) b -= 1;
@@ -107,15 +131,15 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
     for (int g0 = 0; g0 < n_gpt; g0 += 32)
         maxb = std::max(maxb, g2b[std::min(g0 + 31, n_gpt - 1)] - g2b[g0] + 1);
     L.maxb = maxb;
-    A.add(g2b, L.gpt2bnd);
+    A.add_small(grp, g2b, L.gpt2bnd);
 
     std::vector<FT> p_ref = cast<FT>(getd(p, pre + "/p_ref"));
     L.n_p_ref = (int)p_ref.size();
     std::vector<FT> lnp(p_ref.size());
     for (size_t i = 0; i < p_ref.size(); ++i) lnp[i] = std::log(p_ref[i]);  // lookup_constructors.jl:336
-    A.add(lnp, L.ln_p_ref);
-    A.add(cast<FT>(getd(p, pre + "/t_ref")), L.t_ref);
-    A.add(cast<FT>(getd(p, pre + "/vmr_ref")), L.vmr_ref);
+    A.add_small(grp, lnp, L.ln_p_ref);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/t_ref")), L.t_ref);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/vmr_ref")), L.vmr_ref);
 
     auto relayout4 = [&](const std::string& name) {
         std::vector<double> src = getd(p, name);
@@ -175,8 +199,8 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
         }
         std::vector<int> b0 = bst[tr];
         for (auto& v : b0) v -= 1;
-        A.add(b0, L.minor_bnd_st[tr]);
-        A.add(geti(p, pre + tags[tr] + "/gasdata"), L.minor_gasdata[tr]);
+        A.add_small(grp, b0, L.minor_bnd_st[tr]);
+        A.add_small(grp, geti(p, pre + tags[tr] + "/gasdata"), L.minor_gasdata[tr]);
     }
 
     L.pfrac = nullptr; L.t_planck = nullptr; L.tot_planck = nullptr; L.rayl = nullptr; L.solar_src_scaled = nullptr;
@@ -199,8 +223,8 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
         A.add(relayout4(pre + "/planck_fraction"), L.pfrac);
         std::vector<FT> tp = cast<FT>(getd(p, pre + "/t_planck"));
         L.n_t_plnk = (int)tp.size();
-        A.add(tp, L.t_planck);
-        A.add(cast<FT>(getd(p, pre + "/tot_planck")), L.tot_planck);
+        A.add_small(grp, tp, L.t_planck);
+        A.add_small(grp, cast<FT>(getd(p, pre + "/tot_planck")), L.tot_planck);
     } else {
         std::vector<double> lo = getd(p, pre + "/rayl_lower"), up = getd(p, pre + "/rayl_upper");
         std::vector<FT> dst((size_t)2 * n_t * n_eta * n_gpt);
@@ -217,37 +241,40 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
     }
 }
 
-template <class FT> void build_cld(const Pack& p, const std::string& pre, CldLut<FT>& C, Arena& A) {
+template <class FT> void build_cld(const Pack& p, const std::string& pre, CldLut<FT>& C, Arena& A, int grp) {
     std::vector<int> d = geti(p, pre + "/dims");
     C.nband = d[0]; C.nrghice = d[1]; C.nsize_liq = d[2]; C.nsize_ice = d[3];
     std::vector<double> b = getd(p, pre + "/bounds");
     C.radliq_lwr = (FT)b[0]; C.radliq_upr = (FT)b[1]; C.radice_lwr = (FT)b[2]; C.radice_upr = (FT)b[3];
-    A.add(cast<FT>(getd(p, pre + "/liqdata")), C.liqdata);
-    A.add(cast<FT>(getd(p, pre + "/icedata")), C.icedata);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/liqdata")), C.liqdata);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/icedata")), C.icedata);
 }
 
-template <class FT> void build_aero(const Pack& p, const std::string& pre, AeroLut<FT>& L, Arena& A) {
+template <class FT> void build_aero(const Pack& p, const std::string& pre, AeroLut<FT>& L, Arena& A, int grp) {
     std::vector<int> d = geti(p, pre + "/dims");
     L.nband = d[0]; L.nbin = d[2]; L.nrh = d[3];
     L.iband_550nm = geti(p, pre + "/iband_550nm")[0];
-    A.add(cast<FT>(getd(p, pre + "/size_bin_limits")), L.size_bin_limits);
-    A.add(cast<FT>(getd(p, pre + "/rh_levels")), L.rh_levels);
-    A.add(cast<FT>(getd(p, pre + "/dust")), L.dust);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/size_bin_limits")), L.size_bin_limits);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/rh_levels")), L.rh_levels);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/dust")), L.dust);
     A.add(cast<FT>(getd(p, pre + "/sea_salt")), L.sea_salt);
-    A.add(cast<FT>(getd(p, pre + "/sulfate")), L.sulfate);
-    A.add(cast<FT>(getd(p, pre + "/black_carbon_rh")), L.black_carbon_rh);
-    A.add(cast<FT>(getd(p, pre + "/black_carbon")), L.black_carbon);
-    A.add(cast<FT>(getd(p, pre + "/organic_carbon_rh")), L.organic_carbon_rh);
-    A.add(cast<FT>(getd(p, pre + "/organic_carbon")), L.organic_carbon);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/sulfate")), L.sulfate);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/black_carbon_rh")), L.black_carbon_rh);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/black_carbon")), L.black_carbon);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/organic_carbon_rh")), L.organic_carbon_rh);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/organic_carbon")), L.organic_carbon);
 }
 
 template <class FT> void build_all(const Pack& p, Luts<FT>& L, Arena& A) {
     build_gas(p, "lw", false, L.lw, A);
     build_gas(p, "sw", true, L.sw, A);
-    build_cld(p, "cld_lw", L.cld_lw, A);
-    build_cld(p, "cld_sw", L.cld_sw, A);
-    build_aero(p, "aero_lw", L.aero_lw, A);
-    build_aero(p, "aero_sw", L.aero_sw, A);
+    // block order = staging priority: gas tables, aerosol tables (sea salt, the one big one, stays outside), cloud
+    build_aero(p, "aero_lw", L.aero_lw, A, 0);
+    build_aero(p, "aero_sw", L.aero_sw, A, 1);
+    build_cld(p, "cld_lw", L.cld_lw, A, 0);
+    build_cld(p, "cld_sw", L.cld_sw, A, 1);
+    A.finalize_small(0, L.lw.blob, L.lw.blob_bytes, L.lw.n_blob_cut, L.lw.blob_cut);
+    A.finalize_small(1, L.sw.blob, L.sw.blob_bytes, L.sw.n_blob_cut, L.sw.blob_cut);
 }
 
 }  // namespace

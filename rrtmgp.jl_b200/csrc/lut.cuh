@@ -37,6 +37,16 @@ struct GasLut {
     const FT* kminor4[2];        // fast kernels: [group][n_t][n_eta][n_gpt][4], four slots per 128-bit load;
                                  // SW: slot 0 = Rayleigh of that atmosphere, minors follow; zero padded
     int n_minor_groups;          // groups of four slots in kminor4
+    // Every SMALL table of this sweep (the gas tables above that are not g-point sized, the cloud tables and the
+    // aerosol tables except sea salt) sits in one contiguous block of the arena, so the fast kernels stage the
+    // block into shared memory with one TMA bulk copy and address a table at (its pointer - blob) in the copy.
+    // When the whole block does not fit beside the per-warp state, a prefix ending at one of `blob_cut` (table
+    // boundaries, ascending; tables are ordered by how often a column reads them) is staged and the rest is
+    // read from global memory.
+    const unsigned char* blob;
+    int blob_bytes;              // multiple of 16
+    int n_blob_cut;
+    int blob_cut[32];
 };
 
 template <typename FT>

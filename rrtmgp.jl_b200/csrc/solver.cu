@@ -40,11 +40,12 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
 }
 
 // Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
-static int plan_smem_fast(SolveParams<float>& P, FastSmem& F) {
+static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin) {
     const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
     const int nrec = nlay < 32 ? nlay : 32;                    // band records cover half a column at a time
-    // record = {fe1, fe2, s1, s2}, 4 slot scalings per group, {aerosol-only products, eta offsets}, {cloud+aerosol, eta offsets}
-    P.rec_words = 4 + 4 * P.lut.n_minor_groups + 8;
+    // record = 8 corner weights, {s1, s2, two major-table offsets}, 4 slot scalings per group,
+    // {aerosol-only products, minor-table offset}, {cloud+aerosol products, minor-table offset}
+    P.rec_words = 20 + 4 * P.lut.n_minor_groups;
     int off = 0;
     P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
     P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(float), 16);
@@ -57,7 +58,15 @@ static int plan_smem_fast(SolveParams<float>& P, FastSmem& F) {
     F.off_stage = off; off = align_up(off + 16 * kStageStride * (int)sizeof(float), 16);
     F.off_acc = off;   off = align_up(off + 3 * kAccStride * (int)sizeof(float), 128);
     P.warp_bytes = off;
-    return off;
+    // CTA-shared tail: the staged small-table block and the global-mean vmr array
+    int tail = kFastWarps * off;
+    F.off_vmr = tail;  tail = align_up(tail + (P.ngas > 0 ? P.ngas : 1) * (int)sizeof(float), 128);
+    F.off_blob = tail;
+    const int room = max_smem_optin - 64 - tail;   // 64: static shared memory of the kernel
+    F.staged_bytes = 0;
+    for (int i = 0; i < P.lut.n_blob_cut; ++i)
+        if (P.lut.blob_cut[i] <= room) F.staged_bytes = P.lut.blob_cut[i];
+    return tail + F.staged_bytes;
 }
 
 static int sm_count_of_current_device() {
@@ -72,8 +81,7 @@ static int sm_count_of_current_device() {
 template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER>
 static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
     FastSmem F;
-    const int wb = plan_smem_fast(P, F);
-    const size_t smem = (size_t)kFastWarps * wb;
+    const size_t smem = (size_t)plan_smem_fast(P, F, max_smem_optin);
     if ((int)smem > max_smem_optin) return -1;   // does not fit: generic kernel
     auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -66,14 +66,15 @@ struct SolveParams {
 // ---------------------------------------------------------------------------------------------
 // VolumeMixingRatios.jl:91-129; ig 1-based gas index (0 = dry air)
 // ---------------------------------------------------------------------------------------------
+// `svmr`: optional on-chip copy of the global-mean array (fast kernels)
 template <typename FT>
-__device__ __forceinline__ FT get_vmr(const SolveParams<FT>& P, int ig, int lay, long long col) {
+__device__ __forceinline__ FT get_vmr(const SolveParams<FT>& P, int ig, int lay, long long col, const FT* svmr = nullptr) {
     if (ig == 0) return FT(1);
     size_t k = (size_t)col * P.nlay + lay;
     if (P.vmr_kind == 0) {
         if (ig == 1) return __ldg(P.io.vmr_h2o + k);
         if (ig == 3) return __ldg(P.io.vmr_o3 + k);
-        return __ldg(P.io.vmr + ig - 1);
+        return svmr != nullptr ? svmr[ig - 1] : __ldg(P.io.vmr + ig - 1);
     }
     return __ldg(P.io.vmr + k * P.ngas + ig - 1);
 }
@@ -92,23 +93,23 @@ __device__ __forceinline__ void cld_locate(int nsize, FT lwr, FT upr, FT re, int
     loc = loc > 1 ? loc : 1;
     fac = hdiv(re - lwr - (loc - 1) * dr, dr);
 }
-template <typename FT>
+template <bool S = false, typename FT>
 __device__ __forceinline__ void cld_eval(int nsize, const FT* __restrict__ tbl, int loc, FT fac, FT path, FT& tau,
                                          FT& tau_ssa, FT& tau_ssag) {
     tau = tau_ssa = tau_ssag = FT(0);
     if (path > Num<FT>::eps()) {
         FT fc1 = FT(1) - fac;
-        tau = rmax((fc1 * __ldg(tbl + loc - 1) + fac * __ldg(tbl + loc)) * path, FT(0));
-        tau_ssa = (fc1 * __ldg(tbl + nsize + loc - 1) + fac * __ldg(tbl + nsize + loc)) * tau;
-        tau_ssag = (fc1 * __ldg(tbl + 2 * nsize + loc - 1) + fac * __ldg(tbl + 2 * nsize + loc)) * tau_ssa;
+        tau = rmax((fc1 * ldt<S>(tbl + loc - 1) + fac * ldt<S>(tbl + loc)) * path, FT(0));
+        tau_ssa = (fc1 * ldt<S>(tbl + nsize + loc - 1) + fac * ldt<S>(tbl + nsize + loc)) * tau;
+        tau_ssag = (fc1 * ldt<S>(tbl + 2 * nsize + loc - 1) + fac * ldt<S>(tbl + 2 * nsize + loc)) * tau_ssa;
     }
 }
 
 // aerosol_optics.jl:438-451
-template <typename FT> __device__ __forceinline__ int merra_size_bin(const FT* __restrict__ lims, int nbins, FT size) {
+template <bool S = false, typename FT> __device__ __forceinline__ int merra_size_bin(const FT* __restrict__ lims, int nbins, FT size) {
     int bin = 1;
     for (int ib = 1; ib <= nbins; ++ib) {
-        if (__ldg(lims + 2 * (ib - 1)) <= size && size <= __ldg(lims + 2 * (ib - 1) + 1)) { bin = ib; break; }
+        if (ldt<S>(lims + 2 * (ib - 1)) <= size && size <= ldt<S>(lims + 2 * (ib - 1) + 1)) { bin = ib; break; }
         bin = nbins;
     }
     return bin;
@@ -119,8 +120,8 @@ template <typename FT> __device__ __forceinline__ int merra_size_bin(const FT* _
 // 1, 8..11), 5-9 sea salt (2, 12..15), 10 sulfate, 11 BC-rh, 12 BC, 13 OC-rh, 14 OC -- `bins` the MERRA size bin
 // of the ten sized species (3 bits per position) and `rh_loc` the RH interval.  The usual input has one species
 // per layer, so the table row of the FIRST active species is resolved here once per layer: `off0` = element
-// offset from AeroLut::dust of its (bin, RH interval) row for band 0, `bs0` = band stride | rh-interpolated << 24
-// | 0-based species index << 25.
+// offset from AeroLut::dust of its (bin, RH interval) row for band 0, `bs0` = band stride | sea salt << 23 |
+// rh-interpolated << 24 | 0-based species index << 25.
 struct AeroLayer { unsigned active; unsigned bins; int rh_loc; int off0; int bs0; };
 
 __device__ __forceinline__ int aero_pos_of_species(int i) {   // 0-based species -> summation position
@@ -139,7 +140,7 @@ __device__ __forceinline__ void aero_entry(const AeroLut<FT>& A, int pos, unsign
         const int k = pos - 5;
         const int bin = (int)((bins >> (3 * pos)) & 7u);
         off = (int)(A.sea_salt - A.dust) + 3 * nrh * (bin - 1) + 3 * (loc - 1);
-        bs = (3 * nrh * nbin) | (1 << 24) | ((k == 0 ? 1 : 10 + k) << 25);
+        bs = (3 * nrh * nbin) | (1 << 23) | (1 << 24) | ((k == 0 ? 1 : 10 + k) << 25);
     } else {
         const FT* t = pos == 10 ? A.sulfate : (pos == 11 ? A.black_carbon_rh : (pos == 12 ? A.black_carbon
                                 : (pos == 13 ? A.organic_carbon_rh : A.organic_carbon)));
@@ -151,19 +152,21 @@ __device__ __forceinline__ void aero_entry(const AeroLut<FT>& A, int pos, unsign
 
 // aerosol_optics.jl:141-235; ibnd 0-based.  Dry species read one (ext, ssa, asy) row, RH-dependent ones
 // interpolate between two adjacent rows; one branch-free form serves both (f_eff = 0, second row = first).
-template <typename FT>
-__device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, int ibnd, const FT* __restrict__ mass,
+// `small` = where AeroLut::dust (and, at the same relative offsets, every aerosol table but sea salt) is read from:
+// the global array, or the fast kernels' shared-memory copy (S = true; sea salt is always read from global memory).
+template <bool S = false, typename FT>
+__device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, const FT* small, int ibnd, const FT* __restrict__ mass,
                                                const AeroLayer& al, FT f, FT& tc, FT& tsc, FT& tsgc) {
     tc = tsc = tsgc = FT(0);
     auto species = [&](int off, int bs) {
-        const FT* __restrict__ p = A.dust + off + (size_t)(bs & 0xffffff) * ibnd;
+        const FT* p = (((bs >> 23) & 1) ? A.dust : small) + off + (size_t)(bs & 0x7fffff) * ibnd;
         const bool rh = (bs >> 24) & 1;
         const int d = rh ? 3 : 0;
         const FT fe = rh ? f : FT(0);
         const FT m = __ldg(mass + (bs >> 25));
-        FT t = m * (__ldg(p) * (FT(1) - fe) + __ldg(p + d) * fe);
-        FT ts = t * (__ldg(p + 1) * (FT(1) - fe) + __ldg(p + d + 1) * fe);
-        FT tsg = ts * (__ldg(p + 2) * (FT(1) - fe) + __ldg(p + d + 2) * fe);
+        FT t = m * (ldt<S>(p) * (FT(1) - fe) + ldt<S>(p + d) * fe);
+        FT ts = t * (ldt<S>(p + 1) * (FT(1) - fe) + ldt<S>(p + d + 1) * fe);
+        FT tsg = ts * (ldt<S>(p + 2) * (FT(1) - fe) + ldt<S>(p + d + 2) * fe);
         tc += t; tsc += ts; tsgc += tsg;
     };
     species(al.off0, al.bs0);
@@ -197,6 +200,10 @@ struct Warp {
     FT* rec;     // [nlay][maxb][RW]: fe1, fe2, s1, s2, minor scalings, cloud(3), aerosol(3)
     FT* plk;     // LW: [maxb][2*nlev] B(t_lev) | B(t_lay) (noscat) | B(t_sfc)
     const int RW, maxb;
+    // fast kernels: shared-memory copy of the small-table block (GasLut::blob) and of the global-mean vmr array
+    const unsigned char* sblob;
+    const int staged;   // bytes of the block that are staged (a prefix ending at a table boundary)
+    const FT* svmr;
     // per-lane registers for the layers this lane owns in phase 0/1: lane, lane+32, lane+64
     FT own_h2o[NOWN], own_dens[NOWN], own_cdry[NOWN];
     AeroLayer own_aero[NOWN];
@@ -211,17 +218,31 @@ struct Warp {
     bool lane_on;
     unsigned mask[NOWN];
 
-    __device__ __forceinline__ Warp(const SolveParams<FT>& P_, unsigned char* wbase, int lane_, long long col_)
-        : P(P_), L(P_.lut), lane(lane_), col(col_), nlay(P_.nlay), nlev(P_.nlay + 1),
+    __device__ __forceinline__ Warp(const SolveParams<FT>& P_, unsigned char* wbase, int lane_, long long col_,
+                                    const unsigned char* sblob_ = nullptr, int staged_ = 0, const FT* svmr_ = nullptr)
+        : P(P_), L(P_.lut), lane(lane_), col(col_), nlay(P_.nlay), nlev(P_.nlay + 1), sblob(sblob_), staged(staged_), svmr(svmr_),
           colj(reinterpret_cast<int*>(wbase + P_.off_colj)), colp(reinterpret_cast<FT*>(wbase + P_.off_colp)),
           recj(reinterpret_cast<int*>(wbase + P_.off_recj)), rec(reinterpret_cast<FT*>(wbase + P_.off_rec)),
           plk(reinterpret_cast<FT*>(wbase + P_.off_plk)), RW(P_.rec_words), maxb(P_.lut.maxb) {}
+
+    // A small table: the global array, or (fast kernels) its copy inside the staged part of the block
+    template <class T> __device__ __forceinline__ const T* tb(const T* g) const {
+        if (FUSED) {
+            const long long off = reinterpret_cast<const unsigned char*>(g) - L.blob;
+            if (off >= 0 && off < staged) return reinterpret_cast<const T*>(sblob + off);
+        }
+        return g;
+    }
+    __device__ __forceinline__ FT vmr_of(int ig, int k) const { return get_vmr(P, ig, k, col, FUSED ? svmr : nullptr); }
 
     // ---------------- phase 0 (gas_optics.jl:87-115,188 and the hoisted per-layer searches) ----------------
     __device__ __forceinline__ void phase0() {
         const FT* ld = P.io.layerdata + (size_t)col * nlay * 4;
         const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
         const int n_t = L.n_t;
+        const FT* t_ref = tb(L.t_ref);
+        const FT* ln_p_ref = tb(L.ln_p_ref);
+        const FT* t_planck = tb(L.t_planck);
 #pragma unroll
         for (int j = 0; j < NOWN; ++j) {
             const int k = lane + 32 * j;
@@ -231,17 +252,17 @@ struct Warp {
             if (k >= nlay) continue;
             FT col_dry = __ldg(ld + 4 * k + 0), p_lay = __ldg(ld + 4 * k + 1), t_lay = __ldg(ld + 4 * k + 2);
             int tropo = p_lay > L.p_ref_tropo ? 1 : 2;
-            FT dT = __ldg(L.t_ref + 1) - __ldg(L.t_ref);
-            int jt = loc_lower_eq(t_lay, dT, n_t, L.t_ref);
-            FT ft = hdiv(t_lay - __ldg(L.t_ref + jt - 1), dT);
-            FT dlnp = __ldg(L.ln_p_ref) - __ldg(L.ln_p_ref + 1);
+            FT dT = ldt<FUSED>(t_ref + 1) - ldt<FUSED>(t_ref);
+            int jt = loc_lower_eq<FUSED>(t_lay, dT, n_t, t_ref);
+            FT ft = hdiv(t_lay - ldt<FUSED>(t_ref + jt - 1), dT);
+            FT dlnp = ldt<FUSED>(ln_p_ref) - ldt<FUSED>(ln_p_ref + 1);
             FT lp = rlog(p_lay);
-            int jpress = (int)hdiv(__ldg(L.ln_p_ref) - lp, dlnp) + 1;
+            int jpress = (int)hdiv(ldt<FUSED>(ln_p_ref) - lp, dlnp) + 1;
             jpress = jpress > 1 ? jpress : 1;
             jpress = (jpress < L.n_p_ref - 1 ? jpress : L.n_p_ref - 1) + 1;
-            FT fp = hdiv(__ldg(L.ln_p_ref + jpress - 2) - lp, dlnp);
+            FT fp = hdiv(ldt<FUSED>(ln_p_ref + jpress - 2) - lp, dlnp);
             int jp = jpress + tropo - 1;
-            FT h2o = get_vmr(P, L.idx_h2o, k, col);
+            FT h2o = vmr_of(L.idx_h2o, k);
             own_h2o[j] = h2o;
             own_cdry[j] = col_dry;
             own_dens[j] = hdiv(FT(0.01) * p_lay, t_lay);
@@ -254,10 +275,10 @@ struct Warp {
                 if (act) {
                     for (int pos = 0; pos < 10; ++pos) {   // sized species: dust 1, 8..11 then sea salt 2, 12..15
                         const int i = pos < 5 ? (pos == 0 ? 0 : 6 + pos) : (pos == 5 ? 1 : 5 + pos);
-                        if ((act >> pos) & 1u) bins |= (unsigned)merra_size_bin(P.aero.size_bin_limits, P.aero.nbin, __ldg(as + i)) << (3 * pos);
+                        if ((act >> pos) & 1u) bins |= (unsigned)merra_size_bin<FUSED>(tb(P.aero.size_bin_limits), P.aero.nbin, __ldg(as + i)) << (3 * pos);
                     }
                     int loc; FT f;
-                    interp1d_loc_factor(__ldg(ld + 4 * k + 3), P.aero.rh_levels, P.aero.nrh, loc, f);
+                    interp1d_loc_factor<FUSED>(__ldg(ld + 4 * k + 3), tb(P.aero.rh_levels), P.aero.nrh, loc, f);
                     int off0, bs0;
                     aero_entry(P.aero, __ffs((int)act) - 1, bins, loc, off0, bs0);
                     own_aero[j] = AeroLayer{act, bins, loc, off0, bs0};
@@ -277,8 +298,8 @@ struct Warp {
             }
             if (LW) {
                 const FT* tl = P.io.t_lev + (size_t)col * nlev;
-                interp1d_eq_locate(__ldg(tl + k + 1), L.t_planck, L.n_t_plnk, own_pl_loc[j], own_pl_f[j]);
-                if (NOSCAT) interp1d_eq_locate(t_lay, L.t_planck, L.n_t_plnk, own_py_loc[j], own_py_f[j]);
+                interp1d_eq_locate<FUSED>(__ldg(tl + k + 1), t_planck, L.n_t_plnk, own_pl_loc[j], own_pl_f[j]);
+                if (NOSCAT) interp1d_eq_locate<FUSED>(t_lay, t_planck, L.n_t_plnk, own_py_loc[j], own_py_f[j]);
             }
             colj[k] = jt | (jp << 8) | ((tropo - 1) << 16) | (aero_on << 17);
             colp[4 * k + 0] = ft; colp[4 * k + 1] = fp;
@@ -295,8 +316,8 @@ struct Warp {
         }
         p0_loc = psfc_loc = 0; p0_f = psfc_f = FT(0);
         if (LW && lane == 0) {
-            interp1d_eq_locate(__ldg(P.io.t_lev + (size_t)col * nlev), L.t_planck, L.n_t_plnk, p0_loc, p0_f);
-            interp1d_eq_locate(__ldg(P.io.t_sfc + col), L.t_planck, L.n_t_plnk, psfc_loc, psfc_f);
+            interp1d_eq_locate<FUSED>(__ldg(P.io.t_lev + (size_t)col * nlev), t_planck, L.n_t_plnk, p0_loc, p0_f);
+            interp1d_eq_locate<FUSED>(__ldg(P.io.t_sfc + col), t_planck, L.n_t_plnk, psfc_loc, psfc_f);
         }
         __syncwarp();
     }
@@ -305,10 +326,11 @@ struct Warp {
         const int n_gpt = L.n_gpt;
         lane_on = g0 + lane < n_gpt;
         gpt = lane_on ? g0 + lane : n_gpt - 1;
-        b_first = __ldg(L.gpt2bnd + g0);
-        const int b_last = __ldg(L.gpt2bnd + (g0 + 31 < n_gpt ? g0 + 31 : n_gpt - 1));
+        const int* gpt2bnd = tb(L.gpt2bnd);
+        b_first = ldt<FUSED>(gpt2bnd + g0);
+        const int b_last = ldt<FUSED>(gpt2bnd + (g0 + 31 < n_gpt ? g0 + 31 : n_gpt - 1));
         nb = b_last - b_first + 1;
-        ibnd = __ldg(L.gpt2bnd + gpt);
+        ibnd = ldt<FUSED>(gpt2bnd + gpt);
         bl = ibnd - b_first;
     }
 
@@ -334,61 +356,67 @@ struct Warp {
                 const int ib = b_first + b;
                 FT* r = rec + ((size_t)kr * maxb + b) * RW;
                 // gas_optics.jl:129-170
-                const int ig1 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib));
-                const int ig2 = __ldg(L.key_species + 2 * ((tropo - 1) + 2 * ib) + 1);
-                const FT vmr1 = get_vmr(P, ig1, k, col), vmr2 = get_vmr(P, ig2, k, col);
+                const int* ksp = tb(L.key_species) + 2 * ((tropo - 1) + 2 * ib);
+                const int ig1 = ldt<FUSED>(ksp), ig2 = ldt<FUSED>(ksp + 1);
+                const FT vmr1 = vmr_of(ig1, k), vmr2 = vmr_of(ig2, k);
                 int je[2];
+                FT fe[2], smix[2];
+                // fast kernels (FUSED): record = 8 corner weights | s1, s2, major-table offsets of the two T nodes |
+                // slot scalings | {aerosol-only products, minor-table offset} | {cloud+aerosol products, same offset}
+                const int sc0 = FUSED ? 12 : 4;
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                    const FT* vr = L.vmr_ref + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
-                    FT eta_half = hdiv(__ldg(vr + 2 * ig1), __ldg(vr + 2 * ig2));
+                    const FT* vr = tb(L.vmr_ref) + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
+                    FT eta_half = hdiv(ldt<FUSED>(vr + 2 * ig1), ldt<FUSED>(vr + 2 * ig2));
                     FT col_mix = vmr1 + eta_half * vmr2;
                     FT eta = vmr1 * hdiv(FT(1), col_mix);
                     if (col_mix <= FT(0)) eta = FT(0.5);
                     FT loc_eta = eta * FT(n_eta - 1);
                     int jj = (int)loc_eta + 1;
                     jj = jj < n_eta - 1 ? jj : n_eta - 1;
-                    je[it] = jj; r[it] = loc_eta - FT(jj - 1);
-                    r[2 + it] = FUSED ? col_mix * col_dry : col_mix;   // fast kernels fold col_dry in here
+                    je[it] = jj; fe[it] = loc_eta - FT(jj - 1);
+                    smix[it] = FUSED ? col_mix * col_dry : col_mix;   // fast kernels fold col_dry in here
+                    if (!FUSED) { r[it] = fe[it]; r[2 + it] = smix[it]; }
                 }
                 // gas_optics.jl:344-412: per-absorber scalings.  Fast kernels (FUSED) gather four slots per
                 // 128-bit load: slots are zero padded to a multiple of four and SW slot 0 is Rayleigh
                 // (gas_optics.jl:430-444: (vmr_h2o + 1) * col_dry).
                 const int soff = (FUSED && !LW) ? 1 : 0;
                 const int nslots = FUSED ? 4 * L.n_minor_groups : L.nminor_max;
-                if (FUSED && !LW) r[4] = (vmr_h2o + FT(1)) * col_dry;
-                const int* bst = L.minor_bnd_st[tropo - 1];
-                const int m0 = __ldg(bst + ib), nmin = __ldg(bst + ib + 1) - m0;
+                if (FUSED && !LW) r[sc0] = (vmr_h2o + FT(1)) * col_dry;
+                const int* bst = tb(L.minor_bnd_st[tropo - 1]);
+                const int4* gdt = reinterpret_cast<const int4*>(tb(L.minor_gasdata[tropo - 1]));
+                const int m0 = ldt<FUSED>(bst + ib), nmin = ldt<FUSED>(bst + ib + 1) - m0;
                 for (int i = 0; i < nmin; ++i) {
-                    const int4 gd = __ldg(reinterpret_cast<const int4*>(L.minor_gasdata[tropo - 1]) + (m0 + i));
-                    FT vmr_i = get_vmr(P, gd.x, k, col);
+                    const int4 gd = ldt<FUSED>(gdt + (m0 + i));
+                    FT vmr_i = vmr_of(gd.x, k);
                     FT scaling = FT(0);
                     if (vmr_i > FT(0)) {
                         scaling = vmr_i * col_dry;
                         if (gd.z == 1) {
                             scaling *= own_dens[j];
                             if (gd.y > 0) {
-                                if (gd.w == 1) scaling *= (FT(1) - get_vmr(P, gd.y, k, col) * dry_fact);
-                                else scaling *= get_vmr(P, gd.y, k, col) * dry_fact;
+                                if (gd.w == 1) scaling *= (FT(1) - vmr_of(gd.y, k) * dry_fact);
+                                else scaling *= vmr_of(gd.y, k) * dry_fact;
                             }
                         }
                     }
-                    r[4 + soff + i] = scaling;
+                    r[sc0 + soff + i] = scaling;
                 }
                 if (FUSED)
-                    for (int i = soff + nmin; i < nslots; ++i) r[4 + i] = FT(0);
-                FT* rc = r + 4 + nslots;   // cloud (3) then aerosol (3)  [FUSED: aerosol-only / cloud+aerosol products]
+                    for (int i = soff + nmin; i < nslots; ++i) r[sc0 + i] = FT(0);
+                FT* rc = r + sc0 + nslots;   // cloud (3) then aerosol (3)  [FUSED: aerosol-only / cloud+aerosol products]
                 FT tc = FT(0), sc = FT(0), gc = FT(0);
                 // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
                 if (use_cloud) {
                     if ((own_cld[j] >> 16) & 1) {
                         const CldLut<FT>& C = P.cld;
                         size_t kk = (size_t)col * nlay + k;
-                        const FT* liq = C.liqdata + (size_t)3 * C.nsize_liq * ib;
-                        const FT* ice = C.icedata + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
+                        const FT* liq = tb(C.liqdata) + (size_t)3 * C.nsize_liq * ib;
+                        const FT* ice = tb(C.icedata) + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
                         FT tl, tls, tlsg, ti, tis, tisg;
-                        cld_eval(C.nsize_liq, liq, own_cld[j] & 0xff, own_cld_fl[j], __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
-                        cld_eval(C.nsize_ice, ice, (own_cld[j] >> 8) & 0xff, own_cld_fi[j], __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
+                        cld_eval<FUSED>(C.nsize_liq, liq, own_cld[j] & 0xff, own_cld_fl[j], __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
+                        cld_eval<FUSED>(C.nsize_ice, ice, (own_cld[j] >> 8) & 0xff, own_cld_fi[j], __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
                         if (NOSCAT) {
                             tc = (tl - tls) + (ti - tis);
                         } else {
@@ -406,7 +434,7 @@ struct Warp {
                     if ((cj >> 17) & 1) {
                         size_t kk = ((size_t)col * nlay + k) * 15;
                         FT tsa, tsga;
-                        lookup_aerosol(P.aero, ib, P.io.aero_mass + kk, own_aero[j], own_rh_f[j], ta, tsa, tsga);
+                        lookup_aerosol<FUSED>(P.aero, tb(P.aero.dust), ib, P.io.aero_mass + kk, own_aero[j], own_rh_f[j], ta, tsa, tsga);
                         if (!LW && ib + 1 == P.aero.iband_550nm) { aod_e += ta; aod_s += tsa; }   // :96-116
                         if (NOSCAT) {
                             ta = ta - tsa;
@@ -420,11 +448,25 @@ struct Warp {
                 if (FUSED) {
                     // increment_2stream (optics_utils.jl:189-202) is additive in (tau, tau ssa, tau ssa g):
                     // store those products for "aerosol only" and "cloud + aerosol" as two 16-byte groups whose
-                    // fourth word is the pair of eta offsets, so a cell needs one 128-bit load for both
+                    // fourth word is the minor-table offset, so a cell needs one 128-bit load for both
                     const FT a0 = ta, a1 = ta * sa, a2 = ta * sa * ga;
-                    const FT rj = int_as_ft<FT>(((je[0] - 1) * L.n_gpt) | (((je[1] - 1) * L.n_gpt) << 16));
-                    rc[0] = a0; rc[1] = a1; rc[2] = a2; rc[3] = rj;
-                    rc[4] = a0 + tc; rc[5] = a1 + tc * sc; rc[6] = a2 + tc * sc * gc; rc[7] = rj;
+                    // trilinear corner weights (optics_utils.jl:136-181): index = T node * 4 + p node * 2 + eta node,
+                    // eta cell and fraction per T node; the cell sums weight * corner and scales by s1 / s2
+                    const FT ft = colp[4 * k + 0], fp = colp[4 * k + 1];
+                    const FT omft = FT(1) - ft, omfp = FT(1) - fp;
+                    const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
+                    r[0] = wa0 * (FT(1) - fe[0]); r[1] = wa0 * fe[0]; r[2] = wa1 * (FT(1) - fe[0]); r[3] = wa1 * fe[0];
+                    r[4] = wb0 * (FT(1) - fe[1]); r[5] = wb0 * fe[1]; r[6] = wb1 * (FT(1) - fe[1]); r[7] = wb1 * fe[1];
+                    r[8] = smix[0]; r[9] = smix[1];
+                    // element offsets without the g-point: (jp-1, jt, je1) and (jp-1, jt+1, je2) rows of the major
+                    // table, (jt, je1) row of the packed minor table; its (jt+1, je2) row is at ma + (ib - ia)
+                    const int e1 = (je[0] - 1) * L.n_gpt, e2 = (je[1] - 1) * L.n_gpt;
+                    const int rowoff = __float_as_int((float)colp[4 * k + 3]), moff = __float_as_int((float)colp[4 * k + 2]);
+                    r[10] = int_as_ft<FT>(rowoff + e1);
+                    r[11] = int_as_ft<FT>(rowoff + L.n_eta * L.n_gpt + e2);
+                    const FT ma = int_as_ft<FT>(moff + e1);
+                    rc[0] = a0; rc[1] = a1; rc[2] = a2; rc[3] = ma;
+                    rc[4] = a0 + tc; rc[5] = a1 + tc * sc; rc[6] = a2 + tc * sc * gc; rc[7] = ma;
                 } else {
                     if (use_cloud) { rc[0] = tc; rc[1] = sc; rc[2] = gc; }
                     if (use_aero) { rc[3] = ta; rc[4] = sa; rc[5] = ga; }
@@ -432,14 +474,14 @@ struct Warp {
                 }
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {
-                    const FT* totplnk = L.tot_planck + (size_t)L.n_t_plnk * ib;
+                    const FT* totplnk = tb(L.tot_planck) + (size_t)L.n_t_plnk * ib;
                     FT* pb = plk + (size_t)b * 2 * nlev;
-                    pb[k + 1] = interp1d_eq_eval(own_pl_loc[j], own_pl_f[j], totplnk, L.n_t_plnk);
+                    pb[k + 1] = interp1d_eq_eval<FUSED>(own_pl_loc[j], own_pl_f[j], totplnk, L.n_t_plnk);
                     if (k == 0) {
-                        pb[0] = interp1d_eq_eval(p0_loc, p0_f, totplnk, L.n_t_plnk);
-                        pb[nlev + nlay] = interp1d_eq_eval(psfc_loc, psfc_f, totplnk, L.n_t_plnk);
+                        pb[0] = interp1d_eq_eval<FUSED>(p0_loc, p0_f, totplnk, L.n_t_plnk);
+                        pb[nlev + nlay] = interp1d_eq_eval<FUSED>(psfc_loc, psfc_f, totplnk, L.n_t_plnk);
                     }
-                    if (NOSCAT) pb[nlev + k] = interp1d_eq_eval(own_py_loc[j], own_py_f[j], totplnk, L.n_t_plnk);
+                    if (NOSCAT) pb[nlev + k] = interp1d_eq_eval<FUSED>(own_py_loc[j], own_py_f[j], totplnk, L.n_t_plnk);
                 }
             }
         }

@@ -52,15 +52,44 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& a) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-constexpr int kFastWarps = 12;        // warps per CTA = per SM
-constexpr int kFastColsPerWarp = 170; // TMEM columns per warp (3 warps share the 512 columns of a lane quadrant)
+#ifndef RB_FAST_WARPS
+#define RB_FAST_WARPS 12
+#endif
+constexpr int kFastWarps = RB_FAST_WARPS;   // warps per CTA = per SM (a multiple of 4; 12 in production, 8 for A/B experiments)
+constexpr int kFastColsPerWarp = 512 / (kFastWarps / 4);   // TMEM columns per warp: the warps of a lane quadrant share its 512 columns
 constexpr int kAlphaTmemLevels = kFastColsPerWarp - 128 - 1;   // 41 albedos in TMEM (+1 dummy column), the rest in shared memory
 constexpr int kStageStride = 36;      // staging-tile row stride: 16-byte aligned rows, conflict-free 128-bit row reads
 constexpr int kAccStride = 68;        // per-quantity stride of the shared broadband accumulators
 
-struct FastSmem {   // byte offsets from the warp's base, extending SolveParams' layout
-    int off_alpha, off_stage, off_acc;
+struct FastSmem {
+    int off_alpha, off_stage, off_acc;   // byte offsets from the warp's base, extending SolveParams' layout
+    int off_blob, off_vmr;               // CTA-shared: staged small-table block, global-mean vmr array (from the smem base)
+    int staged_bytes;                    // staged prefix of GasLut::blob
 };
+
+// ---- TMA bulk copy global -> shared with mbarrier completion (the small-table block, once per CTA) ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // Raw table corners and band-record words of one (layer, g-point) cell: the loads are issued together
 // (fast_gather) and consumed later (fast_finish), with independent arithmetic of the previous layer in between.
@@ -68,9 +97,10 @@ template <bool LW, int NG> struct FastCell {
     float2 c2[LW ? 8 : 1];   // LW: {kmajor, planck_fraction} corners
     float c1[LW ? 1 : 8];    // SW: kmajor corners
     float4 m[4 * NG];        // per group: four minor-absorber slots (SW slot 0 = Rayleigh) at the four (T, eta) corners
-    float4 r0, x;            // band record: {fe1, fe2, s1, s2}, increment products
-    float4 r1[NG];           // slot scalings
-    float ft, fp;
+    float4 v0, v1;           // band record: trilinear corner weights
+    float4 s;                // s1, s2 (column amounts of the two T nodes), major-table offsets
+    float4 sc[NG];           // slot scalings
+    float4 x;                // increment products (aerosol only or cloud + aerosol), minor-table offset
 };
 
 template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER>
@@ -78,6 +108,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     using FT = float;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(8) uint64_t blob_bar;
     constexpr bool LW = MODE == MODE_LW_2STREAM;
     constexpr bool INCR = HAS_CLD || HAS_AER;
     constexpr int NETA = 9, NT = 14;
@@ -90,10 +121,23 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     // memory bases, table descriptors) lives in uniform registers instead of being re-broadcast with R2UR
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 
+    // Stage this sweep's small tables (GasLut::blob: key species, reference vmr, minor-absorber lists, Planck
+    // table, cloud and aerosol tables) into shared memory with one TMA bulk copy: the persistent CTA reads them
+    // ~10^5 times per column and they would otherwise fight the k-distribution gathers for L1.
+    unsigned char* sblob = smem_raw + F.off_blob;
+    float* svmr = P.vmr_kind == 0 ? reinterpret_cast<float*>(smem_raw + F.off_vmr) : nullptr;
+    if (threadIdx.x == 0) {
+        mbar_init(&blob_bar, 1);
+        mbar_expect_tx(&blob_bar, (uint32_t)F.staged_bytes);
+        if (F.staged_bytes > 0) tma_bulk_g2s(sblob, P.lut.blob, (uint32_t)F.staged_bytes, &blob_bar);
+    }
+    if (svmr != nullptr)
+        for (int i = threadIdx.x; i < P.ngas; i += blockDim.x) svmr[i] = __ldg(P.io.vmr + i);
     if (warp == 0) tmem_alloc(&tmem_base_smem, 512u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mbar_wait(&blob_bar, 0);
     // lane field (bits 31:16) = 32 * (warp % 4); column = 170 * (warp / 4)
     const uint32_t tA = tmem_base_smem + ((uint32_t)(warp & 3) << 21) + (uint32_t)((warp >> 2) * kFastColsPerWarp);
     const uint32_t tAl = tA + 128u;
@@ -109,7 +153,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     const int RW = P.rec_words;
 
     for (long long col = (long long)blockIdx.x * kFastWarps + warp; col < P.ncol; col += (long long)gridDim.x * kFastWarps) {
-        Warp<FT, MODE, 2, true> W(P, wbase, lane, col);
+        Warp<FT, MODE, 2, true> W(P, wbase, lane, col, sblob, F.staged_bytes, svmr);
         W.phase0();
         for (int i = lane; i < 3 * kAccStride; i += 32) accs[i] = FT(0);
 
@@ -156,69 +200,63 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
 
             const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
             const FT* rec_lane = W.rec + bl * RW;          // this lane's band within a record row pair
+            const FT* major_lane = major + (LW ? 2 : 1) * gpt;   // tables offset by this lane's g-point
+            const float4* minor_lane = minor4 + gpt;
             const unsigned mask0 = W.mask[0], mask1 = W.mask[1];
 
             // ---- issue every load of cell (layer k, this g-point): compile-time strides, 64/128-bit gathers ----
             auto gather = [&](int k, FastCell<LW, NG>& G) {
-                const float4 cp = reinterpret_cast<const float4*>(W.colp)[k];   // ft, fp, minor row, major row
                 const FT* r = rec_lane + (k & 31) * 2 * RW;
                 bool cb = false;
                 if (HAS_CLD) cb = ((k < 32 ? mask0 : mask1) >> (k & 31)) & 1u;
-                G.r0 = *reinterpret_cast<const float4*>(r);
-                G.x = *reinterpret_cast<const float4*>(r + 4 + 4 * NG + (cb ? 4 : 0));
+                G.s = *reinterpret_cast<const float4*>(r + 8);
+                G.x = *reinterpret_cast<const float4*>(r + 12 + 4 * NG + (cb ? 4 : 0));
+                G.v0 = *reinterpret_cast<const float4*>(r);
+                G.v1 = *reinterpret_cast<const float4*>(r + 4);
 #pragma unroll
-                for (int gi = 0; gi < NG; ++gi) G.r1[gi] = *reinterpret_cast<const float4*>(r + 4 + 4 * gi);
-                G.ft = cp.x; G.fp = cp.y;
-                const int rj = __float_as_int(G.x.w);
-                const int e1 = (rj & 0xffff) + gpt, e2 = (rj >> 16) + gpt;     // (je - 1) * NGPT + gpt
-                const int ia = __float_as_int(cp.w) + e1;                       // (jp-1, jt,   je1)
-                const int ib = __float_as_int(cp.w) + KT + e2;                  // (jp-1, jt+1, je2)
+                for (int gi = 0; gi < NG; ++gi) G.sc[gi] = *reinterpret_cast<const float4*>(r + 12 + 4 * gi);
+                const int ia = __float_as_int(G.s.z), ib = __float_as_int(G.s.w);   // (jp-1, jt, je1), (jp-1, jt+1, je2)
+                const int ma = __float_as_int(G.x.w), mb = ma + (ib - ia);          // (jt, je1), (jt+1, je2): MT == KT
                 if (LW) {   // {kmajor, planck_fraction} pairs
-                    const float2* pa = reinterpret_cast<const float2*>(major) + ia;
-                    const float2* pb = reinterpret_cast<const float2*>(major) + ib;
+                    const float2* pa = reinterpret_cast<const float2*>(major_lane) + ia;
+                    const float2* pb = reinterpret_cast<const float2*>(major_lane) + ib;
                     G.c2[0] = __ldg(pa); G.c2[1] = __ldg(pa + KE); G.c2[2] = __ldg(pa + KP); G.c2[3] = __ldg(pa + KP + KE);
                     G.c2[4] = __ldg(pb); G.c2[5] = __ldg(pb + KE); G.c2[6] = __ldg(pb + KP); G.c2[7] = __ldg(pb + KP + KE);
                 } else {
-                    const FT* pa = major + ia;
-                    const FT* pb = major + ib;
+                    const FT* pa = major_lane + ia;
+                    const FT* pb = major_lane + ib;
                     G.c1[0] = __ldg(pa); G.c1[1] = __ldg(pa + KE); G.c1[2] = __ldg(pa + KP); G.c1[3] = __ldg(pa + KP + KE);
                     G.c1[4] = __ldg(pb); G.c1[5] = __ldg(pb + KE); G.c1[6] = __ldg(pb + KP); G.c1[7] = __ldg(pb + KP + KE);
                 }
-                const float4* ma = minor4 + (__float_as_int(cp.z) + e1);        // (jt,   je1)
-                const float4* mb = minor4 + (__float_as_int(cp.z) + MT + e2);   // (jt+1, je2)
 #pragma unroll
                 for (int gi = 0; gi < NG; ++gi) {
-                    G.m[4 * gi + 0] = __ldg(ma + gi * MS); G.m[4 * gi + 1] = __ldg(ma + gi * MS + ME);
-                    G.m[4 * gi + 2] = __ldg(mb + gi * MS); G.m[4 * gi + 3] = __ldg(mb + gi * MS + ME);
+                    G.m[4 * gi + 0] = __ldg(minor_lane + ma + gi * MS); G.m[4 * gi + 1] = __ldg(minor_lane + ma + gi * MS + ME);
+                    G.m[4 * gi + 2] = __ldg(minor_lane + mb + gi * MS); G.m[4 * gi + 3] = __ldg(minor_lane + mb + gi * MS + ME);
                 }
             };
             // ---- gas + cloud + aerosol optics of the gathered cell (gas_optics.jl:176-320, optics_utils.jl:85-181) ----
-            auto finish = [&](int k, const FastCell<LW, NG>& G, FT& tau, FT& ssa, FT& g, FT& pfrac) {
-                const FT ft = G.ft, fp = G.fp, fe1 = G.r0.x, fe2 = G.r0.y;
-                const FT omft = 1.f - ft, omfp = 1.f - fp;
-                const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
+            auto finish = [&](const FastCell<LW, NG>& G, FT& tau, FT& ssa, FT& g, FT& pfrac) {
+                const float4 v0 = G.v0, v1 = G.v1;
                 if (LW) {
-                    const float2 *c = G.c2;
-                    const FT ka0 = fmaf(fe1, c[1].x - c[0].x, c[0].x), ka1 = fmaf(fe1, c[3].x - c[2].x, c[2].x);
-                    const FT kb0 = fmaf(fe2, c[5].x - c[4].x, c[4].x), kb1 = fmaf(fe2, c[7].x - c[6].x, c[6].x);
-                    tau = G.r0.z * (wa0 * ka0 + wa1 * ka1) + G.r0.w * (wb0 * kb0 + wb1 * kb1);
-                    const FT pa0 = fmaf(fe1, c[1].y - c[0].y, c[0].y), pa1 = fmaf(fe1, c[3].y - c[2].y, c[2].y);
-                    const FT pb0 = fmaf(fe2, c[5].y - c[4].y, c[4].y), pb1 = fmaf(fe2, c[7].y - c[6].y, c[6].y);
-                    pfrac = (wa0 * pa0 + wa1 * pa1) + (wb0 * pb0 + wb1 * pb1);
+                    const float2* c = G.c2;
+                    tau = G.s.x * (v0.x * c[0].x + v0.y * c[1].x + v0.z * c[2].x + v0.w * c[3].x) +
+                          G.s.y * (v1.x * c[4].x + v1.y * c[5].x + v1.z * c[6].x + v1.w * c[7].x);
+                    pfrac = (v0.x * c[0].y + v0.y * c[1].y + v0.z * c[2].y + v0.w * c[3].y) +
+                            (v1.x * c[4].y + v1.y * c[5].y + v1.z * c[6].y + v1.w * c[7].y);
                 } else {
                     const FT* c = G.c1;
-                    const FT ka0 = fmaf(fe1, c[1] - c[0], c[0]), ka1 = fmaf(fe1, c[3] - c[2], c[2]);
-                    const FT kb0 = fmaf(fe2, c[5] - c[4], c[4]), kb1 = fmaf(fe2, c[7] - c[6], c[6]);
-                    tau = G.r0.z * (wa0 * ka0 + wa1 * ka1) + G.r0.w * (wb0 * kb0 + wb1 * kb1);
+                    tau = G.s.x * (v0.x * c[0] + v0.y * c[1] + v0.z * c[2] + v0.w * c[3]) +
+                          G.s.y * (v1.x * c[4] + v1.y * c[5] + v1.z * c[6] + v1.w * c[7]);
                     pfrac = 0.f;
                 }
-                // minor absorbers (+ Rayleigh in SW slot 0): four slots per 128-bit load (optics_utils.jl:85-98)
-                const FT w11 = (1.f - fe1) * omft, w21 = fe1 * omft, w12 = (1.f - fe2) * ft, w22 = fe2 * ft;
+                // minor absorbers (+ Rayleigh in SW slot 0): four slots per 128-bit load (optics_utils.jl:85-98);
+                // the (T, eta) weights are the corner weights summed over the two pressure nodes
+                const FT w11 = v0.x + v0.z, w21 = v0.y + v0.w, w12 = v1.x + v1.z, w22 = v1.y + v1.w;
                 FT tau_ray = 0.f;
 #pragma unroll
                 for (int gi = 0; gi < NG; ++gi) {   // real tables can have more than four (three in SW) minors per band
                     const float4 m11 = G.m[4 * gi], m21 = G.m[4 * gi + 1], m12 = G.m[4 * gi + 2], m22 = G.m[4 * gi + 3];
-                    const float4 sc = G.r1[gi];
+                    const float4 sc = G.sc[gi];
                     const FT v0 = w11 * m11.x + w21 * m21.x + w12 * m12.x + w22 * m22.x;
                     const FT v1 = w11 * m11.y + w21 * m21.y + w12 * m12.y + w22 * m22.y;
                     const FT v2 = w11 * m11.z + w21 * m21.z + w12 * m12.z + w22 * m22.z;
@@ -276,7 +314,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 build_records(0);
                 FT tau, ssa, g, pf;
                 gather(0, G);
-                finish(0, G, tau, ssa, g, pf);
+                finish(G, tau, ssa, g, pf);
                 FT lev_bot = pbk[0] * pf;
                 FT albedo = 1.f - emis;
                 FT src = Num<FT>::pi() * emis * (pbk[nlev + nlay] * pf);
@@ -303,7 +341,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                         const FT denom = hdiv(1.f, 1.f - C.Rdif * albedo);
                         const FT bk = pbk[k];
                         const FT inc_k = bk * pf;
-                        finish(k, G, tau, ssa, g, pf);
+                        finish(G, tau, ssa, g, pf);
                         const FT lev_top = hsqrt(inc_k * (bk * pf));
                         stage[(k - ks) * kStageStride + lane] = close_layer(k - 1, C, denom, lev_top);
                     }
@@ -369,7 +407,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 build_records(nlay > 32 ? 1 : 0);
                 FT tau, ssa, g, pf;
                 gather(nlay - 1, G);
-                finish(nlay - 1, G, tau, ssa, g, pf);
+                finish(G, tau, ssa, g, pf);
                 // layer k: coefficients, TMEM store, marching update; returns d_{k+1} (before the update)
                 auto march = [&](int k) -> FT {
                     FT Rdir, Tdir, Rdif, Tdif;
@@ -395,7 +433,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                         gather(j, G);
                         stage[((j - jc) * 2 + 0) * kStageStride + lane] = march(j + 1);
                         stage[((j - jc) * 2 + 1) * kStageStride + lane] = dir;
-                        finish(j, G, tau, ssa, g, pf);
+                        finish(G, tau, ssa, g, pf);
                     }
                     __syncwarp();
                     {
