@@ -48,6 +48,11 @@ enum { RRTMGP_B200_TWO_STREAM = 0, RRTMGP_B200_ONE_SCALAR = 1 };
 /* VolumeMixingRatios.jl:34-43 (VmrGM) and :75-78 (Vmr) */
 enum { RRTMGP_B200_VMR_GM = 0, RRTMGP_B200_VMR_FULL = 1 };
 
+/* AbstractInterpolation / AbstractBottomExtrapolation (src/api/interpolation.jl:40-135) */
+enum { RRTMGP_B200_NO_INTERPOLATION = 0, RRTMGP_B200_ARITHMETIC_MEAN = 1, RRTMGP_B200_GEOMETRIC_MEAN = 2,
+       RRTMGP_B200_UNIFORM_Z = 3, RRTMGP_B200_UNIFORM_P = 4, RRTMGP_B200_BEST_FIT = 5 };
+enum { RRTMGP_B200_SAME_AS_INTERPOLATION = 0, RRTMGP_B200_USE_SURFACE_TEMP_AT_BOTTOM = 1, RRTMGP_B200_HYDROSTATIC_BOTTOM = 2 };
+
 /* Mirrors what `RRTMGPSolver(grid_params, radiation_method, params, ...; op_lw, n_gauss_angles,
  * spectral_fluxes, deep_atmosphere_inverse_scaling)` fixes at construction
  * (src/api/solver.jl:136-331, src/api/grid_params.jl:38-54, src/Parameters.jl:6-14). */
@@ -138,7 +143,15 @@ int rrtmgp_b200_lut_info(const rrtmgp_b200_handle_t* h, rrtmgp_b200_lut_info_t* 
 /* Registers the caller-owned device arrays (the struct is copied). */
 int rrtmgp_b200_bind(rrtmgp_b200_handle_t* h, const rrtmgp_b200_buffers_t* bufs);
 
-/* prepare_atmosphere!(s) (update_fluxes.jl:252-281): boundary layer fill, clip!, col_dry; in place. */
+/* The `interpolation` / `bottom_extrapolation` / `center_z` / `face_z` keywords of RRTMGPSolver (solver.jl:136-147,
+ * 183-193): from now on prepare_atmosphere! first fills p_lev / t_lev of the domain faces from the layer values
+ * (interpolate_levels!, grid_adaptation.jl:87-113; interp! / extrap!, interpolation.jl:176-252).  `center_z`
+ * [ncol][nlay] and `face_z` [ncol][nlev] are caller-owned device arrays, required by BEST_FIT and HYDROSTATIC_BOTTOM
+ * (else NULL); cp_d, R_d are Parameters.cp_d / R_d, used by the two bottom-only extrapolations. */
+int rrtmgp_b200_set_level_interpolation(rrtmgp_b200_handle_t* h, int32_t interpolation, int32_t bottom_extrapolation,
+                                        const void* center_z, const void* face_z, double cp_d, double R_d);
+
+/* prepare_atmosphere!(s) (update_fluxes.jl:252-281): level interpolation, boundary layer fill, clip!, col_dry; in place. */
 int rrtmgp_b200_prepare_atmosphere(rrtmgp_b200_handle_t* h, void* stream);
 /* update_lw_fluxes!(s) / update_sw_fluxes!(s) / update_net_fluxes!(s) (update_fluxes.jl:12-16,74-78,165-194).
  * `have_seed == 0` mirrors `seedval = nothing`: an internal per-call counter keys the McICA draws. */
@@ -158,6 +171,10 @@ int rrtmgp_b200_update_fluxes_range(rrtmgp_b200_handle_t* h, uint64_t seed, int 
 /* compute_relative_humidity!(...) (src/optics/column_amounts.jl:52-76, gas_optics.jl:58-80): a host
  * duty in the reference (grid_adaptation.jl:267-270); writes layerdata[..][3]. */
 int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream);
+
+/* heating_rate(s) (src/api/standalone.jl:106-124, GrayAtmosphere.jl:152-167): (grav / cp_d) dF_net/dp of the domain
+ * layers from any [ncol][nlev] net-flux array and the bound p_lev; `heating_rate` is [ncol][domain nlay]. */
+int rrtmgp_b200_heating_rate(rrtmgp_b200_handle_t* h, const void* flux_net, void* heating_rate, double cp_d, void* stream);
 
 /* Diagnostics: kernels launched by the last update_* call; last CUDA error string. */
 int rrtmgp_b200_last_launch_count(const rrtmgp_b200_handle_t* h);

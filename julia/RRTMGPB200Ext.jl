@@ -73,8 +73,23 @@ function B200Engine(s::RRTMGPSolver, lut_pack::Vector{UInt8}; col_offset = 0)
     e = B200Engine(h[])
     finalizer(x -> ccall((:rrtmgp_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), e)
     bind!(e, s)
+    # interpolation / bottom_extrapolation / center_z / face_z of the solver (src/api/solver.jl:136-147,183-193)
+    check(ccall((:rrtmgp_b200_set_level_interpolation, LIB), Cint,
+                (Ptr{Cvoid}, Int32, Int32, CuPtr{Cvoid}, CuPtr{Cvoid}, Float64, Float64), e.handle,
+                interpolation_code(s.interpolation), bottom_code(s.bottom_extrapolation), devptr(s.center_z), devptr(s.face_z),
+                RRTMGP.Parameters.cp_d(s.params), RRTMGP.Parameters.R_d(s.params)))
     return e
 end
+
+interpolation_code(::RRTMGP.NoInterpolation) = 0
+interpolation_code(::RRTMGP.ArithmeticMean) = 1
+interpolation_code(::RRTMGP.GeometricMean) = 2
+interpolation_code(::RRTMGP.UniformZ) = 3
+interpolation_code(::RRTMGP.UniformP) = 4
+interpolation_code(::RRTMGP.BestFit) = 5
+bottom_code(::RRTMGP.SameAsInterpolation) = 0
+bottom_code(::RRTMGP.UseSurfaceTempAtBottom) = 1
+bottom_code(::RRTMGP.HydrostaticBottom) = 2
 
 function bind!(e::B200Engine, s::RRTMGPSolver)
     as = s.as; cs = as.cloud_state; ae = as.aerosol_state
@@ -113,6 +128,15 @@ function update_fluxes!(e::B200Engine, seedval = nothing)
 end
 prepare_atmosphere!(e::B200Engine) =
     (check(ccall((:rrtmgp_b200_prepare_atmosphere, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, CUDA.stream().handle)); nothing)
+
+# heating_rate(s) (src/api/standalone.jl:106-124): allocates and returns a fresh (nlay, ncol) array
+function heating_rate(e::B200Engine, s::RRTMGPSolver)
+    nlay = s.grid_params.nlay - Int(s.grid_params.isothermal_boundary_layer)
+    hr = similar(RRTMGP.net_flux(s), nlay, s.grid_params.ncol)
+    check(ccall((:rrtmgp_b200_heating_rate, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Float64, Ptr{Cvoid}), e.handle,
+                devptr(s.net_flux_buffer), devptr(hr), RRTMGP.Parameters.cp_d(s.params), CUDA.stream().handle))
+    return hr
+end
 
 # LUT pack writer: name -> Array in the post-load layouts of src/optics/LookUpTables.jl
 # (format: rrtmgp.jl_b200/lutpack.py; names: rrtmgp.jl_b200/synthetic.py `make_lut_arrays`).

@@ -86,6 +86,7 @@ def lib():
         _lib.oracle_gray_solve_sw.argtypes = [C.c_int] * 5 + [dp] + [vp] * 12
         _lib.oracle_gray_heating_rate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double, vp]
         _lib.oracle_gray_update_profile.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] + [vp] * 7
+        _lib.oracle_interpolate_levels.argtypes = [C.c_int] * 6 + [vp] * 5 + [C.c_double] * 3 + [vp] * 2
     return _lib
 
 
@@ -269,3 +270,28 @@ def solve_gray(dtype, nlay=60, ncol=1, *, latitude=None, inc_flux=None, scaling=
             s[k] = s[k] * sc
     net = lw["net"] + s["net"]
     return dict(state=st, lw=lw, sw=s, net=net, heating_rate=gray_heating_rate(net, st["p_lev"], params))
+
+
+INTERPOLATIONS = {"none": 0, "arithmetic_mean": 1, "geometric_mean": 2, "uniform_z": 3, "uniform_p": 4, "best_fit": 5}
+BOTTOM_EXTRAPOLATIONS = {"same_as_interpolation": 0, "use_surface_temp_at_bottom": 1, "hydrostatic_bottom": 2}
+
+
+def interpolate_levels(p_lay, t_lay, t_sfc, interpolation, bottom_extrapolation="same_as_interpolation", *,
+                       center_z=None, face_z=None, nlay=None, params=GRAY_PARAMS, p_lev=None, t_lev=None):
+    """`interpolate_levels!` (src/api/grid_adaptation.jl:87-113) with `interp!` / `extrap!`
+    (src/api/interpolation.jl:176-252).  Arrays are [ncol][nlay] / [ncol][nlay + 1]; `nlay` restricts the
+    domain (isothermal boundary layer on top).  Returns (p_lev, t_lev)."""
+    dt = p_lay.dtype
+    ncol, stride = p_lay.shape
+    nlay = stride if nlay is None else nlay
+    cp_d = params["gas_constant"] / params["molmass_dryair"] / params["kappa_d"]
+    r_d = params["gas_constant"] / params["molmass_dryair"]
+    p_lev = np.zeros((ncol, stride + 1), dtype=dt) if p_lev is None else p_lev
+    t_lev = np.zeros((ncol, stride + 1), dtype=dt) if t_lev is None else t_lev
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    p_lay, t_lay, t_sfc, center_z, face_z = c(p_lay), c(t_lay), c(t_sfc), c(center_z), c(face_z)
+    lib().oracle_interpolate_levels(int(dt == np.float64), ncol, nlay, stride, INTERPOLATIONS[interpolation],
+                                    BOTTOM_EXTRAPOLATIONS[bottom_extrapolation], _ptr(p_lay), _ptr(t_lay), _ptr(t_sfc),
+                                    _ptr(center_z), _ptr(face_z), float(dt.type(params["grav"])), float(dt.type(cp_d)),
+                                    float(dt.type(r_d)), _ptr(p_lev), _ptr(t_lev))
+    return p_lev, t_lev

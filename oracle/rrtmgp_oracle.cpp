@@ -1498,3 +1498,79 @@ void oracle_gray_update_profile(int is_f64, int ncol, int nlay, double stefan, d
                                              (float*)flux_grad));
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Level <- layer interpolation and bottom extrapolation (src/api/interpolation.jl:176-252),
+// driven as interpolate_levels! does (src/api/grid_adaptation.jl:87-113).
+// Arrays [ncol][nlay_stride] / [ncol][nlay_stride + 1]; `nlay` = domain layers (<= nlay_stride).
+// interpolation: 1 ArithmeticMean, 2 GeometricMean, 3 UniformZ, 4 UniformP, 5 BestFit (0 = NoInterpolation);
+// bottom: 0 SameAsInterpolation, 1 UseSurfaceTempAtBottom, 2 HydrostaticBottom.
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <typename FT> FT uniform_z_p(FT T, FT p1, FT T1, FT p2, FT T2) {   // interpolation.jl:152-153
+    return T1 == T2 ? std::sqrt(p1 * p2) : p1 * std::pow(p2 / p1, std::log(T / T1) / std::log(T2 / T1));
+}
+template <typename FT> FT best_fit_p(FT T, FT z, FT p1, FT T1, FT z1, FT p2, FT T2, FT z2) {   // interpolation.jl:162-164
+    return T1 == T2 ? p1 * std::pow(p2 / p1, (z - z1) / (z2 - z1)) : p1 * std::pow(p2 / p1, std::log(T / T1) / std::log(T2 / T1));
+}
+// interp!(scheme, p, T, p_dn, T_dn, p_up, T_up) (interpolation.jl:176-196)
+template <typename FT>
+void interp_face(int scheme, FT& p, FT& T, FT z, FT pd, FT Td, FT zd, FT pu, FT Tu, FT zu) {
+    switch (scheme) {
+        case 1: T = (Td + Tu) / 2; p = (pd + pu) / 2; break;
+        case 2: T = std::sqrt(Td * Tu); p = std::sqrt(pd * pu); break;
+        case 3: T = (Td + Tu) / 2; p = uniform_z_p(T, pd, Td, pu, Tu); break;
+        case 4: p = (pd + pu) / 2; T = Td * std::pow(Tu / Td, std::log(p / pd) / std::log(pu / pd)); break;
+        case 5: T = Td + (Tu - Td) * (z - zd) / (zu - zd); p = best_fit_p(T, z, pd, Td, zd, pu, Tu, zu); break;
+    }
+}
+// extrap!(scheme, p, T, p1, T1, p2, T2, Ts, params) (interpolation.jl:207-252); scheme 6 / 7 = the two
+// bottom-only extrapolations
+template <typename FT>
+void extrap_face(int scheme, FT& p, FT& T, FT z, FT p1, FT T1, FT z1, FT p2, FT T2, FT z2, FT Ts, FT grav, FT cp, FT R) {
+    switch (scheme) {
+        case 1: T = (3 * T1 - T2) / 2; p = (3 * p1 - p2) / 2; break;
+        case 2: T = std::sqrt(T1 * T1 * T1 / T2); p = std::sqrt(p1 * p1 * p1 / p2); break;
+        case 3: T = (3 * T1 - T2) / 2; p = uniform_z_p(T, p1, T1, p2, T2); break;
+        case 4: p = (3 * p1 - p2) / 2; T = T1 * std::pow(T2 / T1, std::log(p / p1) / std::log(p2 / p1)); break;
+        case 5: T = T1 + (T2 - T1) * (z - z1) / (z2 - z1); p = best_fit_p(T, z, p1, T1, z1, p2, T2, z2); break;
+        case 6: T = Ts; p = p1 * std::pow(T / T1, cp / R); break;                         // UseSurfaceTempAtBottom
+        case 7: T = T1 + grav / cp * (z1 - z); p = p1 * std::pow(T / T1, cp / R); break;  // HydrostaticBottom
+    }
+}
+template <typename FT>
+void interpolate_levels(int ncol, int nlay, int stride, int interpolation, int bottom, const FT* p_lay, const FT* t_lay,
+                        const FT* t_sfc, const FT* zc, const FT* zf, double grav, double cp_d, double r_d, FT* p_lev, FT* t_lev) {
+    if (interpolation == 0) return;   // NoInterpolation (grid_adaptation.jl:73-79)
+    for (int c = 0; c < ncol; ++c) {
+        const FT* pl = p_lay + (size_t)c * stride; const FT* tl = t_lay + (size_t)c * stride;
+        const FT* zl = zc ? zc + (size_t)c * stride : nullptr; const FT* ze = zf ? zf + (size_t)c * (stride + 1) : nullptr;
+        FT* pe = p_lev + (size_t)c * (stride + 1); FT* te = t_lev + (size_t)c * (stride + 1);
+        auto Z = [](const FT* a, int i) { return a ? a[i] : FT(0); };
+        for (int i = 1; i < nlay; ++i)   // faces 2:nlay between layers i-1 (below) and i (above), :103
+            interp_face<FT>(interpolation, pe[i], te[i], Z(ze, i), pl[i - 1], tl[i - 1], Z(zl, i - 1), pl[i], tl[i], Z(zl, i));
+        // top face from the two layers below it (:105)
+        extrap_face<FT>(interpolation, pe[nlay], te[nlay], Z(ze, nlay), pl[nlay - 1], tl[nlay - 1], Z(zl, nlay - 1),
+                        pl[nlay - 2], tl[nlay - 2], Z(zl, nlay - 2), t_sfc[c], (FT)grav, (FT)cp_d, (FT)r_d);
+        // bottom face (:106-111)
+        const int mode = bottom == 0 ? interpolation : 5 + bottom;
+        extrap_face<FT>(mode, pe[0], te[0], Z(ze, 0), pl[0], tl[0], Z(zl, 0), pl[1], tl[1], Z(zl, 1), t_sfc[c], (FT)grav,
+                        (FT)cp_d, (FT)r_d);
+    }
+}
+}  // namespace
+
+extern "C" {
+void oracle_interpolate_levels(int is_f64, int ncol, int nlay, int stride, int interpolation, int bottom, const void* p_lay,
+                               const void* t_lay, const void* t_sfc, const void* center_z, const void* face_z, double grav,
+                               double cp_d, double r_d, void* p_lev, void* t_lev) {
+    if (is_f64)
+        interpolate_levels<double>(ncol, nlay, stride, interpolation, bottom, (const double*)p_lay, (const double*)t_lay,
+                                   (const double*)t_sfc, (const double*)center_z, (const double*)face_z, grav, cp_d, r_d,
+                                   (double*)p_lev, (double*)t_lev);
+    else
+        interpolate_levels<float>(ncol, nlay, stride, interpolation, bottom, (const float*)p_lay, (const float*)t_lay,
+                                  (const float*)t_sfc, (const float*)center_z, (const float*)face_z, grav, cp_d, r_d,
+                                  (float*)p_lev, (float*)t_lev);
+}
+}  // extern "C"

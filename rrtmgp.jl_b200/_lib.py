@@ -47,11 +47,16 @@ class LutInfo(C.Structure):
         (n, C.c_double) for n in ("p_ref_min", "t_ref_min", "t_ref_max", "solar_src_tot")]
 
 
+# AbstractInterpolation / AbstractBottomExtrapolation (src/api/interpolation.jl:40-135)
+INTERPOLATIONS = {"NoInterpolation": 0, "ArithmeticMean": 1, "GeometricMean": 2, "UniformZ": 3, "UniformP": 4, "BestFit": 5}
+BOTTOM_EXTRAPOLATIONS = {"SameAsInterpolation": 0, "UseSurfaceTempAtBottom": 1, "HydrostaticBottom": 2}
+
 # every symbol include/rrtmgp_b200.h declares
 EXPORTS = ("rrtmgp_b200_create", "rrtmgp_b200_destroy", "rrtmgp_b200_load_luts", "rrtmgp_b200_lut_info",
            "rrtmgp_b200_bind", "rrtmgp_b200_prepare_atmosphere", "rrtmgp_b200_update_lw_fluxes",
            "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_net_fluxes", "rrtmgp_b200_update_fluxes",
            "rrtmgp_b200_update_fluxes_range",
+           "rrtmgp_b200_set_level_interpolation", "rrtmgp_b200_heating_rate",
            "rrtmgp_b200_compute_relative_humidity", "rrtmgp_b200_last_launch_count",
            "rrtmgp_b200_last_cuda_error", "rrtmgp_b200_strerror", "rrtmgp_b200_abi_version")
 
@@ -87,6 +92,8 @@ def lib():
         L.rrtmgp_b200_update_net_fluxes.argtypes = [H, C.c_void_p]
         L.rrtmgp_b200_update_fluxes_range.argtypes = [H, C.c_uint64, C.c_int, C.c_int64, C.c_int32, C.c_void_p]
         L.rrtmgp_b200_compute_relative_humidity.argtypes = [H, C.c_void_p]
+        L.rrtmgp_b200_set_level_interpolation.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.rrtmgp_b200_heating_rate.argtypes = [H, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.rrtmgp_b200_last_launch_count.argtypes = [H]
         L.rrtmgp_b200_last_cuda_error.argtypes = [H]
         L.rrtmgp_b200_last_cuda_error.restype = C.c_char_p

@@ -22,6 +22,11 @@ struct rrtmgp_b200_handle {
     unsigned long long call_counter = 0;
     int last_launches = 0;
     char cuda_err[256] = {0};
+    // interpolate_levels! configuration (rrtmgp_b200_set_level_interpolation)
+    int interpolation = RRTMGP_B200_NO_INTERPOLATION, bottom_extrapolation = RRTMGP_B200_SAME_AS_INTERPOLATION;
+    const void* center_z = nullptr;
+    const void* face_z = nullptr;
+    double cp_d = 0, r_d = 0;
 };
 
 namespace {
@@ -60,6 +65,74 @@ __global__ void boundary_layer_kernel(rrtmgp_b200_buffers_t B, long long col0, i
         FT* am = (FT*)B.aero_mass; FT* as = (FT*)B.aero_size;
         for (int i = 0; i < 15; ++i) { am[k * 15 + i] = am[(k - 1) * 15 + i]; as[k * 15 + i] = as[(k - 1) * 15 + i]; }
     }
+}
+
+// interpolate_levels! (grid_adaptation.jl:87-113) with interp! / extrap! (interpolation.jl:176-252); thread per
+// (column, domain face).  `mode` of a face: 1..5 interpolation scheme, 6 UseSurfaceTempAtBottom, 7 HydrostaticBottom.
+template <typename FT> __device__ __forceinline__ FT lev_pow(FT a, FT b);
+template <> __device__ __forceinline__ float lev_pow<float>(float a, float b) { return powf(a, b); }
+template <> __device__ __forceinline__ double lev_pow<double>(double a, double b) { return pow(a, b); }
+template <typename FT> __device__ __forceinline__ FT lev_sqrt(FT a);
+template <> __device__ __forceinline__ float lev_sqrt<float>(float a) { return sqrtf(a); }
+template <> __device__ __forceinline__ double lev_sqrt<double>(double a) { return sqrt(a); }
+
+template <typename FT>
+__device__ __forceinline__ FT power_law_p(FT T, FT p1, FT T1, FT p2, FT T2) {   // interpolation.jl:152-153,162-164
+    return p1 * lev_pow(p2 / p1, rlog(T / T1) / rlog(T2 / T1));
+}
+
+template <typename FT>
+__global__ void interpolate_levels_kernel(rrtmgp_b200_buffers_t B, long long col0, int ncol, int nlay_total, int nlay,
+                                          int interpolation, int bottom, const FT* center_z, const FT* face_z, FT grav,
+                                          FT cp_d, FT r_d) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)ncol * (nlay + 1)) return;
+    const long long lcol = idx / (nlay + 1);
+    const int f = (int)(idx - lcol * (nlay + 1));            // face 0 = bottom, nlay = top of the domain
+    const long long col = col0 + lcol;
+    const FT* ld = (const FT*)B.layerdata + (size_t)col * nlay_total * 4;
+    const FT* zc = center_z ? center_z + (size_t)col * nlay_total : nullptr;
+    const FT* zf = face_z ? face_z + (size_t)col * (nlay_total + 1) : nullptr;
+    // the two layers the face is computed from: interior faces (below, above); boundary faces (nearest, next)
+    const int l1 = f == 0 ? 0 : (f == nlay ? nlay - 1 : f - 1);
+    const int l2 = f == 0 ? 1 : (f == nlay ? nlay - 2 : f);
+    const FT p1 = ld[4 * l1 + 1], T1 = ld[4 * l1 + 2], p2 = ld[4 * l2 + 1], T2 = ld[4 * l2 + 2];
+    const FT z = zf ? zf[f] : FT(0), z1 = zc ? zc[l1] : FT(0), z2 = zc ? zc[l2] : FT(0);
+    const bool boundary = f == 0 || f == nlay;
+    const int mode = (f == 0 && bottom != RRTMGP_B200_SAME_AS_INTERPOLATION) ? 5 + bottom : interpolation;
+    FT p, T;
+    if (mode == RRTMGP_B200_ARITHMETIC_MEAN) {
+        T = boundary ? (FT(3) * T1 - T2) / FT(2) : (T1 + T2) / FT(2);
+        p = boundary ? (FT(3) * p1 - p2) / FT(2) : (p1 + p2) / FT(2);
+    } else if (mode == RRTMGP_B200_GEOMETRIC_MEAN) {
+        T = boundary ? lev_sqrt(T1 * T1 * T1 / T2) : lev_sqrt(T1 * T2);
+        p = boundary ? lev_sqrt(p1 * p1 * p1 / p2) : lev_sqrt(p1 * p2);
+    } else if (mode == RRTMGP_B200_UNIFORM_Z) {
+        T = boundary ? (FT(3) * T1 - T2) / FT(2) : (T1 + T2) / FT(2);
+        p = T1 == T2 ? lev_sqrt(p1 * p2) : power_law_p(T, p1, T1, p2, T2);
+    } else if (mode == RRTMGP_B200_UNIFORM_P) {
+        p = boundary ? (FT(3) * p1 - p2) / FT(2) : (p1 + p2) / FT(2);
+        T = T1 * lev_pow(T2 / T1, rlog(p / p1) / rlog(p2 / p1));   // assumes p1 != p2 (interpolation.jl:188,222)
+    } else if (mode == RRTMGP_B200_BEST_FIT) {
+        T = T1 + (T2 - T1) * (z - z1) / (z2 - z1);
+        p = T1 == T2 ? p1 * lev_pow(p2 / p1, (z - z1) / (z2 - z1)) : power_law_p(T, p1, T1, p2, T2);
+    } else {   // bottom face only: dry isentrope through the first layer (interpolation.jl:227-252)
+        T = mode == 5 + RRTMGP_B200_USE_SURFACE_TEMP_AT_BOTTOM ? ((const FT*)B.t_sfc)[col] : T1 + grav / cp_d * (z1 - z);
+        p = p1 * lev_pow(T / T1, cp_d / r_d);
+    }
+    ((FT*)B.p_lev)[(size_t)col * (nlay_total + 1) + f] = p;
+    ((FT*)B.t_lev)[(size_t)col * (nlay_total + 1) + f] = T;
+}
+
+// heating_rate (standalone.jl:106-124, GrayAtmosphere.jl:152-167): (g / cp) dF_net / dp per domain layer
+template <typename FT>
+__global__ void heating_rate_kernel(const FT* flux_net, const FT* p_lev, FT* hr, int ncol, int nlay_total, int nlay, FT grav, FT cp_d) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)ncol * nlay) return;
+    const long long col = idx / nlay;
+    const int l = (int)(idx - col * nlay);
+    const size_t k = (size_t)col * (nlay_total + 1) + l;
+    hr[(size_t)col * nlay + l] = grav * (flux_net[k + 1] - flux_net[k]) / (p_lev[k + 1] - p_lev[k]) / cp_d;
 }
 
 // clip! (grid_adaptation.jl:232-258) + compute_col_gas_kernel! (gas_optics.jl:16-41); thread per (col, level)
@@ -257,6 +330,14 @@ template <typename FT> int prepare_t(rrtmgp_b200_handle* h, long long c0, int co
     const rrtmgp_b200_config_t& c = h->cfg;
     const LutStore& L = h->luts;
     const int idx_h2o = luts_of<FT>(h).lw.idx_h2o;
+    if (h->interpolation != RRTMGP_B200_NO_INTERPOLATION) {   // update_fluxes.jl:256-264
+        const int nlay_dom = c.nlay - (c.isothermal_boundary_layer ? 1 : 0);
+        const long long nf = (long long)count * (nlay_dom + 1);
+        interpolate_levels_kernel<FT><<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(
+            h->buf, c0, count, c.nlay, nlay_dom, h->interpolation, h->bottom_extrapolation, (const FT*)h->center_z,
+            (const FT*)h->face_z, (FT)c.grav, (FT)h->cp_d, (FT)h->r_d);
+        ++h->last_launches;
+    }
     if (c.isothermal_boundary_layer) {
         boundary_layer_kernel<FT><<<(count + 127) / 128, 128, 0, s>>>(h->buf, c0, count, c.nlay, c.ngas, c.vmr_kind, (FT)L.p_ref_min);
         ++h->last_launches;
@@ -464,6 +545,46 @@ int rrtmgp_b200_update_fluxes_range(rrtmgp_b200_handle_t* h, uint64_t seed, int 
     DeviceGuard g(h->cfg.device);
     h->last_launches = 0;
     return update_range(h, (unsigned long long)seed, col_begin, col_count, (cudaStream_t)stream);
+}
+
+int rrtmgp_b200_set_level_interpolation(rrtmgp_b200_handle_t* h, int32_t interpolation, int32_t bottom_extrapolation,
+                                        const void* center_z, const void* face_z, double cp_d, double R_d) {
+    if (!h) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (interpolation < RRTMGP_B200_NO_INTERPOLATION || interpolation > RRTMGP_B200_BEST_FIT) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (bottom_extrapolation < RRTMGP_B200_SAME_AS_INTERPOLATION || bottom_extrapolation > RRTMGP_B200_HYDROSTATIC_BOTTOM)
+        return RRTMGP_B200_ERR_INVALID_ARG;
+    // solver.jl:183-193: the z-based schemes read the altitudes at solve time
+    const bool needs_z = interpolation == RRTMGP_B200_BEST_FIT ||
+                         (interpolation != RRTMGP_B200_NO_INTERPOLATION && bottom_extrapolation == RRTMGP_B200_HYDROSTATIC_BOTTOM);
+    if (needs_z && (!center_z || !face_z)) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (interpolation != RRTMGP_B200_NO_INTERPOLATION && bottom_extrapolation != RRTMGP_B200_SAME_AS_INTERPOLATION &&
+        (!(cp_d > 0) || !(R_d > 0)))
+        return RRTMGP_B200_ERR_INVALID_ARG;
+    if (interpolation != RRTMGP_B200_NO_INTERPOLATION && h->cfg.nlay - (h->cfg.isothermal_boundary_layer ? 1 : 0) < 2)
+        return RRTMGP_B200_ERR_INVALID_ARG;
+    h->interpolation = interpolation; h->bottom_extrapolation = bottom_extrapolation;
+    h->center_z = center_z; h->face_z = face_z; h->cp_d = cp_d; h->r_d = R_d;
+    return RRTMGP_B200_OK;
+}
+
+int rrtmgp_b200_heating_rate(rrtmgp_b200_handle_t* h, const void* flux_net, void* heating_rate, double cp_d, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    if (!flux_net || !heating_rate || !(cp_d > 0)) return RRTMGP_B200_ERR_INVALID_ARG;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 1;
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const int nlay_dom = c.nlay - (c.isothermal_boundary_layer ? 1 : 0);
+    const long long n = (long long)c.ncol * nlay_dom;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (c.dtype == 1)
+        heating_rate_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)flux_net, (const double*)h->buf.p_lev,
+                                                                            (double*)heating_rate, c.ncol, c.nlay, nlay_dom, c.grav, cp_d);
+    else
+        heating_rate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)flux_net, (const float*)h->buf.p_lev,
+                                                                           (float*)heating_rate, c.ncol, c.nlay, nlay_dom, (float)c.grav, (float)cp_d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RRTMGP_B200_OK : fail_cuda(h, e);
 }
 
 int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream) {

@@ -96,7 +96,8 @@ class RRTMGPSolver:
                  op_lw: str = "two_stream", n_gauss_angles: int = 1, spectral_fluxes: bool = False,
                  deep_atmosphere_inverse_scaling: Optional[torch.Tensor] = None, vmr_kind: str = "gm",
                  ngas: Optional[int] = None, ice_rgh: int = 2, inc_flux_lw: bool = False, with_lat: bool = False,
-                 col_offset: int = 0):
+                 col_offset: int = 0, interpolation: str = "NoInterpolation",
+                 bottom_extrapolation: str = "SameAsInterpolation", center_z=None, face_z=None):
         if type(radiation_method) not in _METHOD_CODE:
             raise TypeError("radiation_method must be ClearSkyRadiation, AllSkyRadiation or "
                             "AllSkyRadiationWithClearSkyDiagnostics (GrayRadiation is not on this path)")
@@ -106,8 +107,17 @@ class RRTMGPSolver:
         if n_gauss_angles != 1 and op_lw != "one_scalar":
             raise ValueError(f"`n_gauss_angles = {n_gauss_angles}` applies only to the non-scattering longwave "
                              "solver; pass op_lw='one_scalar', or keep n_gauss_angles = 1")
+        if interpolation not in _lib.INTERPOLATIONS or bottom_extrapolation not in _lib.BOTTOM_EXTRAPOLATIONS:
+            raise ValueError(f"interpolation must be one of {sorted(_lib.INTERPOLATIONS)} and bottom_extrapolation "
+                             f"one of {sorted(_lib.BOTTOM_EXTRAPOLATIONS)}")
+        # solver.jl:183-193: z-based interpolation / extrapolation reads the altitudes at solve time
+        if (interpolation == "BestFit" or (interpolation != "NoInterpolation" and bottom_extrapolation == "HydrostaticBottom")) \
+                and (center_z is None or face_z is None):
+            raise ValueError("BestFit interpolation and HydrostaticBottom extrapolation need layer and level "
+                             "altitudes; pass `center_z` and `face_z` to the `RRTMGPSolver`")
         if not torch.cuda.is_available():
             raise RuntimeError("RRTMGPSolver needs a CUDA device (there is no CPU fallback)")
+        self.interpolation, self.bottom_extrapolation = interpolation, bottom_extrapolation
         self.grid_params = grid_params
         self.radiation_method = radiation_method
         self.params = dict(params)
@@ -185,6 +195,22 @@ class RRTMGPSolver:
             for k, t in B.items():
                 setattr(cb, k, None if t is None else t.data_ptr())
             check(L.rrtmgp_b200_bind(self._h, C.byref(cb)), self._h)
+            # level interpolation (solver.jl:136-147; Parameters.cp_d / R_d as in src/Parameters.jl)
+            self.center_z = self.face_z = None
+            if center_z is not None and face_z is not None:
+                self.center_z = torch.zeros(ncol, nlay, dtype=self.tdtype, device=self.device)
+                self.face_z = torch.zeros(ncol, nlev, dtype=self.tdtype, device=self.device)
+                zc = torch.as_tensor(np.asarray(center_z), dtype=self.tdtype, device=self.device)
+                zf = torch.as_tensor(np.asarray(face_z), dtype=self.tdtype, device=self.device)
+                self.center_z[:, : zc.shape[1]].copy_(zc)
+                self.face_z[:, : zf.shape[1]].copy_(zf)
+            if interpolation != "NoInterpolation":
+                r_d = params.get("R_d", params["gas_constant"] / params["molmass_dryair"] if "gas_constant" in params else 0.0)
+                cp_d = params.get("cp_d", r_d / params["kappa_d"] if "kappa_d" in params else 0.0)
+                check(L.rrtmgp_b200_set_level_interpolation(
+                    self._h, _lib.INTERPOLATIONS[interpolation], _lib.BOTTOM_EXTRAPOLATIONS[bottom_extrapolation],
+                    None if self.center_z is None else self.center_z.data_ptr(),
+                    None if self.face_z is None else self.face_z.data_ptr(), float(cp_d), float(r_d)), self._h)
         except Exception:
             L.rrtmgp_b200_destroy(self._h)
             self._h = None
@@ -420,8 +446,10 @@ def spectral_sw_flux_net(s): return _need(s, "sw_band_flux_net", "spectral flux"
 
 
 def heating_rate(s) -> torch.Tensor:
-    """`heating_rate(s)` (standalone.jl:106-124): (g / cp) dF_net/dp on the domain layers; allocates."""
+    """`heating_rate(s)` (standalone.jl:106-124): (g / cp) dF_net/dp on the domain layers, from the engine's
+    kernel; allocates and returns a fresh `(ncol, nlay)` array like the reference."""
     p = s.params
-    cp_d = p["gas_constant"] / p["molmass_dryair"] / p["kappa_d"]
-    f, pl = net_flux(s), level_pressure(s)
-    return p["grav"] * (f[:, 1:] - f[:, :-1]) / (pl[:, 1:] - pl[:, :-1]) / cp_d
+    cp_d = p.get("cp_d", p["gas_constant"] / p["molmass_dryair"] / p["kappa_d"])
+    hr = torch.empty(s.grid_params.ncol, s.grid_params.domain_nlay, dtype=s.tdtype, device=s.device)
+    check(lib().rrtmgp_b200_heating_rate(s._h, s.buffers["net_flux"].data_ptr(), hr.data_ptr(), float(cp_d), s._stream()), s._h)
+    return hr

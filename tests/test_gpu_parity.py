@@ -324,3 +324,66 @@ def test_fast_path_several_aerosol_species_per_layer(real_pack):
     _check_f32(e32, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
     np.testing.assert_allclose(e32["aod_sw_ext"], o["aod_sw_ext"], rtol=2e-5)
     _check_f64(run_engine(real_pack, st, np.float64, **kw), o)   # set_state casts the host arrays
+
+
+_SCHEMES = [("ArithmeticMean", "SameAsInterpolation"), ("GeometricMean", "SameAsInterpolation"),
+            ("UniformZ", "UseSurfaceTempAtBottom"), ("UniformP", "SameAsInterpolation"),
+            ("BestFit", "HydrostaticBottom"), ("BestFit", "SameAsInterpolation"), ("UniformZ", "HydrostaticBottom")]
+_OR_I = {"ArithmeticMean": "arithmetic_mean", "GeometricMean": "geometric_mean", "UniformZ": "uniform_z",
+         "UniformP": "uniform_p", "BestFit": "best_fit"}
+_OR_B = {"SameAsInterpolation": "same_as_interpolation", "UseSurfaceTempAtBottom": "use_surface_temp_at_bottom",
+         "HydrostaticBottom": "hydrostatic_bottom"}
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("scheme,bottom", _SCHEMES)
+def test_level_interpolation_schemes(real_pack, dtype, scheme, bottom):
+    """prepare_atmosphere! with every interpolation / bottom-extrapolation scheme (interpolation.jl:176-252,
+    grid_adaptation.jl:87-113): the engine's level pressures and temperatures vs the oracle's restatement."""
+    import oracle
+    import torch
+    ncol, nlay = 48, 64
+    st = R.synthetic.make_atmosphere(ncol, nlay, dtype=dtype)
+    p_lay, t_lay = st["layerdata"][:, :, 1].copy(), st["layerdata"][:, :, 2].copy()
+    # hydrostatic altitudes consistent with the layer values (only their relative spacing matters)
+    r_d = R.synthetic.PARAMS["gas_constant"] / R.synthetic.PARAMS["molmass_dryair"]
+    zc = np.concatenate([np.zeros((ncol, 1)), np.cumsum(r_d * 0.5 * (t_lay[:, 1:] + t_lay[:, :-1]) / 9.80665 *
+                                                         np.log(p_lay[:, :-1] / p_lay[:, 1:]), axis=1)], axis=1) + 40.0
+    zf = np.concatenate([zc[:, :1] - 40.0, 0.5 * (zc[:, 1:] + zc[:, :-1]), zc[:, -1:] + 300.0], axis=1)
+    params = R.default_parameters(**{k: R.synthetic.PARAMS[k] for k in ("grav", "molmass_dryair", "molmass_water")})
+    s = R.RRTMGPSolver(R.RRTMGPGridParams(FT=dtype, domain_nlay=nlay, ncol=ncol), R.ClearSkyRadiation(), params, real_pack,
+                       interpolation=scheme, bottom_extrapolation=bottom, center_z=zc, face_z=zf)
+    s.set_state(st)
+    s.buffers["p_lev"].fill_(-1.0); s.buffers["t_lev"].fill_(-1.0)
+    R.prepare_atmosphere(s)
+    torch.cuda.synchronize()
+    p_o, t_o = oracle.interpolate_levels(p_lay.astype(dtype), t_lay.astype(dtype), st["t_sfc"].astype(dtype), _OR_I[scheme],
+                                         _OR_B[bottom], center_z=zc, face_z=zf, params=params)
+    # prepare also clips (grid_adaptation.jl:232-258): apply the same clip to the oracle's levels
+    info = s.lut_info
+    p_o = np.maximum(p_o, dtype(info.p_ref_min)); t_o = np.clip(t_o, dtype(info.t_ref_min), dtype(info.t_ref_max))
+    rtol = 2e-5 if dtype == np.float32 else 1e-11
+    np.testing.assert_allclose(R.level_pressure(s).cpu().numpy(), p_o, rtol=rtol)
+    np.testing.assert_allclose(R.level_temperature(s).cpu().numpy(), t_o, rtol=rtol)
+    assert s.last_launch_count == 2   # interpolate_levels + clip/col_dry
+
+
+def test_level_interpolation_guards_and_heating_rate(real_pack):
+    """solver.jl:183-193 (z-based schemes need altitudes) and heating_rate (standalone.jl:106-124) from the kernel."""
+    import torch
+    gp = R.RRTMGPGridParams(FT=np.float64, domain_nlay=64, ncol=8)
+    with pytest.raises(ValueError, match="center_z"):
+        R.RRTMGPSolver(gp, R.ClearSkyRadiation(), R.default_parameters(), real_pack, interpolation="BestFit")
+    with pytest.raises(ValueError, match="center_z"):
+        R.RRTMGPSolver(gp, R.ClearSkyRadiation(), R.default_parameters(), real_pack, interpolation="UniformZ",
+                       bottom_extrapolation="HydrostaticBottom")
+    st = R.synthetic.make_atmosphere(8, 64, dtype=np.float64)
+    s = R.RRTMGPSolver(gp, R.ClearSkyRadiation(), R.default_parameters(), real_pack)
+    s.set_state(st)
+    R.update_fluxes(s)
+    hr = R.heating_rate(s).cpu().numpy()
+    p = s.params
+    cp_d = p["gas_constant"] / p["molmass_dryair"] / p["kappa_d"]
+    f, pl = R.net_flux(s).cpu().numpy(), R.level_pressure(s).cpu().numpy()
+    np.testing.assert_allclose(hr, p["grav"] * (f[:, 1:] - f[:, :-1]) / (pl[:, 1:] - pl[:, :-1]) / cp_d, rtol=1e-13)
+    assert hr.shape == (8, 64) and np.isfinite(hr).all()
