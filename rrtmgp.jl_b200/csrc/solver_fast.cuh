@@ -154,6 +154,27 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
 
     for (long long col = (long long)blockIdx.x * kFastWarps + warp; col < P.ncol; col += (long long)gridDim.x * kFastWarps) {
         Warp<FT, MODE, 2, true> W(P, wbase, lane, col, sblob, F.staged_bytes, svmr);
+        {   // pull the NEXT column's inputs (read exactly once, cold in DRAM) into L2 while this one is computed
+            const long long nc = col + (long long)gridDim.x * kFastWarps;
+            if (nc < P.ncol) {
+                auto prefetch_row = [&](const FT* base, int n) {
+                    if (base == nullptr) return;
+                    const char* b = reinterpret_cast<const char*>(base + (size_t)nc * n);
+                    const int bytes = n * (int)sizeof(FT);
+                    for (int o = lane * 128; o < bytes + 127; o += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (o < bytes ? o : bytes - 1)));
+                };
+                prefetch_row(P.io.layerdata, 4 * nlay);
+                prefetch_row(P.io.t_lev, nlev);
+                if (P.vmr_kind == 0) { prefetch_row(P.io.vmr_h2o, nlay); prefetch_row(P.io.vmr_o3, nlay); }
+                else prefetch_row(P.io.vmr, nlay * P.ngas);
+                if (HAS_CLD) {
+                    prefetch_row(P.io.cld_frac, nlay); prefetch_row(P.io.cld_path_liq, nlay); prefetch_row(P.io.cld_path_ice, nlay);
+                    prefetch_row(P.io.cld_r_eff_liq, nlay); prefetch_row(P.io.cld_r_eff_ice, nlay);
+                }
+                if (HAS_AER) { prefetch_row(P.io.aero_mass, 15 * nlay); prefetch_row(P.io.aero_size, 15 * nlay); }
+            }
+        }
         W.phase0();
         for (int i = lane; i < 3 * kAccStride; i += 32) accs[i] = FT(0);
 
