@@ -238,8 +238,18 @@ def main():
     dom_ms, dom_bytes = (ms_lw, lw_bytes) if dom == "LW" else (ms_sw, sw_bytes)
     hbm_peak, peak_src = peaks()
     achieved = ncol * dom_bytes / (dom_ms * 1e-3) / 1e9
+    # measured DRAM traffic of the same kernel: one `ncu --set full` capture (profiles/traffic.json, written by
+    # profiles/summarize.py from dram__bytes_read.sum + dram__bytes_write.sum), scaled per column
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["lw_dram_bytes" if dom == "LW" else "sw_dram_bytes"] / tj["ncol"] * ncol
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": f"solve_kernel<float,{'LW_2STREAM' if dom == 'LW' else 'SW_2STREAM'}>",
+                "traffic": traffic,
+                "kernel": f"solve_kernel_fast<{'LW_2STREAM,256' if dom == 'LW' else 'SW_2STREAM,224'},NG=1,cloud,aerosol>",
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": ncol * dom_bytes, "peak_source": peak_src,
                 "note": "fused path is FP32/LUT-gather bound by construction (SURVEY.md §8d): the HBM fraction is "
                         "<< 1; see roofline_fp32"}

@@ -72,11 +72,14 @@ struct Arena {
         fixes.push_back({(void**)&field, off});
     }
     // Small tables of one sweep (group 0 = LW, 1 = SW) are collected and laid out contiguously by finalize().
-    struct Small { std::vector<unsigned char> buf; std::vector<Fix> fixes; };
+    // `glued`: the table is addressed relative to the previous one (aerosol tables relative to `dust`), so the
+    // staged prefix must not end between them.
+    struct Small { std::vector<unsigned char> buf; std::vector<Fix> fixes; std::vector<int> cuts; };
     Small small[2];
-    template <class T, class P> void add_small(int grp, const std::vector<T>& v, P*& field) {
+    template <class T, class P> void add_small(int grp, const std::vector<T>& v, P*& field, bool glued = false) {
         Small& S = small[grp];
         size_t off = (S.buf.size() + 15) / 16 * 16;
+        if (!glued && off > 0) S.cuts.push_back((int)off);
         S.buf.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
         if (!v.empty()) std::memcpy(S.buf.data() + off, v.data(), v.size() * sizeof(T));
         S.fixes.push_back({(void**)&field, off});
@@ -85,7 +88,7 @@ struct Arena {
         Small& S = small[grp];
         S.buf.resize((S.buf.size() + 15) / 16 * 16);
         n_cut = 0;
-        for (size_t i = 1; i < S.fixes.size() && n_cut < 31; ++i) cut[n_cut++] = (int)S.fixes[i].off;   // table starts
+        for (size_t i = 0; i < S.cuts.size() && n_cut < 31; ++i) cut[n_cut++] = S.cuts[i];   // table starts
         cut[n_cut++] = (int)S.buf.size();
         size_t off = (buf.size() + 255) / 256 * 256;
         buf.resize(off + S.buf.size());
@@ -258,11 +261,11 @@ template <class FT> void build_aero(const Pack& p, const std::string& pre, AeroL
     A.add_small(grp, cast<FT>(getd(p, pre + "/rh_levels")), L.rh_levels);
     A.add_small(grp, cast<FT>(getd(p, pre + "/dust")), L.dust);
     A.add(cast<FT>(getd(p, pre + "/sea_salt")), L.sea_salt);
-    A.add_small(grp, cast<FT>(getd(p, pre + "/sulfate")), L.sulfate);
-    A.add_small(grp, cast<FT>(getd(p, pre + "/black_carbon_rh")), L.black_carbon_rh);
-    A.add_small(grp, cast<FT>(getd(p, pre + "/black_carbon")), L.black_carbon);
-    A.add_small(grp, cast<FT>(getd(p, pre + "/organic_carbon_rh")), L.organic_carbon_rh);
-    A.add_small(grp, cast<FT>(getd(p, pre + "/organic_carbon")), L.organic_carbon);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/sulfate")), L.sulfate, true);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/black_carbon_rh")), L.black_carbon_rh, true);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/black_carbon")), L.black_carbon, true);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/organic_carbon_rh")), L.organic_carbon_rh, true);
+    A.add_small(grp, cast<FT>(getd(p, pre + "/organic_carbon")), L.organic_carbon, true);
 }
 
 template <class FT> void build_all(const Pack& p, Luts<FT>& L, Arena& A) {

@@ -1,6 +1,7 @@
 // Host-side launch of the fused column kernels (solver.cuh).
 #include "solver_fast.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -62,7 +63,9 @@ static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin
     int tail = kFastWarps * off;
     F.off_vmr = tail;  tail = align_up(tail + (P.ngas > 0 ? P.ngas : 1) * (int)sizeof(float), 128);
     F.off_blob = tail;
-    const int room = max_smem_optin - 64 - tail;   // 64: static shared memory of the kernel
+    int room = max_smem_optin - 64 - tail;   // 64: static shared memory of the kernel
+    // RRTMGP_B200_STAGE_BYTES caps the staged prefix (A/B experiments: shared memory is taken from the L1 cache)
+    if (const char* e = std::getenv("RRTMGP_B200_STAGE_BYTES")) room = std::min(room, std::atoi(e));
     F.staged_bytes = 0;
     for (int i = 0; i < P.lut.n_blob_cut; ++i)
         if (P.lut.blob_cut[i] <= room) F.staged_bytes = P.lut.blob_cut[i];

@@ -297,7 +297,24 @@ class HostPipeline:
         wave = 12 * torch.cuda.get_device_properties(s.device).multi_processor_count
         if step > 2 * wave:
             step = max(wave, (step // wave) * wave)
-        self.chunks = [(a, min(step, ncol - a)) for a in range(0, ncol, step)]
+        # ramp up (1, 2, 4 waves, ...) so that the kernels start after a short first copy, and ramp down so that
+        # only a short last device-to-host copy is exposed
+        sizes, a = [], 0
+        ramp = [wave << i for i in range(8) if (wave << i) < step] if step > 2 * wave else []
+        for r in ramp:
+            if ncol - a > 2 * step:
+                sizes.append(r); a += r
+        tail = [r for r in reversed(ramp)]
+        reserved = sum(tail) if ncol - a > sum(tail) + step else 0
+        while ncol - a - reserved > 0:
+            n = min(step, ncol - a - reserved)
+            sizes.append(n); a += n
+        if reserved:
+            sizes += tail
+        self.chunks, a = [], 0
+        for n in sizes:
+            self.chunks.append((a, n)); a += n
+        assert a == ncol
         self.streams = [torch.cuda.Stream(device=s.device) for _ in range(max(1, n_streams))]
         full = lambda k: (k == "vmr" and s.config.vmr_kind == _lib.VMR_FULL)
         self.in_keys = [k for k in INPUT_KEYS + ("vmr",) if s.buffers.get(k) is not None and (k != "vmr" or full(k))]

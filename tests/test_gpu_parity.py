@@ -387,3 +387,17 @@ def test_level_interpolation_guards_and_heating_rate(real_pack):
     f, pl = R.net_flux(s).cpu().numpy(), R.level_pressure(s).cpu().numpy()
     np.testing.assert_allclose(hr, p["grav"] * (f[:, 1:] - f[:, :-1]) / (pl[:, 1:] - pl[:, :-1]) / cp_d, rtol=1e-13)
     assert hr.shape == (8, 64) and np.isfinite(hr).all()
+
+
+@pytest.mark.parametrize("cap", [0, 3000, 6000, 20000, 30000, 45000])
+def test_fast_path_partial_table_staging(real_pack, monkeypatch, cap):
+    """The fast kernels stage a prefix of the small-table block into shared memory (TMA bulk copy) and read the
+    rest from global memory; wherever the prefix ends, the results are bit-identical."""
+    st = R.synthetic.make_atmosphere(48, 64, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, seed=3)
+    monkeypatch.delenv("RRTMGP_B200_STAGE_BYTES", raising=False)
+    full = run_engine(real_pack, st, np.float32, **kw)
+    monkeypatch.setenv("RRTMGP_B200_STAGE_BYTES", str(cap))
+    part = run_engine(real_pack, st, np.float32, **kw)
+    for k in FLUX_KEYS + ("aod_sw_ext", "cld_cover_lw"):
+        np.testing.assert_array_equal(part[k], full[k], err_msg=k)
