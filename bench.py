@@ -49,14 +49,45 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every 10 ms
+    from a thread (the timed region is a fraction of a second), `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    BITS = (0x8, 0x40, 0x20, 0x4)   # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        try:
+            self.index = int(vis.split(",")[index]) if vis else index
+        except Exception:
+            self.index = index
+        self.rows, self.proc, self.t, self.stop = [], None, None, threading.Event()
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop.is_set():
+            try:
+                sm, mx = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for b in self.BITS])
+            except Exception:
+                pass
+            self.stop.wait(0.01)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.t = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -72,21 +103,22 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        if self.t:
             self.t.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[2:6]):
+                for n, v in zip(self.NAMES, r[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
