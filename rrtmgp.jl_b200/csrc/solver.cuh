@@ -205,7 +205,7 @@ struct Warp {
     const int staged;   // bytes of the block that are staged (a prefix ending at a table boundary)
     const FT* svmr;
     // per-lane registers for the layers this lane owns in phase 0/1: lane, lane+32, lane+64
-    FT own_h2o[NOWN], own_dens[NOWN], own_cdry[NOWN];
+    FT own_h2o[NOWN], own_g3[NOWN], own_dens[NOWN], own_cdry[NOWN];   // own_g3: vmr of gas 3 (ozone in VmrGM)
     AeroLayer own_aero[NOWN];
     FT own_rh_f[NOWN];
     int own_cld[NOWN];          // loc_liq | loc_ice << 8 | cloudy << 16
@@ -233,7 +233,16 @@ struct Warp {
         }
         return g;
     }
-    __device__ __forceinline__ FT vmr_of(int ig, int k) const { return get_vmr(P, ig, k, col, FUSED ? svmr : nullptr); }
+    // vmr of gas ig at layer k = lane + 32 j.  Fast kernels: the two gases that vary per layer in VmrGM (1 = h2o,
+    // 3 = o3, VolumeMixingRatios.jl:91-106) come from the registers phase 0 filled and the global means from the
+    // staged copy, so the dependent chains of phase 1 (key species -> gas -> vmr) never wait on global memory.
+    __device__ __forceinline__ FT vmr_of(int ig, int k, int j) const {
+        if (FUSED) {
+            if (ig == 1 && L.idx_h2o == 1) return own_h2o[j];
+            if (ig == 3) return own_g3[j];
+        }
+        return get_vmr(P, ig, k, col, FUSED ? svmr : nullptr);
+    }
 
     // ---------------- phase 0 (gas_optics.jl:87-115,188 and the hoisted per-layer searches) ----------------
     __device__ __forceinline__ void phase0() {
@@ -246,7 +255,7 @@ struct Warp {
 #pragma unroll
         for (int j = 0; j < NOWN; ++j) {
             const int k = lane + 32 * j;
-            own_h2o[j] = FT(0); own_dens[j] = FT(0); own_cdry[j] = FT(0); own_aero[j] = AeroLayer{0u, 0u, 1, 0, 0}; own_rh_f[j] = FT(0);
+            own_h2o[j] = FT(0); own_g3[j] = FT(0); own_dens[j] = FT(0); own_cdry[j] = FT(0); own_aero[j] = AeroLayer{0u, 0u, 1, 0, 0}; own_rh_f[j] = FT(0);
             own_cld[j] = 0; own_cld_fl[j] = own_cld_fi[j] = FT(0);
             own_pl_loc[j] = own_py_loc[j] = 0; own_pl_f[j] = own_py_f[j] = FT(0);
             if (k >= nlay) continue;
@@ -262,8 +271,9 @@ struct Warp {
             jpress = (jpress < L.n_p_ref - 1 ? jpress : L.n_p_ref - 1) + 1;
             FT fp = hdiv(ldt<FUSED>(ln_p_ref + jpress - 2) - lp, dlnp);
             int jp = jpress + tropo - 1;
-            FT h2o = vmr_of(L.idx_h2o, k);
+            FT h2o = get_vmr(P, L.idx_h2o, k, col, FUSED ? svmr : nullptr);
             own_h2o[j] = h2o;
+            if (FUSED && P.ngas >= 3) own_g3[j] = get_vmr(P, 3, k, col);
             own_cdry[j] = col_dry;
             own_dens[j] = hdiv(FT(0.01) * p_lay, t_lay);
             int aero_on = 0;
@@ -273,9 +283,12 @@ struct Warp {
                 unsigned act = 0u, bins = 0u;
                 for (int i = 0; i < 15; ++i) act |= (__ldg(am + i) > FT(0)) ? (1u << aero_pos_of_species(i)) : 0u;
                 if (act) {
-                    for (int pos = 0; pos < 10; ++pos) {   // sized species: dust 1, 8..11 then sea salt 2, 12..15
+                    unsigned sized = act & 0x3ffu;   // sized species: dust 1, 8..11 (positions 0-4) then sea salt 2, 12..15
+                    while (sized) {                  // one pass per species present, not per species slot
+                        const int pos = __ffs((int)sized) - 1;
+                        sized &= sized - 1u;
                         const int i = pos < 5 ? (pos == 0 ? 0 : 6 + pos) : (pos == 5 ? 1 : 5 + pos);
-                        if ((act >> pos) & 1u) bins |= (unsigned)merra_size_bin<FUSED>(tb(P.aero.size_bin_limits), P.aero.nbin, __ldg(as + i)) << (3 * pos);
+                        bins |= (unsigned)merra_size_bin<FUSED>(tb(P.aero.size_bin_limits), P.aero.nbin, __ldg(as + i)) << (3 * pos);
                     }
                     int loc; FT f;
                     interp1d_loc_factor<FUSED>(__ldg(ld + 4 * k + 3), tb(P.aero.rh_levels), P.aero.nrh, loc, f);
@@ -358,7 +371,7 @@ struct Warp {
                 // gas_optics.jl:129-170
                 const int* ksp = tb(L.key_species) + 2 * ((tropo - 1) + 2 * ib);
                 const int ig1 = ldt<FUSED>(ksp), ig2 = ldt<FUSED>(ksp + 1);
-                const FT vmr1 = vmr_of(ig1, k), vmr2 = vmr_of(ig2, k);
+                const FT vmr1 = vmr_of(ig1, k, j), vmr2 = vmr_of(ig2, k, j);
                 int je[2];
                 FT fe[2], smix[2];
                 // fast kernels (FUSED): record = 8 corner weights | s1, s2, major-table offsets of the two T nodes |
@@ -389,15 +402,15 @@ struct Warp {
                 const int m0 = ldt<FUSED>(bst + ib), nmin = ldt<FUSED>(bst + ib + 1) - m0;
                 for (int i = 0; i < nmin; ++i) {
                     const int4 gd = ldt<FUSED>(gdt + (m0 + i));
-                    FT vmr_i = vmr_of(gd.x, k);
+                    FT vmr_i = vmr_of(gd.x, k, j);
                     FT scaling = FT(0);
                     if (vmr_i > FT(0)) {
                         scaling = vmr_i * col_dry;
                         if (gd.z == 1) {
                             scaling *= own_dens[j];
                             if (gd.y > 0) {
-                                if (gd.w == 1) scaling *= (FT(1) - vmr_of(gd.y, k) * dry_fact);
-                                else scaling *= vmr_of(gd.y, k) * dry_fact;
+                                if (gd.w == 1) scaling *= (FT(1) - vmr_of(gd.y, k, j) * dry_fact);
+                                else scaling *= vmr_of(gd.y, k, j) * dry_fact;
                             }
                         }
                     }
