@@ -52,7 +52,7 @@ static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin
     P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(float), 16);
     P.off_recj = off;   // unused by the fast kernels (eta offsets travel in the record)
     P.off_rec = off;  off = align_up(off + nrec * maxb * P.rec_words * (int)sizeof(float), 16);
-    P.off_plk = off;  off = align_up(off + maxb * 2 * nlev * (int)sizeof(float), 16);
+    P.off_plk = off;  off = align_up(off + maxb * (nlev + 1) * (int)sizeof(float), 16);   // B(t_lev), B(t_sfc) per band
     P.off_store = off;
     const int n_hi = (nlay > kAlphaTmemLevels ? nlay - kAlphaTmemLevels : 0) + 1;   // + dummy slot
     F.off_alpha = off; off = align_up(off + n_hi * 32 * (int)sizeof(float), 128);

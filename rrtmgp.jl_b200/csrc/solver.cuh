@@ -488,11 +488,13 @@ struct Warp {
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {
                     const FT* totplnk = tb(L.tot_planck) + (size_t)L.n_t_plnk * ib;
-                    FT* pb = plk + (size_t)b * 2 * nlev;
+                    // per band: B(t_lev[0..nlay]), then B(t_lay) (no-scattering only), B(t_sfc) last;
+                    // the fast kernels keep just the nlev + 1 values they use
+                    FT* pb = plk + (size_t)b * (FUSED ? nlev + 1 : 2 * nlev);
                     pb[k + 1] = interp1d_eq_eval<FUSED>(own_pl_loc[j], own_pl_f[j], totplnk, L.n_t_plnk);
                     if (k == 0) {
                         pb[0] = interp1d_eq_eval<FUSED>(p0_loc, p0_f, totplnk, L.n_t_plnk);
-                        pb[nlev + nlay] = interp1d_eq_eval<FUSED>(psfc_loc, psfc_f, totplnk, L.n_t_plnk);
+                        pb[FUSED ? nlev : nlev + nlay] = interp1d_eq_eval<FUSED>(psfc_loc, psfc_f, totplnk, L.n_t_plnk);
                     }
                     if (NOSCAT) pb[nlev + k] = interp1d_eq_eval<FUSED>(own_py_loc[j], own_py_f[j], totplnk, L.n_t_plnk);
                 }

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             if (LW) {
                 // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom).
                 // Iteration k gathers layer k and finishes layer k-1 (its top-level source needs pfrac of layer k).
-                const FT* pbk = W.plk + bl * 2 * nlev;
+                const FT* pbk = W.plk + bl * (nlev + 1);
                 const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
                 const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : 0.f;
                 build_records(0);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 finish(G, tau, ssa, g, pf);
                 FT lev_bot = pbk[0] * pf;
                 FT albedo = 1.f - emis;
-                FT src = Num<FT>::pi() * emis * (pbk[nlev + nlay] * pf);
+                FT src = Num<FT>::pi() * emis * (pbk[nlev] * pf);
                 // finishes layer kl = k - 1 given the Planck source at its top
                 auto close_layer = [&](int kl, const LwCoef& C, FT denom, FT lev_top) {
                     const FT dB = lev_bot - lev_top;
