@@ -22,6 +22,10 @@ struct rrtmgp_b200_handle {
     unsigned long long call_counter = 0;
     int last_launches = 0;
     char cuda_err[256] = {0};
+    // work-queue counters of the persistent kernels: one per launch, taken round-robin (launches of one handle
+    // may overlap on several streams, rrtmgp_b200_update_fluxes_range)
+    unsigned int* work_counters = nullptr;
+    mutable unsigned work_seq = 0;
     // interpolate_levels! configuration (rrtmgp_b200_set_level_interpolation)
     int interpolation = RRTMGP_B200_NO_INTERPOLATION, bottom_extrapolation = RRTMGP_B200_SAME_AS_INTERPOLATION;
     const void* center_z = nullptr;
@@ -250,6 +254,7 @@ void base_params(const rrtmgp_b200_handle* h, SolveParams<FT>& P, bool sw, bool 
     P.n_mu = c.op_lw == RRTMGP_B200_ONE_SCALAR ? c.n_gauss_angles : 1;
     P.col_offset = c.col_offset + c0;
     P.seed = seed;
+    P.work_counter = h->work_counters ? h->work_counters + (h->work_seq++ & 255u) : nullptr;
     gauss_angles<FT>(P.n_mu, P.Ds, P.wts);
 }
 
@@ -422,6 +427,10 @@ int rrtmgp_b200_create(const rrtmgp_b200_config_t* cfg, rrtmgp_b200_handle_t** o
     std::memset(&h->buf, 0, sizeof(h->buf));
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+    {
+        DeviceGuard g(cfg->device);
+        if (cudaMalloc(&h->work_counters, 256 * sizeof(unsigned int)) != cudaSuccess) { delete h; return RRTMGP_B200_ERR_CUDA; }
+    }
     *out = h;
     return RRTMGP_B200_OK;
 }
@@ -430,6 +439,7 @@ void rrtmgp_b200_destroy(rrtmgp_b200_handle_t* h) {
     if (!h) return;
     DeviceGuard g(h->cfg.device);
     free_lut_store(h->luts);
+    if (h->work_counters) cudaFree(h->work_counters);
     delete h;
 }
 

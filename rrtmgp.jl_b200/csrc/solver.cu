@@ -89,6 +89,9 @@ static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t
     auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    if (P.work_counter == nullptr) return -1;
+    e = cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return (int)e;
     const int need = (P.ncol + kFastWarps - 1) / kFastWarps;
     const int sms = sm_count_of_current_device();
     const int grid = need < sms ? need : sms;   // persistent: one CTA per SM

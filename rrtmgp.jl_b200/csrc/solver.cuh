@@ -57,6 +57,7 @@ struct SolveParams {
     int use_cloud, use_aero, n_mu;
     long long col_offset;
     unsigned long long seed;
+    unsigned int* work_counter;   // fast kernels: next column to hand out (zeroed before the launch)
     FT Ds[4], wts[4];
     // per-warp shared-memory layout, in bytes from the warp's base
     int off_colj, off_colp, off_recj, off_rec, off_plk, off_store, warp_bytes;

@@ -152,10 +152,22 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     const float4* minor4 = reinterpret_cast<const float4*>(L.kminor4[0]);
     const int RW = P.rec_words;
 
-    for (long long col = (long long)blockIdx.x * kFastWarps + warp; col < P.ncol; col += (long long)gridDim.x * kFastWarps) {
+    // Columns are handed out by an atomic counter, in order, one at a time: night columns (SW) and cloud-free
+    // columns cost a fraction of the others, and a static assignment leaves the time of a launch to the unluckiest
+    // of the 1776 warps.  Every warp holds its next assignment one column ahead, so that column's inputs (read
+    // exactly once, cold in DRAM) are pulled into L2 while the current one is computed.
+    auto next_column = [&]() -> long long {
+        unsigned int v = 0;
+        if (lane == 0) v = atomicAdd(P.work_counter, 1u);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    long long col_next = next_column();
+    while (col_next < P.ncol) {
+        const long long col = col_next;
+        col_next = next_column();
         Warp<FT, MODE, 2, true> W(P, wbase, lane, col, sblob, F.staged_bytes, svmr);
-        {   // pull the NEXT column's inputs (read exactly once, cold in DRAM) into L2 while this one is computed
-            const long long nc = col + (long long)gridDim.x * kFastWarps;
+        {
+            const long long nc = col_next;
             if (nc < P.ncol) {
                 auto prefetch_row = [&](const FT* base, int n) {
                     if (base == nullptr) return;
