@@ -401,3 +401,52 @@ def test_fast_path_partial_table_staging(real_pack, monkeypatch, cap):
     part = run_engine(real_pack, st, np.float32, **kw)
     for k in FLUX_KEYS + ("aod_sw_ext", "cld_cover_lw"):
         np.testing.assert_array_equal(part[k], full[k], err_msg=k)
+
+
+def test_full_size_properties_f32(real_pack):
+    """BASELINE config 4 at its full size (ncol = 100 000, nlay = 64, Float32, all-sky with aerosols): properties that
+    need no oracle run at that size -- same seed => bit-identical fluxes; two column shards with the right
+    `col_offset` reproduce the full run bit for bit (McICA is keyed by the global column); shortwave fluxes are
+    linear in the TOA flux (a factor 2 is exact in binary floating point); night columns are exactly zero -- plus
+    the oracle on a 384-column subsample."""
+    import torch
+    ncol = 100_000
+    st = R.synthetic.make_atmosphere(ncol, 64, cld_frac=None, cos_zenith=None)
+    kw = dict(method="all_sky", aerosols=True)
+    s = make_solver_for(real_pack, st, np.float32, **kw)
+    R.update_fluxes(s, 77)
+    full = {k: s.buffers[k].clone() for k in ("lw_flux_up", "lw_flux_dn", "sw_flux_up", "sw_flux_dn", "sw_flux_dn_dir", "net_flux")}
+    R.update_fluxes(s, 77)
+    for k, v in full.items():
+        assert torch.equal(s.buffers[k], v), k
+    night = torch.as_tensor(st["cos_zenith"] <= 0).to(s.device)
+    assert int(night.sum()) > 1000
+    assert float(full["sw_flux_dn"][night].abs().max()) == 0.0 and float(full["sw_flux_up"][night].abs().max()) == 0.0
+    # linearity in the TOA flux
+    s.buffers["toa_flux"].mul_(2.0)
+    R.update_sw_fluxes(s, 77)
+    assert torch.equal(s.buffers["sw_flux_dn"], 2.0 * full["sw_flux_dn"]) and torch.equal(s.buffers["sw_flux_up"], 2.0 * full["sw_flux_up"])
+    del s
+    # two shards
+    h = ncol // 2
+    for a, b in ((0, h), (h, ncol)):
+        sub = {k: (v[a:b] if (getattr(v, "ndim", 0) >= 1 and v.shape[0] == ncol) else v) for k, v in st.items()}
+        sh = make_solver_for(real_pack, sub, np.float32, col_offset=a, **kw)
+        R.update_fluxes(sh, 77)
+        for k, v in full.items():
+            assert torch.equal(sh.buffers[k], v[a:b]), (k, a)
+        del sh
+    # oracle on a subsample (columns keep their global index through col_offset)
+    a = 61_440
+    sub = {k: (v[a:a + 384] if (getattr(v, "ndim", 0) >= 1 and v.shape[0] == ncol) else v) for k, v in st.items()}
+    o = run_oracle(real_pack, sub, np.float64, seed=77, col_offset=a, **kw)
+    o32 = run_oracle(real_pack, sub, np.float32, seed=77, col_offset=a, **kw)
+    e = {"lw_up": full["lw_flux_up"], "lw_dn": full["lw_flux_dn"], "sw_up": full["sw_flux_up"], "sw_dn": full["sw_flux_dn"]}
+    for k, tol in (("lw_up", F32_LW), ("lw_dn", F32_LW), ("sw_up", F32_SW_CLOUDY), ("sw_dn", F32_SW_CLOUDY)):
+        err = maxdiff(e[k][a:a + 384].cpu().numpy(), o[k])
+        assert err <= max(tol, 1.5 * maxdiff(o32[k], o[k])), (k, err)
+
+
+def make_solver_for(pack, state, dtype, **kw):
+    from helpers import make_solver
+    return make_solver(pack, state, dtype, **kw)
