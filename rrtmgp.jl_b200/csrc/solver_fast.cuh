@@ -1,8 +1,8 @@
 // Blackwell-native fast path of the two-stream kernels: Float32, nlay <= 64, real-table shape
-// (n_eta = 9, n_T = 14, 16-g-point bands, n_gpt a template constant).
+// (n_eta = 9, n_T = 14, 16-g-point bands, n_gpt and the number of minor-slot groups template constants).
 //
-//  * PERSISTENT: one CTA of 12 warps per SM; every warp walks its own sequence of columns
-//    (warp = column, lane = g-point, as in solver.cuh).
+//  * PERSISTENT: one CTA of 12 warps per SM; warp = column, lane = g-point (as in solver.cuh).  Columns come
+//    from an atomic work queue, the next one is known one column ahead and its inputs are prefetched into L2.
 //  * TENSOR MEMORY as the level store.  The adding method needs, for every level, three values
 //    per (column, g-point) from the first sweep when the second sweep passes the same level:
 //    768 B per lane, 24.6 KB per warp.  In shared memory that caps residency at 4-6 warps per
@@ -10,13 +10,21 @@
 //    otherwise idle here (no MMA on this path) and tcgen05.ld/st give every thread a private
 //    column array in its own TMEM lane -- exactly the access pattern of this store.  The CTA
 //    allocates all 512 columns; the three warps that share a lane quadrant get 170 columns
-//    each: (A, B) of 64 levels + the albedo of the lowest 42 levels; the other 22 albedos sit
+//    each: (A, B) of 64 levels + the albedo of the lowest 41 levels; the other 23 albedos sit
 //    in shared memory.
+//  * SMALL TABLES STAGED BY TMA: key species, reference vmr, minor-absorber lists, Planck table, cloud and
+//    aerosol tables of the sweep are one block of the arena (GasLut::blob), copied to shared memory once per
+//    CTA with cp.async.bulk + mbarrier; phase 1 never waits on global memory for them.
+//  * BAND RECORDS: everything a (layer, band) contributes to its 16 g-points -- 8 trilinear corner weights,
+//    column amounts, table offsets, slot scalings, cloud/aerosol increment products -- is computed once per
+//    (layer, band) by phase 1 (lane = layer) and read by the cells with five 128-bit loads.
 //  * COMPILE-TIME TABLE STRIDES and PACKED TABLES: a cell gathers its 8 {kmajor, Planck fraction}
 //    corners with 64-bit loads and its minor absorbers (+ Rayleigh) four slots at a time with
-//    128-bit loads: 12 loads from four address registers instead of 28-32 scalar loads.
-//  * G-POINT REDUCTION through a 4 KB shared staging tile read transposed (lane = level),
-//    ~2 instructions per (level, quantity) instead of a 10-instruction shuffle tree.
+//    128-bit loads: 12 loads instead of 28-32 scalar loads.
+//  * LOADS FIRST, ONE BASIC BLOCK PER ITERATION: an iteration issues the gathers of layer k, then does the
+//    source-independent two-stream coefficients of layer k-1, then interpolates layer k and closes layer k-1;
+//    record rebuilds and g-point reductions sit between tiles of <= 16 iterations, nothing branches inside.
+//  * G-POINT REDUCTION through a shared staging tile read transposed (lane = level) with 128-bit loads.
 //  * SW adding marched from the TOP (reflectance/source of everything ABOVE a level),
 //    algebraically identical to shortwave_2stream.jl:300-392, so the direct beam, the layer
 //    coefficients and the first recurrence share one sweep; see DESIGN.md.
