@@ -146,11 +146,17 @@ def run_reference(args, rank, world):
         return
     import rrtmgp_b200 as R
     from oracle import Oracle
-    ncol_s = min(args.ncol, args.cpu_sample)
     pack = R.synthetic.make_lut_pack(seed=7)
-    st = make_state(ncol_s, args.nlay, 0)
     o = Oracle(pack, np.float32)
     cores = host_threads()   # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
+    # bounded sample: a short calibration run sizes it so that warmup + steps take about 90 s of CPU time
+    cal = make_state(2048, args.nlay, 0)
+    t0 = time.perf_counter()
+    o.update_fluxes(cal, seed=1, params=PARAMS, nthreads=cores)
+    rate = 2048 / max(time.perf_counter() - t0, 1e-6)
+    budget_cols = int(90.0 * rate / max(1, args.steps + args.warmup))
+    ncol_s = max(2048, min(args.ncol, args.cpu_sample, budget_cols))
+    st = make_state(ncol_s, args.nlay, 0)
     for _ in range(args.warmup):
         o.update_fluxes(st, seed=1, params=PARAMS, nthreads=cores)
     t0 = time.perf_counter()
