@@ -1112,6 +1112,13 @@ template <class FT> void apply_metric_scaling(FluxOut<FT> f, const FT* sc, size_
     }
 }
 
+// Fluxes.jl:443-455 (RTESolver.jl:141,246): the (nlev, ncol) scaling broadcasts across the band dimension
+template <class FT> void apply_metric_scaling_bands(FT* band_up, FT* band_dn, int n_bnd, const FT* sc, size_t n) {
+    if (!sc || !band_up) return;
+    for (int b = 0; b < n_bnd; ++b)
+        for (size_t k = 0; k < n; ++k) { band_up[(size_t)b * n + k] *= sc[k]; band_dn[(size_t)b * n + k] *= sc[k]; }
+}
+
 // update_fluxes.jl:252-281 (clip! grid_adaptation.jl:232-258; col_dry gas_optics.jl:16-41)
 template <class FT> void prepare_atmosphere(const Lookups<FT>& L, Ctx<FT>& c, const OracleOpts& o) {
     const OracleState* st = c.st;
@@ -1177,6 +1184,7 @@ template <class FT> int update_fluxes(const OracleHandle<FT>* h, const OracleSta
         solve_lw(h->L, c, *o, allsky, f, allsky ? (FT*)out->cld_cover_lw : nullptr, (FT*)out->lw_band_up,
                  (FT*)out->lw_band_dn, out->mask_lw);
         apply_metric_scaling(f, sc, n);
+        apply_metric_scaling_bands((FT*)out->lw_band_up, (FT*)out->lw_band_dn, h->L.lw.n_bnd, sc, n);
     }
     if (o->do_sw) {
         if (o->method == 2) {
@@ -1188,6 +1196,7 @@ template <class FT> int update_fluxes(const OracleHandle<FT>* h, const OracleSta
         solve_sw(h->L, c, *o, allsky, f, allsky ? (FT*)out->cld_cover_sw : nullptr, (FT*)out->aod_sw_ext,
                  (FT*)out->aod_sw_sca, (FT*)out->sw_band_up, (FT*)out->sw_band_dn, out->mask_sw);
         apply_metric_scaling(f, sc, n);
+        apply_metric_scaling_bands((FT*)out->sw_band_up, (FT*)out->sw_band_dn, h->L.sw.n_bnd, sc, n);
     }
     if (o->do_lw && o->do_sw && out->net) {  // Fluxes.jl:423-435
         FT* net = (FT*)out->net;

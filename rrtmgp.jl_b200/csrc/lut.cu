@@ -134,6 +134,9 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
     for (int g0 = 0; g0 < n_gpt; g0 += 32)
         maxb = std::max(maxb, g2b[std::min(g0 + 31, n_gpt - 1)] - g2b[g0] + 1);
     L.maxb = maxb;
+    L.bands_of_16 = (n_gpt == 16 * L.n_bnd) ? 1 : 0;
+    for (int g = 0; g < n_gpt && L.bands_of_16; ++g)
+        if (g2b[g] != g / 16) L.bands_of_16 = 0;
     A.add_small(grp, g2b, L.gpt2bnd);
 
     std::vector<FT> p_ref = cast<FT>(getd(p, pre + "/p_ref"));

@@ -17,6 +17,7 @@ struct GasLut {
     int nminor_max;   // max minor absorbers of any (band, lower/upper)
     int maxb;         // max number of bands that touch one 32-g-point block
     int is_sw;
+    int bands_of_16;  // every band is 16 consecutive g-points (the real g256 / g224 tables)
     FT p_ref_tropo, p_ref_min, t_ref_min, t_ref_max, solar_src_tot;
     const FT* t_ref;        // [n_t]
     const FT* ln_p_ref;     // [n_p_ref]

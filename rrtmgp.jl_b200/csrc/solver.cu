@@ -58,6 +58,8 @@ static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin
     F.off_alpha = off; off = align_up(off + n_hi * 32 * (int)sizeof(float), 128);
     F.off_stage = off; off = align_up(off + 16 * kStageStride * (int)sizeof(float), 16);
     F.off_acc = off;   off = align_up(off + 3 * kAccStride * (int)sizeof(float), 128);
+    F.off_bacc = -1;
+    if (P.io.band_up != nullptr) { F.off_bacc = off; off = align_up(off + 4 * kAccStride * (int)sizeof(float), 128); }
     P.warp_bytes = off;
     // CTA-shared tail: the staged small-table block and the global-mean vmr array
     int tail = kFastWarps * off;
@@ -81,12 +83,12 @@ static int sm_count_of_current_device() {
     return cached[dev] > 0 ? cached[dev] : 148;
 }
 
-template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER>
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL>
 static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
     FastSmem F;
     const size_t smem = (size_t)plan_smem_fast(P, F, max_smem_optin);
     if ((int)smem > max_smem_optin) return -1;   // does not fit: generic kernel
-    auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER>;
+    auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER, SPECTRAL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     if (P.work_counter == nullptr) return -1;
@@ -99,13 +101,19 @@ static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t
     return (int)cudaGetLastError();
 }
 
+template <int MODE, int NGPT, int NG, bool SPECTRAL>
+static int launch_fast_sp(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
+    const bool c = P.use_cloud != 0, a = P.use_aero != 0;
+    if (c && a) return launch_fast_t<MODE, NGPT, NG, true, true, SPECTRAL>(P, max_smem_optin, s);
+    if (c) return launch_fast_t<MODE, NGPT, NG, true, false, SPECTRAL>(P, max_smem_optin, s);
+    if (a) return launch_fast_t<MODE, NGPT, NG, false, true, SPECTRAL>(P, max_smem_optin, s);
+    return launch_fast_t<MODE, NGPT, NG, false, false, SPECTRAL>(P, max_smem_optin, s);
+}
+
 template <int MODE, int NGPT, int NG>
 static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
-    const bool c = P.use_cloud != 0, a = P.use_aero != 0;
-    if (c && a) return launch_fast_t<MODE, NGPT, NG, true, true>(P, max_smem_optin, s);
-    if (c) return launch_fast_t<MODE, NGPT, NG, true, false>(P, max_smem_optin, s);
-    if (a) return launch_fast_t<MODE, NGPT, NG, false, true>(P, max_smem_optin, s);
-    return launch_fast_t<MODE, NGPT, NG, false, false>(P, max_smem_optin, s);
+    return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true>(P, max_smem_optin, s)
+                                   : launch_fast_sp<MODE, NGPT, NG, false>(P, max_smem_optin, s);
 }
 
 // groups of four minor-absorber slots per band: 1 (synthetic pack) or 2 (up to 8 / 7 + Rayleigh, real tables)
@@ -125,7 +133,8 @@ static bool fast_enabled() {
 template <typename FT> static int try_fast(int, SolveParams<FT>&, int, cudaStream_t) { return -1; }
 template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
     const GasLut<float>& L = P.lut;
-    if (!fast_enabled() || P.nlay > 64 || P.nlay < 2 || mode == MODE_LW_NOSCAT || P.io.band_up != nullptr) return -1;
+    if (!fast_enabled() || P.nlay > 64 || P.nlay < 2 || mode == MODE_LW_NOSCAT) return -1;
+    if (P.io.band_up != nullptr && !L.bands_of_16) return -1;   // per-band sums = half-row sums only for aligned 16-g-point bands
     if (L.n_eta != 9 || L.n_t != 14 || L.maxb != 2 || L.n_minor_groups > 2 || (L.n_gpt % 32) != 0) return -1;
     if (mode == MODE_LW_2STREAM && L.n_gpt == 256 && L.kmaj_pf != nullptr) return launch_fast_flags<MODE_LW_2STREAM, 256>(P, max_smem_optin, s);
     if (mode == MODE_SW_2STREAM && L.n_gpt == 224) return launch_fast_flags<MODE_SW_2STREAM, 224>(P, max_smem_optin, s);

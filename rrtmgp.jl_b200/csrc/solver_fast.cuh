@@ -73,6 +73,7 @@ struct FastSmem {
     int off_alpha, off_stage, off_acc;   // byte offsets from the warp's base, extending SolveParams' layout
     int off_blob, off_vmr;               // CTA-shared: staged small-table block, global-mean vmr array (from the smem base)
     int staged_bytes;                    // staged prefix of GasLut::blob
+    int off_bacc;                        // per warp: per-band accumulators [2 bands][up, dn][kAccStride] (spectral fluxes), or -1
 };
 
 // ---- TMA bulk copy global -> shared with mbarrier completion (the small-table block, once per CTA) ----
@@ -111,7 +112,7 @@ template <bool LW, int NG> struct FastCell {
     float4 x;                // increment products (aerosol only or cloud + aerosol), minor-table offset
 };
 
-template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER>
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL>
 __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const SolveParams<float> P, const FastSmem F) {
     using FT = float;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,6 +155,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     FT* alpha_hi = reinterpret_cast<FT*>(wbase + F.off_alpha);   // [nlay - 41 + 1][32]
     FT* stage = reinterpret_cast<FT*>(wbase + F.off_stage);      // [16][kStageStride]
     FT* accs = reinterpret_cast<FT*>(wbase + F.off_acc);         // [3][kAccStride]
+    // per-band (spectral) fluxes, Fluxes.jl:170-215: lanes 0-15 / 16-31 of a block are its two 16-g-point bands, so
+    // the half-row sums of the staging tile are the band sums
+    constexpr bool spectral = SPECTRAL;   // a template parameter: the broadband-only kernels carry none of this
+    FT* bacc = reinterpret_cast<FT*>(wbase + (F.off_bacc >= 0 ? F.off_bacc : 0));   // [2][2][kAccStride]
+    const int hb = lane >> 4;                                    // this lane's half = band within the block
     const GasLut<FT>& L = P.lut;
     const int nlay = P.nlay, nlev = nlay + 1;
     const FT* major = LW ? L.kmaj_pf : L.kmajor;
@@ -197,6 +203,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
         }
         W.phase0();
         for (int i = lane; i < 3 * kAccStride; i += 32) accs[i] = FT(0);
+        if (spectral)
+            for (int i = lane; i < 4 * kAccStride; i += 32) bacc[i] = FT(0);
 
         const uint64_t col_key = mcica_col_key(P.seed, (uint64_t)(P.col_offset + col));
         int cld_start = 0, cld_finish = 0;
@@ -229,7 +237,23 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 W.phase1(e, sc, half);
                 aod_e += e; aod_s += sc;
             };
+            // writes (or, at night, zeroes) the per-band fluxes of this block's two bands and clears the accumulators
+            auto flush_bands = [&](bool zero) {
+                __syncwarp();
+                for (int b = 0; b < W.nb; ++b) {
+                    const size_t ob = ((size_t)(W.b_first + b) * P.ncol_total + col) * nlev;
+                    for (int lev = lane; lev < nlev; lev += 32) {
+                        FT bu = zero ? 0.f : bacc[(b * 2 + UP) * kAccStride + lev];
+                        FT bd = zero ? 0.f : bacc[(b * 2 + DN) * kAccStride + lev];
+                        bacc[(b * 2 + UP) * kAccStride + lev] = 0.f; bacc[(b * 2 + DN) * kAccStride + lev] = 0.f;
+                        if (P.io.metric_scaling != nullptr) { const FT sc = __ldg(P.io.metric_scaling + (size_t)col * nlev + lev); bu *= sc; bd *= sc; }
+                        P.io.band_up[ob + lev] = bu; P.io.band_dn[ob + lev] = bd; P.io.band_net[ob + lev] = bu - bd;
+                    }
+                }
+                __syncwarp();
+            };
             if (!day) {   // night: AOD and masks only (shortwave_2stream.jl:66-102)
+                if (spectral) flush_bands(true);
                 if (aod_here) {
                     build_records(0);
                     if (nlay > 32) build_records(1);
@@ -338,13 +362,22 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             auto ld_alpha_s = [&](int k) -> FT { return alpha_hi[(k < kAlphaTmemLevels ? 0 : k - kAlphaTmemLevels + 1) * 32 + lane]; };
             // g-point sum of the staging tile, read transposed: lane r and lane r + 16 each add half of row r
             // (128-bit reads), one shuffle joins the halves; every lane ends with the total of row (lane & 15)
-            auto row_sum = [&]() -> FT {
+            auto row_sum = [&](FT& half) -> FT {
                 const float4* row = reinterpret_cast<const float4*>(stage + (lane & 15) * kStageStride + (lane >> 4) * 16);
                 const float4 a = row[0], b = row[1], c = row[2], d = row[3];
-                FT s = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
-                return s + __shfl_xor_sync(0xffffffffu, s, 16);
+                half = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+                return half + __shfl_xor_sync(0xffffffffu, half, 16);
             };
-
+            // sum over the warp of a per-lane value; `half` = the sum over this lane's 16-lane half (its band)
+            auto warp_sum2 = [&](FT v, FT& half) -> FT {
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                half = v;
+                return v + __shfl_xor_sync(0xffffffffu, v, 16);
+            };
+            // band accumulators: quantity q (UP / DN) of level lev gets this half's sum; callers pass lanes whose
+            // (lane & 15) names a valid row, and one lane per half for warp_sum2 results
+            auto band_add = [&](int q, int lev, FT half) { bacc[(hb * 2 + q) * kAccStride + lev] += half; };
             FastCell<LW, NG> G;
             if (LW) {
                 // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom).
@@ -388,8 +421,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     }
                     __syncwarp();
                     {                                                     // sum_g src of levels ks-1 .. ke-2
-                        const FT sum = row_sum();
+                        FT hs;
+                        const FT sum = row_sum(hs);
                         if (lane < 16 && lane < ke - ks) accs[UP * kAccStride + ks - 1 + lane] += sum;
+                        if (spectral && (lane & 15) < ke - ks) band_add(UP, ks - 1 + (lane & 15), hs);
                     }
                     __syncwarp();
                 }
@@ -397,13 +432,17 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
                     const FT denom = hdiv(1.f, 1.f - C.Rdif * albedo);
                     const FT s_top = close_layer(nlay - 1, C, denom, pbk[nlay] * pf);
-                    const FT ssum = warp_sum(s_top);
+                    FT hs;
+                    const FT ssum = warp_sum2(s_top, hs);
                     if (lane == 0) accs[UP * kAccStride + nlay - 1] += ssum;
+                    if (spectral && (lane & 15) == 0) band_add(UP, nlay - 1, hs);
                 }
                 FT dn = inc;
                 {
-                    FT u = warp_sum(dn * albedo + src), d = warp_sum(dn);
+                    FT hu, hd;
+                    FT u = warp_sum2(dn * albedo + src, hu), d = warp_sum2(dn, hd);
                     if (lane == 0) { accs[UP * kAccStride + nlay] += u; accs[DN * kAccStride + nlay] += d; }
+                    if (spectral && (lane & 15) == 0) { band_add(UP, nlay, hu); band_add(DN, nlay, hd); }
                 }
                 tmem_wait_st();
                 FT A, B, al;
@@ -426,8 +465,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     __syncwarp();
                     {
                         const int lev = kc + ((lane & 15) >> 1);
-                        const FT sum = row_sum();
+                        FT hs;
+                        const FT sum = row_sum(hs);
                         if (lane < 16 && lev <= ktop) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += sum;
+                        if (spectral && lev <= ktop) band_add((lane & 1) ? UP : DN, lev, hs);
                     }
                     __syncwarp();
                 }
@@ -442,8 +483,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 FT tau_cum = 0.f, dir = dir_top;
                 FT beta = 0.f, d = 0.f;   // reflectance / downward diffuse source of everything above the level
                 {
-                    FT sum = warp_sum(dir_top);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
+                    FT hs;
+                    FT sum = warp_sum2(dir_top, hs);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
                     if (lane == 0) { accs[DIR * kAccStride + nlay] += sum; accs[DN * kAccStride + nlay] += sum; }
+                    if (spectral && (lane & 15) == 0) band_add(DN, nlay, hs);
                 }
                 build_records(nlay > 32 ? 1 : 0);
                 FT tau, ssa, g, pf;
@@ -479,19 +522,24 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     __syncwarp();
                     {
                         const int kk = jc + 1 + ((lane & 15) >> 1);
-                        const FT sum = row_sum();
-                        const bool ok = lane < 16 && kk <= jtop + 1;
+                        FT hs;
+                        const FT sum = row_sum(hs);
+                        const bool okb = kk <= jtop + 1, ok = lane < 16 && okb;
                         // d_{kk+1} (even lanes) and dir_kk (odd lanes) both feed F_dn: two ordered steps,
                         // never two lanes read-modify-writing one accumulator in the same instruction
                         if (ok && (lane & 1)) { accs[DN * kAccStride + kk] += sum; accs[DIR * kAccStride + kk] += sum; }
+                        if (spectral && okb && (lane & 1)) band_add(DN, kk, hs);
                         __syncwarp();
                         if (ok && !(lane & 1)) accs[DN * kAccStride + kk + 1] += sum;
+                        if (spectral && okb && !(lane & 1)) band_add(DN, kk + 1, hs);
                     }
                     __syncwarp();
                 }
                 {   // lowest layer
-                    const FT d1 = warp_sum(march(0)), dir0 = warp_sum(dir);
+                    FT hd1, hdir0;
+                    const FT d1 = warp_sum2(march(0), hd1), dir0 = warp_sum2(dir, hdir0);
                     if (lane == 0) { accs[DN * kAccStride + 1] += d1; accs[DN * kAccStride] += dir0; accs[DIR * kAccStride] += dir0; }
+                    if (spectral && (lane & 15) == 0) { band_add(DN, 1, hd1); band_add(DN, 0, hdir0); }
                 }
                 if (aod_here) {
                     aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
@@ -500,8 +548,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 // surface: F_up(0) = alb_dif F_dn_dif(0) + alb_dir dir(0) ; F_dn_dif(0) = d_0 + beta_0 F_up(0)
                 FT up = hdiv(alb_dif * d + alb_dir * dir, 1.f - alb_dif * beta);
                 {
-                    FT u = warp_sum(up), dd = warp_sum(d + beta * up);
+                    FT hu, hdd;
+                    FT u = warp_sum2(up, hu), dd = warp_sum2(d + beta * up, hdd);
                     if (lane == 0) { accs[UP * kAccStride] += u; accs[DN * kAccStride] += dd; }
+                    if (spectral && (lane & 15) == 0) { band_add(UP, 0, hu); band_add(DN, 0, hdd); }
                 }
                 tmem_wait_st();
                 FT A, B, be;
@@ -524,12 +574,15 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     __syncwarp();
                     {
                         const int kk = kc + ((lane & 15) >> 1);
-                        const FT sum = row_sum();
+                        FT hs;
+                        const FT sum = row_sum(hs);
                         if (lane < 16 && kk < kend) accs[((lane & 1) ? DN : UP) * kAccStride + kk + 1] += sum;
+                        if (spectral && kk < kend) band_add((lane & 1) ? DN : UP, kk + 1, hs);
                     }
                     __syncwarp();
                 }
             }
+            if (spectral) flush_bands(false);
         }
         __syncwarp();
 

@@ -201,6 +201,32 @@ def test_spectral_fluxes_sum_to_broadband(real_pack):
     np.testing.assert_allclose(e["sw_band_dn"].sum(0), e["sw_dn"], rtol=1e-10, atol=1e-9)
 
 
+@pytest.mark.parametrize("scaled", [False, True])
+def test_spectral_fluxes_fast_path_f32(real_pack, scaled):
+    """Per-band fluxes from the Float32 fast kernels (the half-row sums of the staging tile are the band sums):
+    bands vs the Float64 oracle within the Float32 thresholds, bands sum to the broadband flux, night columns are
+    zero, metric scaling applies to the bands too, and the broadband results are bit-identical to a
+    non-spectral run."""
+    ncol = 96
+    st = R.synthetic.make_atmosphere(ncol, 64, cld_frac=None, cos_zenith=None)
+    if scaled:
+        st["metric_scaling"] = np.linspace(1.0, 1.3, ncol * 65, dtype=np.float32).reshape(ncol, 65)
+    kw = dict(method="all_sky", aerosols=True, seed=8)
+    e = run_engine(real_pack, st, np.float32, spectral=True, **kw)
+    o = run_oracle(real_pack, st, np.float64, spectral=True, **kw)
+    o32 = run_oracle(real_pack, st, np.float32, spectral=True, **kw)
+    for k, tol in (("lw_band_up", F32_LW), ("lw_band_dn", F32_LW), ("sw_band_up", F32_SW_CLOUDY), ("sw_band_dn", F32_SW_CLOUDY)):
+        assert maxdiff(e[k], o[k]) <= max(tol, 1.5 * maxdiff(o32[k], o[k])), (k, maxdiff(e[k], o[k]))
+    np.testing.assert_allclose(e["lw_band_up"].sum(0), e["lw_up"], rtol=2e-6)
+    np.testing.assert_allclose(e["sw_band_dn"].sum(0), e["sw_dn"], rtol=2e-6, atol=1e-4)
+    np.testing.assert_array_equal(e["solver"].buffers["sw_band_flux_net"].cpu().numpy(), e["sw_band_up"] - e["sw_band_dn"])
+    night = st["cos_zenith"] <= 0
+    assert night.any() and np.abs(e["sw_band_dn"][:, night]).max() == 0.0 and np.abs(e["sw_band_up"][:, night]).max() == 0.0
+    plain = run_engine(real_pack, st, np.float32, **kw)
+    for k in FLUX_KEYS:
+        np.testing.assert_array_equal(e[k], plain[k], err_msg=k)
+
+
 def test_irregular_band_layout_small_tables():
     """Reduced-resolution style tables: bands with unequal g-point counts, a g-point count that is not
     a multiple of 32, and more than two bands per 32-g-point block."""
