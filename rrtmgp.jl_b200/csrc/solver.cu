@@ -41,7 +41,10 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
 }
 
 // Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
+template <int WARPS>
 static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin) {
+    using Geom = FastGeom<WARPS>;
+    constexpr int kAlphaTmemLevels = Geom::alpha_tmem_levels, kAccStride = Geom::acc_stride, kFastWarps = WARPS;
     const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
     const int nrec = nlay < 32 ? nlay : 32;                    // band records cover half a column at a time
     // record = 8 corner weights, {s1, s2, two major-table offsets}, 4 slot scalings per group,
@@ -83,12 +86,13 @@ static int sm_count_of_current_device() {
     return cached[dev] > 0 ? cached[dev] : 148;
 }
 
-template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL>
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL, int WARPS>
 static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
     FastSmem F;
-    const size_t smem = (size_t)plan_smem_fast(P, F, max_smem_optin);
+    constexpr int kFastWarps = WARPS;
+    const size_t smem = (size_t)plan_smem_fast<WARPS>(P, F, max_smem_optin);
     if ((int)smem > max_smem_optin) return -1;   // does not fit: generic kernel
-    auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER, SPECTRAL>;
+    auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER, SPECTRAL, WARPS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     if (P.work_counter == nullptr) return -1;
@@ -101,19 +105,22 @@ static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t
     return (int)cudaGetLastError();
 }
 
-template <int MODE, int NGPT, int NG, bool SPECTRAL>
+template <int MODE, int NGPT, int NG, bool SPECTRAL, int WARPS>
 static int launch_fast_sp(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
     const bool c = P.use_cloud != 0, a = P.use_aero != 0;
-    if (c && a) return launch_fast_t<MODE, NGPT, NG, true, true, SPECTRAL>(P, max_smem_optin, s);
-    if (c) return launch_fast_t<MODE, NGPT, NG, true, false, SPECTRAL>(P, max_smem_optin, s);
-    if (a) return launch_fast_t<MODE, NGPT, NG, false, true, SPECTRAL>(P, max_smem_optin, s);
-    return launch_fast_t<MODE, NGPT, NG, false, false, SPECTRAL>(P, max_smem_optin, s);
+    if (c && a) return launch_fast_t<MODE, NGPT, NG, true, true, SPECTRAL, WARPS>(P, max_smem_optin, s);
+    if (c) return launch_fast_t<MODE, NGPT, NG, true, false, SPECTRAL, WARPS>(P, max_smem_optin, s);
+    if (a) return launch_fast_t<MODE, NGPT, NG, false, true, SPECTRAL, WARPS>(P, max_smem_optin, s);
+    return launch_fast_t<MODE, NGPT, NG, false, false, SPECTRAL, WARPS>(P, max_smem_optin, s);
 }
 
+// nlay <= 64: 12 warps per SM; taller columns (<= 95 layers): the 8-warp geometry, broadband fluxes only
 template <int MODE, int NGPT, int NG>
 static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
-    return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true>(P, max_smem_optin, s)
-                                   : launch_fast_sp<MODE, NGPT, NG, false>(P, max_smem_optin, s);
+    if (P.nlay > FastGeom<12>::max_lay)
+        return P.io.band_up != nullptr ? -1 : launch_fast_sp<MODE, NGPT, NG, false, 8>(P, max_smem_optin, s);
+    return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true, 12>(P, max_smem_optin, s)
+                                   : launch_fast_sp<MODE, NGPT, NG, false, 12>(P, max_smem_optin, s);
 }
 
 // groups of four minor-absorber slots per band: 1 (synthetic pack) or 2 (up to 8 / 7 + Rayleigh, real tables)
@@ -133,7 +140,7 @@ static bool fast_enabled() {
 template <typename FT> static int try_fast(int, SolveParams<FT>&, int, cudaStream_t) { return -1; }
 template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
     const GasLut<float>& L = P.lut;
-    if (!fast_enabled() || P.nlay > 64 || P.nlay < 2 || mode == MODE_LW_NOSCAT) return -1;
+    if (!fast_enabled() || P.nlay >= FastGeom<8>::max_lay || P.nlay < 2 || mode == MODE_LW_NOSCAT) return -1;
     if (P.io.band_up != nullptr && !L.bands_of_16) return -1;   // per-band sums = half-row sums only for aligned 16-g-point bands
     if (L.n_eta != 9 || L.n_t != 14 || L.maxb != 2 || L.n_minor_groups > 2 || (L.n_gpt % 32) != 0) return -1;
     if (mode == MODE_LW_2STREAM && L.n_gpt == 256 && L.kmaj_pf != nullptr) return launch_fast_flags<MODE_LW_2STREAM, 256>(P, max_smem_optin, s);

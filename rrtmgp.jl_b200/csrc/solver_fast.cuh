@@ -1,7 +1,8 @@
-// Blackwell-native fast path of the two-stream kernels: Float32, nlay <= 64, real-table shape
+// Blackwell-native fast path of the two-stream kernels: Float32, nlay <= 95, real-table shape
 // (n_eta = 9, n_T = 14, 16-g-point bands, n_gpt and the number of minor-slot groups template constants).
 //
-//  * PERSISTENT: one CTA of 12 warps per SM; warp = column, lane = g-point (as in solver.cuh).  Columns come
+//  * PERSISTENT: one CTA of 12 warps per SM (8 for columns taller than 64 layers, FastGeom); warp = column,
+//    lane = g-point (as in solver.cuh).  Columns come
 //    from an atomic work queue, the next one is known one column ahead and its inputs are prefetched into L2.
 //  * TENSOR MEMORY as the level store.  The adding method needs, for every level, three values
 //    per (column, g-point) from the first sweep when the second sweep passes the same level:
@@ -60,14 +61,19 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& a) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-#ifndef RB_FAST_WARPS
-#define RB_FAST_WARPS 12
-#endif
-constexpr int kFastWarps = RB_FAST_WARPS;   // warps per CTA = per SM (a multiple of 4; 12 in production, 8 for A/B experiments)
-constexpr int kFastColsPerWarp = 512 / (kFastWarps / 4);   // TMEM columns per warp: the warps of a lane quadrant share its 512 columns
-constexpr int kAlphaTmemLevels = kFastColsPerWarp - 128 - 1;   // 41 albedos in TMEM (+1 dummy column), the rest in shared memory
+// Geometry of the persistent CTA: 12 warps (3 per TMEM lane quadrant, 170 columns each) for nlay <= 64, or 8 warps
+// (2 per quadrant, 256 columns each) for nlay <= 96.  Per warp: (A, B) of every level, then as many albedos as fit
+// (+ one dummy column); the other albedos go to shared memory.
+template <int WARPS> struct FastGeom {
+    static_assert(WARPS == 12 || WARPS == 8, "3 or 2 warps per TMEM lane quadrant");
+    static constexpr int warps = WARPS;
+    static constexpr int max_lay = WARPS == 12 ? 64 : 96;
+    static constexpr int cols_per_warp = 512 / (WARPS / 4);
+    static constexpr int alpha_tmem_levels = cols_per_warp - 2 * max_lay - 1;   // 41 / 63
+    static constexpr int acc_stride = max_lay + 4;    // per-quantity stride of the shared broadband accumulators
+    static constexpr int n_own = max_lay / 32;        // layers per lane in phases 0 / 1; record parts per column
+};
 constexpr int kStageStride = 36;      // staging-tile row stride: 16-byte aligned rows, conflict-free 128-bit row reads
-constexpr int kAccStride = 68;        // per-quantity stride of the shared broadband accumulators
 
 struct FastSmem {
     int off_alpha, off_stage, off_acc;   // byte offsets from the warp's base, extending SolveParams' layout
@@ -112,9 +118,12 @@ template <bool LW, int NG> struct FastCell {
     float4 x;                // increment products (aerosol only or cloud + aerosol), minor-table offset
 };
 
-template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL>
-__global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const SolveParams<float> P, const FastSmem F) {
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolveParams<float> P, const FastSmem F) {
     using FT = float;
+    using Geom = FastGeom<WARPS>;
+    constexpr int kFastWarps = Geom::warps, kFastColsPerWarp = Geom::cols_per_warp, kAlphaTmemLevels = Geom::alpha_tmem_levels;
+    constexpr int kAccStride = Geom::acc_stride, NOWN = Geom::n_own, kMaxLay = Geom::max_lay;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(8) uint64_t blob_bar;
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     mbar_wait(&blob_bar, 0);
     // lane field (bits 31:16) = 32 * (warp % 4); column = 170 * (warp / 4)
     const uint32_t tA = tmem_base_smem + ((uint32_t)(warp & 3) << 21) + (uint32_t)((warp >> 2) * kFastColsPerWarp);
-    const uint32_t tAl = tA + 128u;
+    const uint32_t tAl = tA + 2u * kMaxLay;
 
     unsigned char* wbase = smem_raw + (size_t)warp * P.warp_bytes;
     FT* alpha_hi = reinterpret_cast<FT*>(wbase + F.off_alpha);   // [nlay - 41 + 1][32]
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
     while (col_next < P.ncol) {
         const long long col = col_next;
         col_next = next_column();
-        Warp<FT, MODE, 2, true> W(P, wbase, lane, col, sblob, F.staged_bytes, svmr);
+        Warp<FT, MODE, NOWN, true> W(P, wbase, lane, col, sblob, F.staged_bytes, svmr);
         {
             const long long nc = col_next;
             if (nc < P.ncol) {
@@ -255,8 +264,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             if (!day) {   // night: AOD and masks only (shortwave_2stream.jl:66-102)
                 if (spectral) flush_bands(true);
                 if (aod_here) {
-                    build_records(0);
-                    if (nlay > 32) build_records(1);
+                    for (int part = 0; part * 32 < nlay; ++part) build_records(part);
                     aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
                     if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
                 }
@@ -267,13 +275,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
             const FT* rec_lane = W.rec + bl * RW;          // this lane's band within a record row pair
             const FT* major_lane = major + (LW ? 2 : 1) * gpt;   // tables offset by this lane's g-point
             const float4* minor_lane = minor4 + gpt;
-            const unsigned mask0 = W.mask[0], mask1 = W.mask[1];
+            const unsigned mask0 = W.mask[0], mask1 = W.mask[1], mask2 = W.mask[NOWN - 1];   // (mask2 used when NOWN = 3)
 
             // ---- issue every load of cell (layer k, this g-point): compile-time strides, 64/128-bit gathers ----
             auto gather = [&](int k, FastCell<LW, NG>& G) {
                 const FT* r = rec_lane + (k & 31) * 2 * RW;
                 bool cb = false;
-                if (HAS_CLD) cb = ((k < 32 ? mask0 : mask1) >> (k & 31)) & 1u;
+                if (HAS_CLD) cb = ((k < 32 ? mask0 : ((NOWN > 2 && k >= 64) ? mask2 : mask1)) >> (k & 31)) & 1u;
                 G.s = *reinterpret_cast<const float4*>(r + 8);
                 G.x = *reinterpret_cast<const float4*>(r + 12 + 4 * NG + (cb ? 4 : 0));
                 G.v0 = *reinterpret_cast<const float4*>(r);
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                 };
                 for (int k0 = 0; k0 < nlay; k0 += 16) {                 // tiles of <= 16 interfaces k
                     const int ks = k0 > 0 ? k0 : 1, ke = k0 + 16 < nlay ? k0 + 16 : nlay;
-                    if (k0 == 32) build_records(1);
+                    if (k0 > 0 && (k0 & 31) == 0) build_records(k0 >> 5);   // next 32 layers' records
                     for (int k = ks; k < ke; ++k) {                       // single basic block
                         gather(k, G);
                         const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     if (lane == 0) { accs[DIR * kAccStride + nlay] += sum; accs[DN * kAccStride + nlay] += sum; }
                     if (spectral && (lane & 15) == 0) band_add(DN, nlay, hs);
                 }
-                build_records(nlay > 32 ? 1 : 0);
+                build_records((nlay - 1) >> 5);
                 FT tau, ssa, g, pf;
                 gather(nlay - 1, G);
                 finish(G, tau, ssa, g, pf);
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
                     return d_above;
                 };
                 for (int jc = (nlay - 2) & ~7; jc >= 0; jc -= 8) {     // 8 layers x (d_{k+1}, dir_k) per tile, k = j + 1
-                    if (jc == 24 && nlay > 32) build_records(0);
+                    if ((jc & 31) == 24 && jc + 8 < nlay) build_records(jc >> 5);   // next 32 layers down
                     const int jtop = jc + 7 < nlay - 2 ? jc + 7 : nlay - 2;
                     for (int j = jtop; j >= jc; --j) {                  // single basic block
                         gather(j, G);
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) solve_kernel_fast(const So
 
         // ---------------- epilogue: (nlev, ncol) presentation, net, scaling, diagnostics ----------------
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < (kMaxLay + 32) / 32; ++i) {
             const int lev = lane + 32 * i;
             if (lev < nlev) {
                 const size_t o = (size_t)col * nlev + lev;

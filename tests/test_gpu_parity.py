@@ -313,10 +313,11 @@ def test_column_range_and_host_pipeline_match_full_call(real_pack):
         R.update_fluxes_range(s2, 31, 650, 100)
 
 
-@pytest.mark.parametrize("nlay", [8, 17, 32, 33, 40, 63])
+@pytest.mark.parametrize("nlay", [8, 17, 32, 33, 40, 63, 65, 72, 95])
 def test_fast_path_runtime_nlay_f32(real_pack, nlay):
-    """The Float32 fast kernels (TMEM level store, tiled level loops, half-column band records) at layer counts
-    that hit every tile / record-half boundary: Float32 engine vs Float64 oracle, all-sky with aerosols."""
+    """The Float32 fast kernels (TMEM level store, tiled level loops, 32-layer band-record parts) at layer counts
+    that hit every tile / record-part boundary, in both CTA geometries (12 warps up to 64 layers, 8 warps up to 95):
+    Float32 engine vs Float64 oracle, all-sky with aerosols."""
     st = R.synthetic.make_atmosphere(96, nlay, cld_frac=None)
     kw = dict(method="all_sky", aerosols=True, seed=99)
     e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
