@@ -15,6 +15,7 @@
 module RRTMGPB200Ext
 
 using CUDA
+import Adapt
 import RRTMGP
 import RRTMGP: RRTMGPSolver
 
@@ -137,6 +138,53 @@ function heating_rate(e::B200Engine, s::RRTMGPSolver)
                 devptr(s.net_flux_buffer), devptr(hr), RRTMGP.Parameters.cp_d(s.params), CUDA.stream().handle))
     return hr
 end
+
+# name -> Array pairs of a loaded `LookupBundle` (src/api/lookup_bundle.jl:29-46), i.e. exactly what
+# `lookup_tables(grid_params, method)` built from the rrtmgp-data artifact, in the entry names
+# `rrtmgp_b200_load_luts` reads.  `rrtmgp.jl_b200/tables.py` produces the same entries from the NetCDF files
+# without Julia.  Cloud / aerosol sections are written only when the bundle holds them.
+function lut_arrays(b)
+    h = x -> Array(Adapt.adapt(Array, x))
+    out = Pair{String, Array}[]
+    gas(pre, l, sw) = begin
+        push!(out, "$pre/key_species" => h(l.key_species), "$pre/kmajor" => h(l.kmajor),
+              "$pre/bnd_lims_gpt" => h(l.band_data.bnd_lims_gpt), "$pre/major_gpt2bnd" => h(l.band_data.major_gpt2bnd),
+              "$pre/bnd_lims_wn" => h(l.band_data.bnd_lims_wn),
+              "$pre/ln_p_ref" => h(l.ref_points.ln_p_ref),          # the struct keeps only log(p_ref)
+              "$pre/t_ref" => h(l.ref_points.t_ref), "$pre/vmr_ref" => h(l.ref_points.vmr_ref),
+              "$pre/idx_h2o" => Int32[l.idx_h2o],
+              "$pre/params" => Float64[l.p_ref_tropo, l.p_ref_min, l.t_ref_min, l.t_ref_max, sw ? l.solar_src_tot : 0])
+        for (tag, m) in (("lower", l.minor_lower), ("upper", l.minor_upper))
+            push!(out, "$pre/minor_$tag/bnd_st" => h(m.bnd_st), "$pre/minor_$tag/gpt_st" => h(m.gpt_st),
+                  "$pre/minor_$tag/gasdata" => h(m.gasdata), "$pre/minor_$tag/kminor" => h(m.kminor))
+        end
+        if sw
+            push!(out, "$pre/rayl_lower" => h(l.rayl_lower), "$pre/rayl_upper" => h(l.rayl_upper),
+                  "$pre/solar_src_scaled" => h(l.solar_src_scaled))
+        else
+            push!(out, "$pre/planck_fraction" => h(l.planck.planck_fraction), "$pre/t_planck" => h(l.planck.t_planck),
+                  "$pre/tot_planck" => h(l.planck.tot_planck))
+        end
+    end
+    gas("lw", b.lookup_lw, false)
+    gas("sw", b.lookup_sw, true)
+    for (tag, c) in (("cld_lw", b.lookup_lw_cld), ("cld_sw", b.lookup_sw_cld))
+        isnothing(c) && continue
+        push!(out, "$tag/dims" => Int32.(h(c.dims)), "$tag/bounds" => h(c.bounds), "$tag/liqdata" => h(c.liqdata),
+              "$tag/icedata" => h(c.icedata), "$tag/bnd_lims_wn" => h(c.bnd_lims_wn))
+    end
+    for (tag, a) in (("aero_lw", b.lookup_lw_aero), ("aero_sw", b.lookup_sw_aero))
+        isnothing(a) && continue
+        push!(out, "$tag/dims" => Int32.(h(a.dims)), "$tag/size_bin_limits" => h(a.size_bin_limits),
+              "$tag/rh_levels" => h(a.rh_levels), "$tag/dust" => h(a.dust), "$tag/sea_salt" => h(a.sea_salt),
+              "$tag/sulfate" => h(a.sulfate), "$tag/black_carbon_rh" => h(a.black_carbon_rh),
+              "$tag/black_carbon" => h(a.black_carbon), "$tag/organic_carbon_rh" => h(a.organic_carbon_rh),
+              "$tag/organic_carbon" => h(a.organic_carbon), "$tag/bnd_lims_wn" => h(a.bnd_lims_wn),
+              "$tag/iband_550nm" => Int32[a.iband_550nm])
+    end
+    return out
+end
+lut_pack(s::RRTMGPSolver) = write_lut_pack(lut_arrays(s.lookups))
 
 # LUT pack writer: name -> Array in the post-load layouts of src/optics/LookUpTables.jl
 # (format: rrtmgp.jl_b200/lutpack.py; names: rrtmgp.jl_b200/synthetic.py `make_lut_arrays`).

@@ -234,10 +234,14 @@ template <class FT> void load_gas(const Pack& p, const std::string& pre, bool sw
         }
     l.major_gpt2bnd = geti(p, pre + "/major_gpt2bnd");
     l.kmajor = getf<FT>(p, pre + "/kmajor");
-    std::vector<FT> p_ref = getf<FT>(p, pre + "/p_ref");
-    l.n_p_ref = (int)p_ref.size();
-    l.ln_p_ref.resize(p_ref.size());
-    for (size_t i = 0; i < p_ref.size(); ++i) l.ln_p_ref[i] = std::log(p_ref[i]);  // lookup_constructors.jl:336
+    if (p.count(pre + "/ln_p_ref")) {   // a dump of the loaded struct keeps only the logarithm (LookUpTables.jl:70-74)
+        l.ln_p_ref = getf<FT>(p, pre + "/ln_p_ref");
+    } else {
+        std::vector<FT> p_ref = getf<FT>(p, pre + "/p_ref");
+        l.ln_p_ref.resize(p_ref.size());
+        for (size_t i = 0; i < p_ref.size(); ++i) l.ln_p_ref[i] = std::log(p_ref[i]);  // lookup_constructors.jl:336
+    }
+    l.n_p_ref = (int)l.ln_p_ref.size();
     l.t_ref = getf<FT>(p, pre + "/t_ref");
     l.vmr_ref = getf<FT>(p, pre + "/vmr_ref");
     load_minor(p, pre + "/minor_lower", l.minor_lower);
@@ -1254,14 +1258,14 @@ void* oracle_create(const unsigned char* pack, size_t nbytes, int is_f64) {
         if (is_f64) {
             auto* h = new OracleHandle<double>();
             load_gas(p, "lw", false, h->L.lw); load_gas(p, "sw", true, h->L.sw);
-            load_cld(p, "cld_lw", h->L.cld_lw); load_cld(p, "cld_sw", h->L.cld_sw);
-            load_aero(p, "aero_lw", h->L.aero_lw); load_aero(p, "aero_sw", h->L.aero_sw);
+            if (p.count("cld_lw/dims")) { load_cld(p, "cld_lw", h->L.cld_lw); load_cld(p, "cld_sw", h->L.cld_sw); }
+            if (p.count("aero_lw/dims")) { load_aero(p, "aero_lw", h->L.aero_lw); load_aero(p, "aero_sw", h->L.aero_sw); }
             return h;
         }
         auto* h = new OracleHandle<float>();
         load_gas(p, "lw", false, h->L.lw); load_gas(p, "sw", true, h->L.sw);
-        load_cld(p, "cld_lw", h->L.cld_lw); load_cld(p, "cld_sw", h->L.cld_sw);
-        load_aero(p, "aero_lw", h->L.aero_lw); load_aero(p, "aero_sw", h->L.aero_sw);
+        if (p.count("cld_lw/dims")) { load_cld(p, "cld_lw", h->L.cld_lw); load_cld(p, "cld_sw", h->L.cld_sw); }
+        if (p.count("aero_lw/dims")) { load_aero(p, "aero_lw", h->L.aero_lw); load_aero(p, "aero_sw", h->L.aero_sw); }
         return h;
     } catch (...) { return nullptr; }
 }

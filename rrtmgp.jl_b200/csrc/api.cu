@@ -451,6 +451,14 @@ int rrtmgp_b200_load_luts(rrtmgp_b200_handle_t* h, const void* pack, size_t nbyt
     if (st == RRTMGP_B200_ERR_CUDA && err) std::snprintf(h->cuda_err, sizeof(h->cuda_err), "%s", err);
     if (st != RRTMGP_B200_OK) return st;
     if (h->luts.ngas > h->cfg.ngas) return RRTMGP_B200_ERR_INVALID_ARG;   // vmr gas axis shorter than the tables'
+    // a pack without the cloud / aerosol sections only serves the methods that never read them
+    // (lookup_tables, ext/RRTMGPNCDatasetsExt.jl:26-133, loads exactly what the method needs)
+    const bool has_cld = h->cfg.dtype == 1 ? h->luts.f64.cld_lw.liqdata != nullptr : h->luts.f32.cld_lw.liqdata != nullptr;
+    const bool has_aer = h->cfg.dtype == 1 ? h->luts.f64.aero_lw.dust != nullptr : h->luts.f32.aero_lw.dust != nullptr;
+    if ((h->cfg.method >= RRTMGP_B200_ALL_SKY && !has_cld) || (h->cfg.aerosol_radiation && !has_aer)) {
+        free_lut_store(h->luts);
+        return RRTMGP_B200_ERR_BAD_LUT_PACK;
+    }
     if (h->luts.f32.lw.n_eta > 16 || h->luts.f64.lw.n_eta > 16) return RRTMGP_B200_ERR_UNSUPPORTED;
     return RRTMGP_B200_OK;
 }

@@ -139,10 +139,17 @@ void build_gas(const Pack& p, const std::string& pre, bool sw, GasLut<FT>& L, Ar
         if (g2b[g] != g / 16) L.bands_of_16 = 0;
     A.add_small(grp, g2b, L.gpt2bnd);
 
-    std::vector<FT> p_ref = cast<FT>(getd(p, pre + "/p_ref"));
-    L.n_p_ref = (int)p_ref.size();
-    std::vector<FT> lnp(p_ref.size());
-    for (size_t i = 0; i < p_ref.size(); ++i) lnp[i] = std::log(p_ref[i]);  // lookup_constructors.jl:336
+    // `p_ref` as the file has it, or -- from a host that dumps the loaded struct, which only keeps the logarithm
+    // (ReferencePoints, LookUpTables.jl:70-74) -- `ln_p_ref` as is
+    std::vector<FT> lnp;
+    if (p.count(pre + "/ln_p_ref")) {
+        lnp = cast<FT>(getd(p, pre + "/ln_p_ref"));
+    } else {
+        std::vector<FT> p_ref = cast<FT>(getd(p, pre + "/p_ref"));
+        lnp.resize(p_ref.size());
+        for (size_t i = 0; i < p_ref.size(); ++i) lnp[i] = std::log(p_ref[i]);  // lookup_constructors.jl:336
+    }
+    L.n_p_ref = (int)lnp.size();
     A.add_small(grp, lnp, L.ln_p_ref);
     A.add_small(grp, cast<FT>(getd(p, pre + "/t_ref")), L.t_ref);
     A.add_small(grp, cast<FT>(getd(p, pre + "/vmr_ref")), L.vmr_ref);
@@ -275,10 +282,17 @@ template <class FT> void build_all(const Pack& p, Luts<FT>& L, Arena& A) {
     build_gas(p, "lw", false, L.lw, A);
     build_gas(p, "sw", true, L.sw, A);
     // block order = staging priority: gas tables, aerosol tables (sea salt, the one big one, stays outside), cloud
-    build_aero(p, "aero_lw", L.aero_lw, A, 0);
-    build_aero(p, "aero_sw", L.aero_sw, A, 1);
-    build_cld(p, "cld_lw", L.cld_lw, A, 0);
-    build_cld(p, "cld_sw", L.cld_sw, A, 1);
+    // cloud / aerosol sections are optional (a clear-sky host loads the two gas files only,
+    // ext/RRTMGPNCDatasetsExt.jl:26-92); rrtmgp_b200_load_luts rejects a pack that lacks what the method needs
+    L.aero_lw = AeroLut<FT>{}; L.aero_sw = AeroLut<FT>{}; L.cld_lw = CldLut<FT>{}; L.cld_sw = CldLut<FT>{};
+    if (p.count("aero_lw/dims") && p.count("aero_sw/dims")) {
+        build_aero(p, "aero_lw", L.aero_lw, A, 0);
+        build_aero(p, "aero_sw", L.aero_sw, A, 1);
+    }
+    if (p.count("cld_lw/dims") && p.count("cld_sw/dims")) {
+        build_cld(p, "cld_lw", L.cld_lw, A, 0);
+        build_cld(p, "cld_sw", L.cld_sw, A, 1);
+    }
     A.finalize_small(0, L.lw.blob, L.lw.blob_bytes, L.lw.n_blob_cut, L.lw.blob_cut);
     A.finalize_small(1, L.sw.blob, L.sw.blob_bytes, L.sw.n_blob_cut, L.sw.blob_cut);
 }

@@ -477,3 +477,54 @@ def test_full_size_properties_f32(real_pack):
 def make_solver_for(pack, state, dtype, **kw):
     from helpers import make_solver
     return make_solver(pack, state, dtype, **kw)
+
+
+# ---- real-table ingestion: NetCDF files in the artifact's raw layout -> tables.py -> engine ----
+@pytest.fixture(scope="module")
+def ingested(tmp_path_factory):
+    from artifact_files import write_artifact
+    arrays = R.synthetic.make_lut_arrays(seed=7)                       # the real table dimensions
+    d = str(tmp_path_factory.mktemp("rrtmgp_data"))
+    write_artifact(d, arrays, R.synthetic.GAS_NAMES)
+    return d
+
+
+def test_engine_on_ingested_tables_f32_fast_path(ingested, real_pack):
+    """Tables read from NetCDF (raw rrtmgp-data layout) drive the Float32 fast kernels to the same fluxes as the
+    directly built pack; the Float64 oracle on the ingested pack is the parity reference."""
+    pack, _ = R.tables.lut_pack_from_artifact(ingested)
+    st = R.synthetic.make_atmosphere(256, 64, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, seed=3)
+    e, d = run_engine(pack, st, np.float32, **kw), run_engine(real_pack, st, np.float32, **kw)
+    for k in FLUX_KEYS:     # only the solar source differs, by rounding of quiet + facular + sunspot
+        assert maxdiff(e[k], d[k]) <= 1e-3, k
+    np.testing.assert_array_equal(e["lw_up"], d["lw_up"])
+    o = run_oracle(pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(pack, st, np.float32, **kw))
+
+
+def test_gas_only_pack_serves_clear_sky_and_is_refused_for_all_sky(ingested):
+    """`lookup_tables` loads what the method needs (ext/RRTMGPNCDatasetsExt.jl:26-133): a pack without cloud /
+    aerosol sections runs clear-sky and `rrtmgp_b200_load_luts` refuses it for methods that would read them."""
+    pack, _ = R.tables.lut_pack_from_artifact(ingested, clouds=False, aerosols=False)
+    st = R.synthetic.make_atmosphere(64, 64, dtype=np.float64, clouds=False, aerosols=False)
+    kw = dict(method="clear_sky", aerosols=False)
+    _check_f64(run_engine(pack, st, np.float64, **kw), run_oracle(pack, st, np.float64, **kw))
+    st32 = R.synthetic.make_atmosphere(64, 64, clouds=False, aerosols=False)
+    _check_f32(run_engine(pack, st32, np.float32, **kw), run_oracle(pack, st32, np.float64, **kw), F32_LW, F32_SW_CLEAR,
+               run_oracle(pack, st32, np.float32, **kw))
+    with pytest.raises(R.RRTMGPB200Error, match="status"):
+        make_solver_for(pack, R.synthetic.make_atmosphere(8, 64), np.float32, method="all_sky", aerosols=False)
+    with pytest.raises(R.RRTMGPB200Error, match="status"):
+        make_solver_for(pack, R.synthetic.make_atmosphere(8, 64, clouds=False), np.float32, method="clear_sky", aerosols=True)
+
+
+def test_ln_p_ref_entry_is_accepted(real_pack):
+    """A host that dumps the loaded struct has `ln_p_ref`, not `p_ref` (ReferencePoints, LookUpTables.jl:70-74)."""
+    arrays = dict(R.lutpack.unpack_luts(real_pack))
+    for pre in ("lw", "sw"):
+        arrays[f"{pre}/ln_p_ref"] = np.log(arrays.pop(f"{pre}/p_ref"))
+    st = R.synthetic.make_atmosphere(32, 64, dtype=np.float64, clouds=False, aerosols=False)
+    kw = dict(method="clear_sky", aerosols=False)
+    a, b = run_engine(R.lutpack.pack_luts(arrays), st, np.float64, **kw), run_engine(real_pack, st, np.float64, **kw)
+    _check_f64(a, b, rel=1e-12)
