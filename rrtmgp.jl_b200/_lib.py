@@ -63,7 +63,7 @@ EXPORTS = ("rrtmgp_b200_create", "rrtmgp_b200_destroy", "rrtmgp_b200_load_luts",
 
 def build_ext(force: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a (nvcc cross-compiles without a GPU)."""
-    args = ["make", "-C", _CSRC] + (["-B"] if force else [])
+    args = ["make", "-j", str(max(1, min(8, os.cpu_count() or 1))), "-C", _CSRC] + (["-B"] if force else [])
     subprocess.check_call(args, stdout=subprocess.DEVNULL)
     return LIB_PATH
 

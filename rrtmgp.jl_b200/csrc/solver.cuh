@@ -62,6 +62,7 @@ struct SolveParams {
     // per-warp shared-memory layout, in bytes from the warp's base
     int off_colj, off_colp, off_recj, off_rec, off_plk, off_store, warp_bytes;
     int rec_words;   // FT words per band record
+    int rec_row;     // FT words per layer row of band records (>= maxb * rec_words; padded in the fast kernels)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -226,6 +227,9 @@ struct Warp {
           recj(reinterpret_cast<int*>(wbase + P_.off_recj)), rec(reinterpret_cast<FT*>(wbase + P_.off_rec)),
           plk(reinterpret_cast<FT*>(wbase + P_.off_plk)), RW(P_.rec_words), maxb(P_.lut.maxb) {}
 
+    // words per band of the Planck buffer
+    __device__ __forceinline__ int plk_stride() const { return FUSED ? (NOSCAT ? 2 * nlev : nlev + 1) : 2 * nlev; }
+
     // A small table: the global array, or (fast kernels) its copy inside the staged part of the block
     template <class T> __device__ __forceinline__ const T* tb(const T* g) const {
         if (FUSED) {
@@ -368,7 +372,7 @@ struct Warp {
             const FT dry_fact = hdiv(FT(1), FT(1) + vmr_h2o);
             for (int b = 0; b < nb; ++b) {
                 const int ib = b_first + b;
-                FT* r = rec + ((size_t)kr * maxb + b) * RW;
+                FT* r = rec + (size_t)kr * P.rec_row + b * RW;
                 // gas_optics.jl:129-170
                 const int* ksp = tb(L.key_species) + 2 * ((tropo - 1) + 2 * ib);
                 const int ig1 = ldt<FUSED>(ksp), ig2 = ldt<FUSED>(ksp + 1);
@@ -491,13 +495,14 @@ struct Warp {
                     const FT* totplnk = tb(L.tot_planck) + (size_t)L.n_t_plnk * ib;
                     // per band: B(t_lev[0..nlay]), then B(t_lay) (no-scattering only), B(t_sfc) last;
                     // the fast kernels keep just the nlev + 1 values they use
-                    FT* pb = plk + (size_t)b * (FUSED ? nlev + 1 : 2 * nlev);
+                    // (fast no-scattering kernel: B(t_lev) [nlev], B(t_sfc), then B(t_lay) [nlay])
+                    FT* pb = plk + (size_t)b * plk_stride();
                     pb[k + 1] = interp1d_eq_eval<FUSED>(own_pl_loc[j], own_pl_f[j], totplnk, L.n_t_plnk);
                     if (k == 0) {
                         pb[0] = interp1d_eq_eval<FUSED>(p0_loc, p0_f, totplnk, L.n_t_plnk);
                         pb[FUSED ? nlev : nlev + nlay] = interp1d_eq_eval<FUSED>(psfc_loc, psfc_f, totplnk, L.n_t_plnk);
                     }
-                    if (NOSCAT) pb[nlev + k] = interp1d_eq_eval<FUSED>(own_py_loc[j], own_py_f[j], totplnk, L.n_t_plnk);
+                    if (NOSCAT) pb[(FUSED ? nlev + 1 : nlev) + k] = interp1d_eq_eval<FUSED>(own_py_loc[j], own_py_f[j], totplnk, L.n_t_plnk);
                 }
             }
         }
@@ -551,7 +556,7 @@ struct Warp {
         const FT ft = colp[4 * k + 0], fp = colp[4 * k + 1], col_dry = colp[4 * k + 2];
         const int rj = recj[k * maxb + bl];
         const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf, nmin = rj >> 8;
-        const FT* r = rec + (k * maxb + bl) * RW;
+        const FT* r = rec + k * P.rec_row + bl * RW;
         const FT fe1 = r[0], fe2 = r[1];
         const FT omfe1 = FT(1) - fe1, omfe2 = FT(1) - fe2, omft = FT(1) - ft, omfp = FT(1) - fp;
         // element offsets (all tables < 2^31 elements)

@@ -118,7 +118,8 @@ template <bool LW, int NG> struct FastCell {
     float4 x;                // increment products (aerosol only or cloud + aerosol), minor-table offset
 };
 
-template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL, int WARPS>
+// NMU (no-scattering LW only): 1 = one Gauss angle, 4 = up to four, P.n_mu of them active
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL, int WARPS, int NMU = 1>
 __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolveParams<float> P, const FastSmem F) {
     using FT = float;
     using Geom = FastGeom<WARPS>;
@@ -128,6 +129,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(8) uint64_t blob_bar;
     constexpr bool LW = MODE == MODE_LW_2STREAM;
+    constexpr bool NOSCAT = MODE == MODE_LW_NOSCAT;
+    constexpr bool LWG = LW || NOSCAT;      // longwave gas optics: {kmajor, Planck fraction} pairs, no Rayleigh, always "day"
     constexpr bool INCR = HAS_CLD || HAS_AER;
     constexpr int NETA = 9, NT = 14;
     constexpr int KE = NGPT, KT = NETA * KE, KP = NT * KT;           // major-table strides (LW: in float2): eta, T, p
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
     const int hb = lane >> 4;                                    // this lane's half = band within the block
     const GasLut<FT>& L = P.lut;
     const int nlay = P.nlay, nlev = nlay + 1;
-    const FT* major = LW ? L.kmaj_pf : L.kmajor;
+    const FT* major = LWG ? L.kmaj_pf : L.kmajor;
     const float4* minor4 = reinterpret_cast<const float4*>(L.kminor4[0]);
     const int RW = P.rec_words;
 
@@ -226,9 +229,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
             hi = __reduce_max_sync(0xffffffffu, hi);
             if (hi > 0) { cld_start = (int)lo; cld_finish = (int)hi; }
         }
-        const FT mu0 = LW ? FT(1) : __ldg(P.io.cos_zenith + col);
-        const bool day = LW || mu0 > FT(0);
-        const FT toa = LW ? FT(0) : __ldg(P.io.toa_flux + col);
+        const FT mu0 = LWG ? FT(1) : __ldg(P.io.cos_zenith + col);
+        const bool day = LWG || mu0 > FT(0);
+        const FT toa = LWG ? FT(0) : __ldg(P.io.toa_flux + col);
         int n_cloudy = 0;
         __syncwarp();
 
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
             if (HAS_CLD) n_cloudy += W.mcica(col_key, cld_start, cld_finish);
             // band records are built half a column (32 layers) at a time, just before the sweep needs them
             FT aod_e = 0.f, aod_s = 0.f;
-            const bool aod_here = !LW && HAS_AER && P.io.aod_ext != nullptr && P.aero.iband_550nm >= W.b_first + 1 &&
+            const bool aod_here = !LWG && HAS_AER && P.io.aod_ext != nullptr && P.aero.iband_550nm >= W.b_first + 1 &&
                                   P.aero.iband_550nm <= W.b_first + W.nb;
             auto build_records = [&](int half) {
                 __syncwarp();
@@ -273,13 +276,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
 
             const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
             const FT* rec_lane = W.rec + bl * RW;          // this lane's band within a record row pair
-            const FT* major_lane = major + (LW ? 2 : 1) * gpt;   // tables offset by this lane's g-point
+            const FT* major_lane = major + (LWG ? 2 : 1) * gpt;   // tables offset by this lane's g-point
             const float4* minor_lane = minor4 + gpt;
             const unsigned mask0 = W.mask[0], mask1 = W.mask[1], mask2 = W.mask[NOWN - 1];   // (mask2 used when NOWN = 3)
 
             // ---- issue every load of cell (layer k, this g-point): compile-time strides, 64/128-bit gathers ----
-            auto gather = [&](int k, FastCell<LW, NG>& G) {
-                const FT* r = rec_lane + (k & 31) * 2 * RW;
+            auto gather = [&](int k, FastCell<LWG, NG>& G) {
+                const FT* r = rec_lane + (k & 31) * P.rec_row;
                 bool cb = false;
                 if (HAS_CLD) cb = ((k < 32 ? mask0 : ((NOWN > 2 && k >= 64) ? mask2 : mask1)) >> (k & 31)) & 1u;
                 G.s = *reinterpret_cast<const float4*>(r + 8);
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 for (int gi = 0; gi < NG; ++gi) G.sc[gi] = *reinterpret_cast<const float4*>(r + 12 + 4 * gi);
                 const int ia = __float_as_int(G.s.z), ib = __float_as_int(G.s.w);   // (jp-1, jt, je1), (jp-1, jt+1, je2)
                 const int ma = __float_as_int(G.x.w), mb = ma + (ib - ia);          // (jt, je1), (jt+1, je2): MT == KT
-                if (LW) {   // {kmajor, planck_fraction} pairs
+                if (LWG) {   // {kmajor, planck_fraction} pairs
                     const float2* pa = reinterpret_cast<const float2*>(major_lane) + ia;
                     const float2* pb = reinterpret_cast<const float2*>(major_lane) + ib;
                     G.c2[0] = __ldg(pa); G.c2[1] = __ldg(pa + KE); G.c2[2] = __ldg(pa + KP); G.c2[3] = __ldg(pa + KP + KE);
@@ -308,9 +311,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 }
             };
             // ---- gas + cloud + aerosol optics of the gathered cell (gas_optics.jl:176-320, optics_utils.jl:85-181) ----
-            auto finish = [&](const FastCell<LW, NG>& G, FT& tau, FT& ssa, FT& g, FT& pfrac) {
+            auto finish = [&](const FastCell<LWG, NG>& G, FT& tau, FT& ssa, FT& g, FT& pfrac) {
                 const float4 v0 = G.v0, v1 = G.v1;
-                if (LW) {
+                if (LWG) {
                     const float2* c = G.c2;
                     tau = G.s.x * (v0.x * c[0].x + v0.y * c[1].x + v0.z * c[2].x + v0.w * c[3].x) +
                           G.s.y * (v1.x * c[4].x + v1.y * c[5].x + v1.z * c[6].x + v1.w * c[7].x);
@@ -334,14 +337,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     const FT v1 = w11 * m11.y + w21 * m21.y + w12 * m12.y + w22 * m22.y;
                     const FT v2 = w11 * m11.z + w21 * m21.z + w12 * m12.z + w22 * m22.z;
                     const FT v3 = w11 * m11.w + w21 * m21.w + w12 * m12.w + w22 * m22.w;
-                    if (!LW && gi == 0) {
+                    if (!LWG && gi == 0) {
                         tau_ray = v0 * sc.x;
                         tau += v1 * sc.y + v2 * sc.z + v3 * sc.w;
                     } else {
                         tau += v0 * sc.x + v1 * sc.y + v2 * sc.z + v3 * sc.w;
                     }
                 }
-                if (LW) {
+                if (LWG) {
                     tau = rmax(tau, 0.f);
                     ssa = 0.f; g = 0.f;
                 } else {
@@ -351,7 +354,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 }
                 // one fused, unconditional increment (optics_utils.jl:189-202 is additive in tau, tau ssa, tau ssa g;
                 // the record holds zeros where neither cloud nor aerosol is present)
-                if (INCR) {
+                if (INCR && NOSCAT) {
+                    tau += G.x.x;   // absorption optical depth of cloud + aerosol (cloud_optics.jl:1-50, aerosol_optics.jl:18-61)
+                } else if (INCR) {
                     const FT tn = tau + G.x.x;
                     const FT w = LW ? G.x.y : tau * ssa + G.x.y;       // LW gas: ssa = 0
                     const FT h = G.x.z;                                  // gas: g = 0 in both
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
             // band accumulators: quantity q (UP / DN) of level lev gets this half's sum; callers pass lanes whose
             // (lane & 15) names a valid row, and one lane per half for warp_sum2 results
             auto band_add = [&](int q, int lev, FT half) { bacc[(hb * 2 + q) * kAccStride + lev] += half; };
-            FastCell<LW, NG> G;
+            FastCell<LWG, NG> G;
             if (LW) {
                 // compute_optical_props.jl:157-195 sources + longwave_2stream.jl:243-334 adding (from the bottom).
                 // Iteration k gathers layer k and finishes layer k-1 (its top-level source needs pfrac of layer k).
@@ -477,6 +482,123 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                         const FT sum = row_sum(hs);
                         if (lane < 16 && lev <= ktop) accs[((lane & 1) ? UP : DN) * kAccStride + lev] += sum;
                         if (spectral && lev <= ktop) band_add((lane & 1) ? UP : DN, lev, hs);
+                    }
+                    __syncwarp();
+                }
+            } else if (NOSCAT) {
+                // compute_optical_props.jl:43-82 sources + longwave_noscat.jl:224-301, marched from the TOP so the
+                // down sweep shares the pass with the gas optics: iteration j gathers layer j and steps the
+                // intensities of every angle through layer j + 1 (its bottom-level source needs pfrac of layer j).
+                // (tau, B_lay pfrac, source of the layer's top level) go to the level store for the up sweep.
+                const FT* pbk = W.plk + bl * (2 * nlev);        // B(t_lev[0..nlay]), B(t_sfc)
+                const FT* pby = pbk + nlev + 1;                 // B(t_lay[0..nlay-1])
+                const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
+                const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : 0.f;
+                FT Ia[NMU], Ds[NMU], i2f[NMU];
+#pragma unroll
+                for (int a = 0; a < NMU; ++a) {
+                    const bool on = NMU == 1 || a < P.n_mu;
+                    Ds[a] = on ? P.Ds[a] : 0.f;                 // an inactive angle: trans = 1, source = 0, weight 0
+                    i2f[a] = on ? Num<FT>::pi() * P.wts[a] : 0.f;
+                    Ia[a] = P.io.inc_flux_lw ? hdiv(inc, Num<FT>::pi()) : 0.f;
+                }
+                {
+                    FT f = 0.f, hs;
+#pragma unroll
+                    for (int a = 0; a < NMU; ++a) f += Ia[a] * i2f[a];
+                    const FT sum = warp_sum2(f, hs);
+                    if (lane == 0) accs[DN * kAccStride + nlay] += sum;
+                }
+                int cur_half = (nlay - 1) >> 5;
+                build_records(cur_half);
+                FT tau, ssa, g, pf;
+                gather(nlay - 1, G);
+                finish(G, tau, ssa, g, pf);
+                FT lev_top = pbk[nlay] * pf;                     // source of the top level of the layer in hand
+                // down step of every angle through layer k = (tau_k, lay_k) given the source of its bottom level
+                auto step_down = [&](int k, FT tau_k, FT lay_k, FT lev_bot) -> FT {
+                    tmem_st2(tA + 2 * k, tau_k, lay_k);
+                    st_alpha(k, lev_top);
+                    FT f = 0.f;
+#pragma unroll
+                    for (int a = 0; a < NMU; ++a) {
+                        const FT tl = tau_k * Ds[a];
+                        const FT tr = hexp(-tl);
+                        Ia[a] = tr * Ia[a] + lw_noscat_source(lev_bot, lay_k, tl, tr);
+                        f += Ia[a] * i2f[a];
+                    }
+                    lev_top = lev_bot;
+                    return f;
+                };
+                // The gathers of layer j are issued one iteration ahead, right after the registers of layer j + 1
+                // are consumed, so they are in flight across the angle loop; at the first layer of a 32-layer record
+                // part there is nothing to run ahead to (its records are not built yet): that iteration re-issues
+                // its own loads (discarded) and the next part starts with a fresh gather.
+                bool need_gather = true;
+                for (int jc = (nlay - 2) & ~15; jc >= 0; jc -= 16) {   // tiles of <= 16 layers j; level j + 1 per row
+                    const int jtop = jc + 15 < nlay - 2 ? jc + 15 : nlay - 2;
+                    if ((jc >> 5) != cur_half) { cur_half = jc >> 5; build_records(cur_half); need_gather = true; }
+                    if (need_gather) { gather(jtop, G); need_gather = false; }
+                    const int part_lo = cur_half << 5;
+                    for (int j = jtop; j >= jc; --j) {                  // single basic block
+                        const FT tau_u = tau, lay_u = pby[j + 1] * pf;    // layer j + 1
+                        const FT bk = pbk[j + 1];
+                        const FT dec_u = bk * pf;
+                        finish(G, tau, ssa, g, pf);                       // layer j
+                        gather(j > part_lo ? j - 1 : j, G);
+                        const FT lev_bot = hsqrt((bk * pf) * dec_u);      // compute_optical_props.jl:66-75
+                        stage[(j - jc) * kStageStride + lane] = step_down(j + 1, tau_u, lay_u, lev_bot);
+                    }
+                    __syncwarp();
+                    {
+                        FT hs;
+                        const FT sum = row_sum(hs);
+                        if (lane < 16 && lane <= jtop - jc) accs[DN * kAccStride + jc + 1 + lane] += sum;
+                    }
+                    __syncwarp();
+                }
+                {   // lowest layer, then the surface (longwave_noscat.jl:262-268)
+                    FT hs;
+                    const FT d0 = warp_sum2(step_down(0, tau, pby[0] * pf, pbk[0] * pf), hs);
+                    const FT sfc_source = pbk[nlev] * pf;
+                    FT f = 0.f;
+#pragma unroll
+                    for (int a = 0; a < NMU; ++a) {
+                        Ia[a] = Ia[a] * (1.f - emis) + emis * sfc_source;
+                        f += Ia[a] * i2f[a];
+                    }
+                    const FT u0 = warp_sum2(f, hs);
+                    if (lane == 0) { accs[DN * kAccStride] += d0; accs[UP * kAccStride] += u0; }
+                }
+                tmem_wait_st();
+                FT tk, yk, lt;
+                tmem_ld2(tA, tk, yk);
+                ld_alpha_t(0, lt);
+                tmem_wait_ld();
+                for (int kc = 0; kc < nlay; kc += 16) {                // up sweep: 16 levels k + 1 per tile
+                    const int kend = kc + 16 < nlay ? kc + 16 : nlay;
+                    for (int k = kc; k < kend; ++k) {
+                        const FT tau_k = tk, lay_k = yk;
+                        const FT lev_k1 = k < kAlphaTmemLevels ? lt : ld_alpha_s(k);
+                        const int kn = k + 1 < nlay ? k + 1 : k;
+                        tmem_ld2(tA + 2 * kn, tk, yk);
+                        ld_alpha_t(kn, lt);
+                        FT f = 0.f;
+#pragma unroll
+                        for (int a = 0; a < NMU; ++a) {
+                            const FT tl = tau_k * Ds[a];
+                            const FT tr = hexp(-tl);
+                            Ia[a] = tr * Ia[a] + lw_noscat_source(lev_k1, lay_k, tl, tr);
+                            f += Ia[a] * i2f[a];
+                        }
+                        stage[(k - kc) * kStageStride + lane] = f;
+                        tmem_wait_ld();
+                    }
+                    __syncwarp();
+                    {
+                        FT hs;
+                        const FT sum = row_sum(hs);
+                        if (lane < 16 && kc + lane < kend) accs[UP * kAccStride + kc + 1 + lane] += sum;
                     }
                     __syncwarp();
                 }
@@ -608,7 +730,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     up *= sc; dn *= sc; net *= sc; dr *= sc;
                 }
                 P.io.out_up[o] = up; P.io.out_dn[o] = dn; P.io.out_net[o] = net;
-                if (!LW) P.io.out_dir[o] = dr;
+                if (!LWG) P.io.out_dir[o] = dr;
                 if (P.io.out_total_net != nullptr) P.io.out_total_net[o] = P.io.add_net[o] + net;
             }
         }

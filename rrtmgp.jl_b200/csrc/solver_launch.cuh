@@ -1,0 +1,118 @@
+// Launch plumbing of the fast kernels (solver_fast.cuh).  The kernels are instantiated in several translation
+// units (solver_fast_inst.cu compiled once per (mode, minor-slot groups), see the Makefile) so the build
+// parallelises; solver.cu dispatches to their entry points.
+#pragma once
+#include "solver_fast.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace rb {
+
+static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// entry points of the per-(mode, NG) translation units; return a cudaError_t as int, or -1 = not applicable
+int launch_fast_lw_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_fast_lw_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_fast_sw_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_fast_sw_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_fast_noscat_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_fast_noscat_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+
+// Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
+template <int WARPS>
+static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin, bool noscat) {
+    using Geom = FastGeom<WARPS>;
+    constexpr int kAlphaTmemLevels = Geom::alpha_tmem_levels, kAccStride = Geom::acc_stride, kFastWarps = WARPS;
+    const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
+    const int nrec = nlay < 32 ? nlay : 32;                    // band records cover half a column at a time
+    // record = 8 corner weights, {s1, s2, two major-table offsets}, 4 slot scalings per group,
+    // {aerosol-only products, minor-table offset}, {cloud+aerosol products, minor-table offset}
+    P.rec_words = 20 + 4 * P.lut.n_minor_groups;
+    // Phase 1 writes a record with lane = layer, so the lane stride is the row: 2 * rec_words = 48 / 56 words puts
+    // every lane on bank 0 or 16 (16-way conflicts on each of the ~50 stores per lane; ncu: 8.4e6 excessive shared
+    // wavefronts per SM, 28 % of the L1 data-pipe time).  A row of 4 * odd words keeps the 16-byte alignment of the
+    // 128-bit record loads and spreads the lanes over 8 bank groups.
+    P.rec_row = maxb * P.rec_words;
+    if (((P.rec_row >> 2) & 1) == 0) P.rec_row += 4;
+    int off = 0;
+    P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
+    P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(float), 16);
+    P.off_recj = off;   // unused by the fast kernels (eta offsets travel in the record)
+    P.off_rec = off;  off = align_up(off + nrec * P.rec_row * (int)sizeof(float), 16);
+    // per band: B(t_lev), B(t_sfc) (+ B(t_lay), no-scattering)
+    P.off_plk = off;  off = align_up(off + maxb * (noscat ? 2 * nlev : nlev + 1) * (int)sizeof(float), 16);
+    P.off_store = off;
+    const int n_hi = (nlay > kAlphaTmemLevels ? nlay - kAlphaTmemLevels : 0) + 1;   // + dummy slot
+    F.off_alpha = off; off = align_up(off + n_hi * 32 * (int)sizeof(float), 128);
+    F.off_stage = off; off = align_up(off + 16 * kStageStride * (int)sizeof(float), 16);
+    F.off_acc = off;   off = align_up(off + 3 * kAccStride * (int)sizeof(float), 128);
+    F.off_bacc = -1;
+    if (P.io.band_up != nullptr) { F.off_bacc = off; off = align_up(off + 4 * kAccStride * (int)sizeof(float), 128); }
+    P.warp_bytes = off;
+    // CTA-shared tail: the staged small-table block and the global-mean vmr array
+    int tail = kFastWarps * off;
+    F.off_vmr = tail;  tail = align_up(tail + (P.ngas > 0 ? P.ngas : 1) * (int)sizeof(float), 128);
+    F.off_blob = tail;
+    int room = max_smem_optin - 64 - tail;   // 64: static shared memory of the kernel
+    // RRTMGP_B200_STAGE_BYTES caps the staged prefix (A/B experiments: shared memory is taken from the L1 cache)
+    if (const char* e = std::getenv("RRTMGP_B200_STAGE_BYTES")) room = std::min(room, std::atoi(e));
+    F.staged_bytes = 0;
+    for (int i = 0; i < P.lut.n_blob_cut; ++i)
+        if (P.lut.blob_cut[i] <= room) F.staged_bytes = P.lut.blob_cut[i];
+    return tail + F.staged_bytes;
+}
+
+static int sm_count_of_current_device() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cached[dev] > 0 ? cached[dev] : 148;
+}
+
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL, int WARPS, int NMU>
+static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
+    FastSmem F;
+    constexpr int kFastWarps = WARPS;
+    const size_t smem = (size_t)plan_smem_fast<WARPS>(P, F, max_smem_optin, MODE == MODE_LW_NOSCAT);
+    if ((int)smem > max_smem_optin) return -1;   // does not fit: generic kernel
+    auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER, SPECTRAL, WARPS, NMU>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (P.work_counter == nullptr) return -1;
+    e = cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return (int)e;
+    const int need = (P.ncol + kFastWarps - 1) / kFastWarps;
+    const int sms = sm_count_of_current_device();
+    const int grid = need < sms ? need : sms;   // persistent: one CTA per SM
+    kern<<<grid, kFastWarps * 32, smem, stream>>>(P, F);
+    return (int)cudaGetLastError();
+}
+
+template <int MODE, int NGPT, int NG, bool SPECTRAL, int WARPS, int NMU = 1>
+static int launch_fast_sp(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
+    const bool c = P.use_cloud != 0, a = P.use_aero != 0;
+    if (c && a) return launch_fast_t<MODE, NGPT, NG, true, true, SPECTRAL, WARPS, NMU>(P, max_smem_optin, s);
+    if (c) return launch_fast_t<MODE, NGPT, NG, true, false, SPECTRAL, WARPS, NMU>(P, max_smem_optin, s);
+    if (a) return launch_fast_t<MODE, NGPT, NG, false, true, SPECTRAL, WARPS, NMU>(P, max_smem_optin, s);
+    return launch_fast_t<MODE, NGPT, NG, false, false, SPECTRAL, WARPS, NMU>(P, max_smem_optin, s);
+}
+
+// nlay <= 64: 12 warps per SM; taller columns (<= 95 layers): the 8-warp geometry, broadband fluxes only
+template <int MODE, int NGPT, int NG>
+static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
+    if constexpr (MODE == MODE_LW_NOSCAT) {   // no-scattering LW: 12-warp geometry, broadband fluxes; one angle or up to four
+        if (P.nlay > FastGeom<12>::max_lay || P.io.band_up != nullptr) return -1;
+        return P.n_mu == 1 ? launch_fast_sp<MODE, NGPT, NG, false, 12, 1>(P, max_smem_optin, s)
+                           : launch_fast_sp<MODE, NGPT, NG, false, 12, 4>(P, max_smem_optin, s);
+    } else {
+        if (P.nlay > FastGeom<12>::max_lay)
+            return P.io.band_up != nullptr ? -1 : launch_fast_sp<MODE, NGPT, NG, false, 8>(P, max_smem_optin, s);
+        return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true, 12>(P, max_smem_optin, s)
+                                       : launch_fast_sp<MODE, NGPT, NG, false, 12>(P, max_smem_optin, s);
+    }
+}
+
+}  // namespace rb

@@ -528,3 +528,48 @@ def test_ln_p_ref_entry_is_accepted(real_pack):
     kw = dict(method="clear_sky", aerosols=False)
     a, b = run_engine(R.lutpack.pack_luts(arrays), st, np.float64, **kw), run_engine(real_pack, st, np.float64, **kw)
     _check_f64(a, b, rel=1e-12)
+
+
+# ---- Float32 fast path of the no-scattering longwave solver (TMEM store, marched from the top) ----
+@pytest.mark.parametrize("n_angles", [1, 2, 3, 4])
+def test_lw_noscat_fast_path_angles_f32(real_pack, n_angles):
+    """`NoScatLWRTE` with 1-4 Gauss angles (AngularDiscretizations.jl:34-63) on the Float32 fast kernel vs the
+    Float64 oracle; partial cloudiness so the McICA masks differ per g-point."""
+    st = R.synthetic.make_atmosphere(192, 64, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, lw_noscat=True, n_gauss_angles=n_angles, seed=21)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+    np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(np.float32))
+
+
+@pytest.mark.parametrize("nlay", [8, 17, 31, 32, 33, 48, 49, 63])
+def test_lw_noscat_fast_path_runtime_nlay_f32(real_pack, nlay):
+    """Layer counts at every tile (16) and record-part (32) boundary of the top-down march."""
+    st = R.synthetic.make_atmosphere(96, nlay, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, lw_noscat=True, seed=8)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+
+
+def test_lw_noscat_fast_path_clear_sky_and_generic_kernel_agree(real_pack, monkeypatch):
+    """Clear sky (no cloud / aerosol increment) and an incident TOA flux; the fast kernel against the oracle and
+    against the generic shared-memory kernel (RRTMGP_B200_KERNEL=generic) on the same inputs."""
+    st = R.synthetic.make_atmosphere(128, 64, clouds=False, aerosols=False)
+    rng = np.random.default_rng(4)
+    st["inc_flux_lw"] = rng.uniform(0.0, 0.02, (256, 128)).astype(np.float32)     # (ngpt, ncol) layout of BCs.jl:14-15
+    kw = dict(method="clear_sky", aerosols=False, lw_noscat=True, n_gauss_angles=3)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLEAR, run_oracle(real_pack, st, np.float32, **kw))
+    monkeypatch.setenv("RRTMGP_B200_KERNEL", "generic")
+    gen = run_engine(real_pack, st, np.float32, **kw)
+    for k in ("lw_up", "lw_dn", "lw_net"):
+        assert maxdiff(e[k], gen[k]) <= F32_LW, k
+
+
+def test_lw_noscat_fast_path_two_minor_groups_f32():
+    dims = R.synthetic.LutDims(minor_lower_lw=6, minor_lower_sw=5)
+    pack = R.synthetic.make_lut_pack(seed=7, dims=dims)
+    st = R.synthetic.make_atmosphere(96, 64, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, lw_noscat=True, n_gauss_angles=2, seed=5)
+    e, o = run_engine(pack, st, np.float32, **kw), run_oracle(pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(pack, st, np.float32, **kw))
