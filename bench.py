@@ -297,6 +297,23 @@ def main():
                      "unit": "TFLOP/s", "frac": cols_per_s_gpu * ALGO_FLOPS_PER_COL / 1e12 / FP32_PEAK_TFLOPS,
                      "peak_source": "nominal 148 SM x 128 x 2 x 1.965 GHz", "algorithmic_flops_per_column": ALGO_FLOPS_PER_COL}
 
+    # The two limits that actually bind: warp-instruction issue (4 schedulers x 1 instr/clk per SM) and
+    # the L1 data pipe (one 128-byte wavefront/clk per SM, shared + global).  Counts per launch are properties of
+    # the workload measured once with ncu (profiles/traffic.json); the time is this run's.
+    roofline_issue = None
+    try:
+        tag = "lw" if dom == "LW" else "sw"
+        sms, ghz = 148, (clk.summary()["sm_mhz"] or 1965.0) * 1e-3
+        scale = ncol / tj["ncol"]
+        cyc = dom_ms * 1e-3 * ghz * 1e9
+        roofline_issue = {"bound": "issue", "kernel": dom,
+                          "warp_instructions_per_launch": tj[f"{tag}_warp_instructions"] * scale,
+                          "issue_frac": tj[f"{tag}_warp_instructions"] * scale / (sms * 4 * cyc),
+                          "l1_data_pipe_frac": tj[f"{tag}_l1_data_wavefronts_per_sm"] * scale / cyc,
+                          "source": "instruction / wavefront counts: " + tj["source"]}
+    except Exception:
+        pass
+
     # --- e2e: the state lives in pinned HOST memory; every step copies every per-column input H2D, runs
     # update_fluxes! and copies every flux / diagnostic D2H (HostPipeline: column chunks on 3 streams) ---
     e2e = None
@@ -357,7 +374,7 @@ def main():
                            "parallelism": f"column shards x{world}" + (", NCCL all-gather of 8 flux views" if world > 1 else ""),
                            "l2_policy": f"inputs {ncol * (in_common + 400) / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "roofline_fp32": roofline_fp32, "cpu_baseline": cpu_baseline,
+                "roofline_fp32": roofline_fp32, "roofline_issue": roofline_issue, "cpu_baseline": cpu_baseline,
                 "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -463,7 +463,7 @@ struct Warp {
                         }
                     }
                 }
-                if (FUSED) {
+                if constexpr (FUSED) {
                     // increment_2stream (optics_utils.jl:189-202) is additive in (tau, tau ssa, tau ssa g):
                     // store those products for "aerosol only" and "cloud + aerosol" as two 16-byte groups whose
                     // fourth word is the minor-table offset, so a cell needs one 128-bit load for both
@@ -473,18 +473,19 @@ struct Warp {
                     const FT ft = colp[4 * k + 0], fp = colp[4 * k + 1];
                     const FT omft = FT(1) - ft, omfp = FT(1) - fp;
                     const FT wa0 = omfp * omft, wa1 = fp * omft, wb0 = omfp * ft, wb1 = fp * ft;
-                    r[0] = wa0 * (FT(1) - fe[0]); r[1] = wa0 * fe[0]; r[2] = wa1 * (FT(1) - fe[0]); r[3] = wa1 * fe[0];
-                    r[4] = wb0 * (FT(1) - fe[1]); r[5] = wb0 * fe[1]; r[6] = wb1 * (FT(1) - fe[1]); r[7] = wb1 * fe[1];
-                    r[8] = smix[0]; r[9] = smix[1];
+                    // (128-bit stores: with lane = layer and a row of 4 * odd words they are bank-conflict free)
+                    float4* r4 = reinterpret_cast<float4*>(r);
+                    r4[0] = make_float4(wa0 * (FT(1) - fe[0]), wa0 * fe[0], wa1 * (FT(1) - fe[0]), wa1 * fe[0]);
+                    r4[1] = make_float4(wb0 * (FT(1) - fe[1]), wb0 * fe[1], wb1 * (FT(1) - fe[1]), wb1 * fe[1]);
                     // element offsets without the g-point: (jp-1, jt, je1) and (jp-1, jt+1, je2) rows of the major
                     // table, (jt, je1) row of the packed minor table; its (jt+1, je2) row is at ma + (ib - ia)
                     const int e1 = (je[0] - 1) * L.n_gpt, e2 = (je[1] - 1) * L.n_gpt;
                     const int rowoff = __float_as_int((float)colp[4 * k + 3]), moff = __float_as_int((float)colp[4 * k + 2]);
-                    r[10] = int_as_ft<FT>(rowoff + e1);
-                    r[11] = int_as_ft<FT>(rowoff + L.n_eta * L.n_gpt + e2);
+                    r4[2] = make_float4(smix[0], smix[1], int_as_ft<FT>(rowoff + e1), int_as_ft<FT>(rowoff + L.n_eta * L.n_gpt + e2));
                     const FT ma = int_as_ft<FT>(moff + e1);
-                    rc[0] = a0; rc[1] = a1; rc[2] = a2; rc[3] = ma;
-                    rc[4] = a0 + tc; rc[5] = a1 + tc * sc; rc[6] = a2 + tc * sc * gc; rc[7] = ma;
+                    float4* rc4 = reinterpret_cast<float4*>(rc);
+                    rc4[0] = make_float4(a0, a1, a2, ma);
+                    rc4[1] = make_float4(a0 + tc, a1 + tc * sc, a2 + tc * sc * gc, ma);
                 } else {
                     if (use_cloud) { rc[0] = tc; rc[1] = sc; rc[2] = gc; }
                     if (use_aero) { rc[3] = ta; rc[4] = sa; rc[5] = ga; }
