@@ -47,7 +47,7 @@ static bool fast_enabled() {
     return !(e && !std::strcmp(e, "generic"));
 }
 
-// Fast path: Float32, nlay <= 95 (no-scattering LW: <= 64), real-table shape. Returns -1 when not applicable.
+// Fast path: Float32, nlay <= 95, real-table shape. Returns -1 when not applicable.
 template <typename FT> static int try_fast(int, SolveParams<FT>&, int, cudaStream_t) { return -1; }
 template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
     const GasLut<float>& L = P.lut;
@@ -57,8 +57,10 @@ template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_op
     const bool ng1 = L.n_minor_groups == 1;
     if (mode == MODE_LW_2STREAM && L.n_gpt == 256 && L.kmaj_pf != nullptr)
         return ng1 ? launch_fast_lw_ng1(P, max_smem_optin, s) : launch_fast_lw_ng2(P, max_smem_optin, s);
-    if (mode == MODE_LW_NOSCAT && L.n_gpt == 256 && L.kmaj_pf != nullptr)
-        return ng1 ? launch_fast_noscat_ng1(P, max_smem_optin, s) : launch_fast_noscat_ng2(P, max_smem_optin, s);
+    if (mode == MODE_LW_NOSCAT && L.n_gpt == 256 && L.kmaj_pf != nullptr) {
+        if (P.n_mu == 1) return ng1 ? launch_fast_noscat1_ng1(P, max_smem_optin, s) : launch_fast_noscat1_ng2(P, max_smem_optin, s);
+        return ng1 ? launch_fast_noscat4_ng1(P, max_smem_optin, s) : launch_fast_noscat4_ng2(P, max_smem_optin, s);
+    }
     if (mode == MODE_SW_2STREAM && L.n_gpt == 224)
         return ng1 ? launch_fast_sw_ng1(P, max_smem_optin, s) : launch_fast_sw_ng2(P, max_smem_optin, s);
     return -1;

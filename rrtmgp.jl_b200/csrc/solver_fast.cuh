@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     for (int a = 0; a < NMU; ++a) f += Ia[a] * i2f[a];
                     const FT sum = warp_sum2(f, hs);
                     if (lane == 0) accs[DN * kAccStride + nlay] += sum;
+                    if (spectral && (lane & 15) == 0) band_add(DN, nlay, hs);
                 }
                 int cur_half = (nlay - 1) >> 5;
                 build_records(cur_half);
@@ -554,12 +555,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                         FT hs;
                         const FT sum = row_sum(hs);
                         if (lane < 16 && lane <= jtop - jc) accs[DN * kAccStride + jc + 1 + lane] += sum;
+                        if (spectral && (lane & 15) <= jtop - jc) band_add(DN, jc + 1 + (lane & 15), hs);
                     }
                     __syncwarp();
                 }
                 {   // lowest layer, then the surface (longwave_noscat.jl:262-268)
-                    FT hs;
-                    const FT d0 = warp_sum2(step_down(0, tau, pby[0] * pf, pbk[0] * pf), hs);
+                    FT hd, hu;
+                    const FT d0 = warp_sum2(step_down(0, tau, pby[0] * pf, pbk[0] * pf), hd);
                     const FT sfc_source = pbk[nlev] * pf;
                     FT f = 0.f;
 #pragma unroll
@@ -567,8 +569,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                         Ia[a] = Ia[a] * (1.f - emis) + emis * sfc_source;
                         f += Ia[a] * i2f[a];
                     }
-                    const FT u0 = warp_sum2(f, hs);
+                    const FT u0 = warp_sum2(f, hu);
                     if (lane == 0) { accs[DN * kAccStride] += d0; accs[UP * kAccStride] += u0; }
+                    if (spectral && (lane & 15) == 0) { band_add(DN, 0, hd); band_add(UP, 0, hu); }
                 }
                 tmem_wait_st();
                 FT tk, yk, lt;
@@ -599,6 +602,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                         FT hs;
                         const FT sum = row_sum(hs);
                         if (lane < 16 && kc + lane < kend) accs[UP * kAccStride + kc + 1 + lane] += sum;
+                        if (spectral && kc + (lane & 15) < kend) band_add(UP, kc + 1 + (lane & 15), hs);
                     }
                     __syncwarp();
                 }

@@ -16,8 +16,10 @@ int launch_fast_lw_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s
 int launch_fast_lw_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
 int launch_fast_sw_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
 int launch_fast_sw_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
-int launch_fast_noscat_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
-int launch_fast_noscat_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_fast_noscat1_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);   // one Gauss angle
+int launch_fast_noscat1_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_fast_noscat4_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);   // two to four angles
+int launch_fast_noscat4_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
 
 // Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
 template <int WARPS>
@@ -101,17 +103,18 @@ static int launch_fast_sp(SolveParams<float>& P, int max_smem_optin, cudaStream_
 }
 
 // nlay <= 64: 12 warps per SM; taller columns (<= 95 layers): the 8-warp geometry, broadband fluxes only
-template <int MODE, int NGPT, int NG>
+// NMU: Gauss angles of the no-scattering LW kernel (1, or 4 = up to four with P.n_mu active); 1 for the two-stream modes
+template <int MODE, int NGPT, int NG, int NMU = 1>
 static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
-    if constexpr (MODE == MODE_LW_NOSCAT) {   // no-scattering LW: 12-warp geometry, broadband fluxes; one angle or up to four
-        if (P.nlay > FastGeom<12>::max_lay || P.io.band_up != nullptr) return -1;
-        return P.n_mu == 1 ? launch_fast_sp<MODE, NGPT, NG, false, 12, 1>(P, max_smem_optin, s)
-                           : launch_fast_sp<MODE, NGPT, NG, false, 12, 4>(P, max_smem_optin, s);
+    if constexpr (MODE == MODE_LW_NOSCAT) {   // NoScatLWRTE carries no band fluxes (src/rte/RTE.jl:53-72)
+        if (P.io.band_up != nullptr) return -1;
+        return P.nlay > FastGeom<12>::max_lay ? launch_fast_sp<MODE, NGPT, NG, false, 8, NMU>(P, max_smem_optin, s)
+                                              : launch_fast_sp<MODE, NGPT, NG, false, 12, NMU>(P, max_smem_optin, s);
     } else {
         if (P.nlay > FastGeom<12>::max_lay)
-            return P.io.band_up != nullptr ? -1 : launch_fast_sp<MODE, NGPT, NG, false, 8>(P, max_smem_optin, s);
-        return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true, 12>(P, max_smem_optin, s)
-                                       : launch_fast_sp<MODE, NGPT, NG, false, 12>(P, max_smem_optin, s);
+            return P.io.band_up != nullptr ? -1 : launch_fast_sp<MODE, NGPT, NG, false, 8, NMU>(P, max_smem_optin, s);
+        return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true, 12, NMU>(P, max_smem_optin, s)
+                                       : launch_fast_sp<MODE, NGPT, NG, false, 12, NMU>(P, max_smem_optin, s);
     }
 }
 

@@ -573,3 +573,13 @@ def test_lw_noscat_fast_path_two_minor_groups_f32():
     kw = dict(method="all_sky", aerosols=True, lw_noscat=True, n_gauss_angles=2, seed=5)
     e, o = run_engine(pack, st, np.float32, **kw), run_oracle(pack, st, np.float64, **kw)
     _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(pack, st, np.float32, **kw))
+
+
+@pytest.mark.parametrize("nlay,n_angles", [(65, 1), (72, 2), (95, 1)])
+def test_lw_noscat_fast_path_tall_columns_f32(real_pack, nlay, n_angles):
+    """Columns taller than 64 layers: the 8-warp CTA geometry (256 TMEM columns per warp, three record parts)."""
+    st = R.synthetic.make_atmosphere(64, nlay, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, lw_noscat=True, n_gauss_angles=n_angles, seed=13)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+    np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(np.float32))
