@@ -59,6 +59,24 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& a) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(taddr) : "memory");
     a = __uint_as_float(x);
 }
+// 8 levels at once: 16 consecutive columns ((A, B) pairs) / 8 consecutive columns (albedos) of this thread's lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Geometry of the persistent CTA: 12 warps (3 per TMEM lane quadrant, 170 columns each) for nlay <= 64, or 8 warps
@@ -458,22 +476,45 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     if (spectral && (lane & 15) == 0) { band_add(UP, nlay, hu); band_add(DN, nlay, hd); }
                 }
                 tmem_wait_st();
-                FT A, B, al;
-                tmem_ld2(tA + 2 * (nlay - 1), A, B);
-                ld_alpha_t(nlay - 1, al);
-                tmem_wait_ld();
+                // Second sweep, 8 levels per tile.  A full tile whose albedos all sit in TMEM or all in shared memory
+                // reads its (A, B) pairs with ONE tcgen05.ld.x16 (and the albedos with one .x8 or eight LDS) and has no
+                // per-level TMEM round trip; the top tile of a column whose layer count is not a multiple of 8 and the
+                // tile that straddles the TMEM / shared-memory albedo split take the level-by-level path.
                 for (int kc = (nlay - 1) & ~7; kc >= 0; kc -= 8) {     // 8 levels x (dn, albedo * dn) per tile
                     const int ktop = kc + 7 < nlay - 1 ? kc + 7 : nlay - 1;
-                    for (int k = ktop; k >= kc; --k) {
-                        const FT Ak = A, Bk = B;
-                        const FT alk = k < kAlphaTmemLevels ? al : ld_alpha_s(k);
-                        const int kn = k > 0 ? k - 1 : 0;                // prefetch the next level (harmless reload at k = 0)
-                        tmem_ld2(tA + 2 * kn, A, B);
-                        ld_alpha_t(kn, al);
-                        dn = Ak * dn + Bk;
-                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = dn;
-                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = alk * dn;
+                    const bool al_tmem = kc + 8 <= kAlphaTmemLevels, al_smem = kc >= kAlphaTmemLevels;
+                    if (ktop == kc + 7 && (al_tmem || al_smem)) {
+                        float ab[16], al8[8];
+                        tmem_ld16(tA + 2 * kc, ab);
+                        if (al_tmem) {
+                            tmem_ld8(tAl + kc, al8);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) al8[i] = alpha_hi[(kc + i - kAlphaTmemLevels + 1) * 32 + lane];
+                        }
                         tmem_wait_ld();
+#pragma unroll
+                        for (int i = 7; i >= 0; --i) {
+                            dn = ab[2 * i] * dn + ab[2 * i + 1];
+                            stage[(i * 2 + 0) * kStageStride + lane] = dn;
+                            stage[(i * 2 + 1) * kStageStride + lane] = al8[i] * dn;
+                        }
+                    } else {
+                        FT A, B, al;
+                        tmem_ld2(tA + 2 * ktop, A, B);
+                        ld_alpha_t(ktop, al);
+                        tmem_wait_ld();
+                        for (int k = ktop; k >= kc; --k) {
+                            const FT Ak = A, Bk = B;
+                            const FT alk = k < kAlphaTmemLevels ? al : ld_alpha_s(k);
+                            const int kn = k > 0 ? k - 1 : 0;            // prefetch the next level (harmless reload at k = 0)
+                            tmem_ld2(tA + 2 * kn, A, B);
+                            ld_alpha_t(kn, al);
+                            dn = Ak * dn + Bk;
+                            stage[((k - kc) * 2 + 0) * kStageStride + lane] = dn;
+                            stage[((k - kc) * 2 + 1) * kStageStride + lane] = alk * dn;
+                            tmem_wait_ld();
+                        }
                     }
                     __syncwarp();
                     {
@@ -574,28 +615,46 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     if (spectral && (lane & 15) == 0) { band_add(DN, 0, hd); band_add(UP, 0, hu); }
                 }
                 tmem_wait_st();
-                FT tk, yk, lt;
-                tmem_ld2(tA, tk, yk);
-                ld_alpha_t(0, lt);
-                tmem_wait_ld();
+                // angle loop of one layer of the up sweep
+                auto step_up = [&](FT tau_k, FT lay_k, FT lev_k1) -> FT {
+                    FT f = 0.f;
+#pragma unroll
+                    for (int a = 0; a < NMU; ++a) {
+                        const FT tl = tau_k * Ds[a];
+                        const FT tr = hexp(-tl);
+                        Ia[a] = tr * Ia[a] + lw_noscat_source(lev_k1, lay_k, tl, tr);
+                        f += Ia[a] * i2f[a];
+                    }
+                    return f;
+                };
                 for (int kc = 0; kc < nlay; kc += 16) {                // up sweep: 16 levels k + 1 per tile
                     const int kend = kc + 16 < nlay ? kc + 16 : nlay;
-                    for (int k = kc; k < kend; ++k) {
-                        const FT tau_k = tk, lay_k = yk;
-                        const FT lev_k1 = k < kAlphaTmemLevels ? lt : ld_alpha_s(k);
-                        const int kn = k + 1 < nlay ? k + 1 : k;
-                        tmem_ld2(tA + 2 * kn, tk, yk);
-                        ld_alpha_t(kn, lt);
-                        FT f = 0.f;
+                    for (int k8 = kc; k8 < kend; k8 += 8) {            // 8 layers per batch of TMEM reads (see the LW sweep)
+                        const int k8e = k8 + 8 < kend ? k8 + 8 : kend;
+                        const bool lt_tmem = k8 + 8 <= kAlphaTmemLevels, lt_smem = k8 >= kAlphaTmemLevels;
+                        if (k8e == k8 + 8 && (lt_tmem || lt_smem)) {
+                            float ty[16], lt8[8];
+                            tmem_ld16(tA + 2 * k8, ty);
+                            if (lt_tmem) {
+                                tmem_ld8(tAl + k8, lt8);
+                            } else {
 #pragma unroll
-                        for (int a = 0; a < NMU; ++a) {
-                            const FT tl = tau_k * Ds[a];
-                            const FT tr = hexp(-tl);
-                            Ia[a] = tr * Ia[a] + lw_noscat_source(lev_k1, lay_k, tl, tr);
-                            f += Ia[a] * i2f[a];
+                                for (int i = 0; i < 8; ++i) lt8[i] = alpha_hi[(k8 + i - kAlphaTmemLevels + 1) * 32 + lane];
+                            }
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                stage[(k8 - kc + i) * kStageStride + lane] = step_up(ty[2 * i], ty[2 * i + 1], lt8[i]);
+                        } else {
+                            for (int k = k8; k < k8e; ++k) {
+                                FT tk, yk, lt;
+                                tmem_ld2(tA + 2 * k, tk, yk);
+                                ld_alpha_t(k, lt);
+                                tmem_wait_ld();
+                                const FT lev_k1 = k < kAlphaTmemLevels ? lt : ld_alpha_s(k);
+                                stage[(k - kc) * kStageStride + lane] = step_up(tk, yk, lev_k1);
+                            }
                         }
-                        stage[(k - kc) * kStageStride + lane] = f;
-                        tmem_wait_ld();
                     }
                     __syncwarp();
                     {
@@ -688,22 +747,41 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     if (spectral && (lane & 15) == 0) { band_add(UP, 0, hu); band_add(DN, 0, hdd); }
                 }
                 tmem_wait_st();
-                FT A, B, be;
-                tmem_ld2(tA, A, B);
-                ld_alpha_t(0, be);
-                tmem_wait_ld();
                 for (int kc = 0; kc < nlay; kc += 8) {                // 8 levels x (F_up, beta * F_up) per tile
                     const int kend = kc + 8 < nlay ? kc + 8 : nlay;
-                    for (int k = kc; k < kend; ++k) {
-                        const FT Ak = A, Bk = B;
-                        const FT bek = k < kAlphaTmemLevels ? be : ld_alpha_s(k);
-                        const int kn = k + 1 < nlay ? k + 1 : k;
-                        tmem_ld2(tA + 2 * kn, A, B);
-                        ld_alpha_t(kn, be);
-                        up = Ak * up + Bk;                                  // F_up(k+1)
-                        stage[((k - kc) * 2 + 0) * kStageStride + lane] = up;
-                        stage[((k - kc) * 2 + 1) * kStageStride + lane] = bek * up;
+                    const bool be_tmem = kc + 8 <= kAlphaTmemLevels, be_smem = kc >= kAlphaTmemLevels;
+                    if (kend == kc + 8 && (be_tmem || be_smem)) {       // one tcgen05.ld.x16 (+ .x8) per tile, as in the LW sweep
+                        float ab[16], be8[8];
+                        tmem_ld16(tA + 2 * kc, ab);
+                        if (be_tmem) {
+                            tmem_ld8(tAl + kc, be8);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) be8[i] = alpha_hi[(kc + i - kAlphaTmemLevels + 1) * 32 + lane];
+                        }
                         tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            up = ab[2 * i] * up + ab[2 * i + 1];              // F_up(k+1)
+                            stage[(i * 2 + 0) * kStageStride + lane] = up;
+                            stage[(i * 2 + 1) * kStageStride + lane] = be8[i] * up;
+                        }
+                    } else {
+                        FT A, B, be;
+                        tmem_ld2(tA + 2 * kc, A, B);
+                        ld_alpha_t(kc, be);
+                        tmem_wait_ld();
+                        for (int k = kc; k < kend; ++k) {
+                            const FT Ak = A, Bk = B;
+                            const FT bek = k < kAlphaTmemLevels ? be : ld_alpha_s(k);
+                            const int kn = k + 1 < nlay ? k + 1 : k;
+                            tmem_ld2(tA + 2 * kn, A, B);
+                            ld_alpha_t(kn, be);
+                            up = Ak * up + Bk;                                  // F_up(k+1)
+                            stage[((k - kc) * 2 + 0) * kStageStride + lane] = up;
+                            stage[((k - kc) * 2 + 1) * kStageStride + lane] = bek * up;
+                            tmem_wait_ld();
+                        }
                     }
                     __syncwarp();
                     {
