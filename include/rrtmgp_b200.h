@@ -135,8 +135,11 @@ int rrtmgp_b200_create(const rrtmgp_b200_config_t* cfg, rrtmgp_b200_handle_t** o
 void rrtmgp_b200_destroy(rrtmgp_b200_handle_t* h);
 
 /* lookup_tables(grid_params, method) (ext/RRTMGPNCDatasetsExt.jl:93-133): `pack` is a HOST
- * pointer to a flat LUT pack (rrtmgp.jl_b200/lutpack.py); tables are converted to `dtype`,
- * re-laid out g-point-fastest and uploaded. */
+ * pointer to a flat LUT pack (rrtmgp.jl_b200/lutpack.py; built from the rrtmgp-data NetCDF files by
+ * rrtmgp.jl_b200/tables.py or from a loaded LookupBundle by `lut_pack` in julia/RRTMGPB200Ext.jl); tables
+ * are converted to `dtype`, re-laid out g-point-fastest and uploaded.  The cloud (`cld_lw/`, `cld_sw/`) and
+ * aerosol (`aero_lw/`, `aero_sw/`) sections may be absent when the handle's method never reads them (clear
+ * sky / no aerosol radiation, as `lookup_tables` loads them); otherwise RRTMGP_B200_ERR_BAD_LUT_PACK. */
 int rrtmgp_b200_load_luts(rrtmgp_b200_handle_t* h, const void* pack, size_t nbytes);
 int rrtmgp_b200_lut_info(const rrtmgp_b200_handle_t* h, rrtmgp_b200_lut_info_t* out);
 
