@@ -102,7 +102,7 @@ static int launch_fast_sp(SolveParams<float>& P, int max_smem_optin, cudaStream_
     return launch_fast_t<MODE, NGPT, NG, false, false, SPECTRAL, WARPS, NMU>(P, max_smem_optin, s);
 }
 
-// nlay <= 64: 12 warps per SM; taller columns (<= 95 layers): the 8-warp geometry, broadband fluxes only
+// nlay <= 64: 12 warps per SM; taller columns (<= 95 layers): the 8-warp geometry
 // NMU: Gauss angles of the no-scattering LW kernel (1, or 4 = up to four with P.n_mu active); 1 for the two-stream modes
 template <int MODE, int NGPT, int NG, int NMU = 1>
 static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
@@ -112,7 +112,8 @@ static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_
                                               : launch_fast_sp<MODE, NGPT, NG, false, 12, NMU>(P, max_smem_optin, s);
     } else {
         if (P.nlay > FastGeom<12>::max_lay)
-            return P.io.band_up != nullptr ? -1 : launch_fast_sp<MODE, NGPT, NG, false, 8, NMU>(P, max_smem_optin, s);
+            return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true, 8, NMU>(P, max_smem_optin, s)
+                                           : launch_fast_sp<MODE, NGPT, NG, false, 8, NMU>(P, max_smem_optin, s);
         return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true, 12, NMU>(P, max_smem_optin, s)
                                        : launch_fast_sp<MODE, NGPT, NG, false, 12, NMU>(P, max_smem_optin, s);
     }

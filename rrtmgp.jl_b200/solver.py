@@ -39,12 +39,35 @@ AEROSOL_INDEX = {"dust1": 1, "sea_salt1": 2, "sulfate": 3, "black_carbon_rh": 4,
                  "sea_salt2": 12, "sea_salt3": 13, "sea_salt4": 14, "sea_salt5": 15}
 
 
+def canonical_aerosol_name(name: str) -> str:
+    """`canonical_aerosol_name(name)` (src/api/aerosols.jl:78-88): the name itself, or an error naming the known ones."""
+    if name in AEROSOL_INDEX:
+        return str(name)
+    raise KeyError(f"unknown aerosol name {name!r}; known names are {sorted(AEROSOL_INDEX)}")
+
+
 def aerosol_index(name: str) -> int:
-    return AEROSOL_INDEX[name]
+    return AEROSOL_INDEX[canonical_aerosol_name(name)]
 
 
 def aerosol_names():
     return sorted(AEROSOL_INDEX, key=AEROSOL_INDEX.get)
+
+
+def aerosol_index_map() -> dict:
+    """`aerosol_index_map()` (src/api/aerosols.jl): name -> slot of the `aero_mass` / `aero_size` arrays."""
+    return dict(AEROSOL_INDEX)
+
+
+def gas_names_sw():
+    """`gas_names_sw()` (src/api/getters.jl:566-588): the gas names `volume_mixing_ratio` accepts."""
+    return ["h2o", "cfc11", "h2o_self", "co2", "cfc12", "hfc134a", "cfc22", "ch4", "hfc23", "ccl4", "hfc143a", "co",
+            "no2", "n2", "o2", "o3", "h2o_frgn", "hfc32", "n2o", "cf4", "hfc125"]
+
+
+def requires_z(scheme: str) -> bool:
+    """`requires_z(scheme)` (src/api/interpolation.jl:139-146): BestFit and HydrostaticBottom need altitudes."""
+    return scheme in ("BestFit", "HydrostaticBottom")
 
 
 @dataclass(frozen=True)
@@ -377,6 +400,21 @@ def compute_relative_humidity(s: RRTMGPSolver) -> None:
 
 
 # -- state getters (getters.jl:79-152,160-330) ----------------------------------------------
+# table ranges the state is clipped to (src/api/grid_adaptation.jl:24-56; `clip!` :232-258)
+def get_p_min(s): return float(s.lut_info.p_ref_min)
+def get_t_min(s): return float(s.lut_info.t_ref_min)
+def get_t_max(s): return float(s.lut_info.t_ref_max)
+
+
+def center_z(s):
+    """`center_z(s)` / `face_z(s)` (getters.jl:255-262): altitudes given at construction, or None."""
+    return None if s.center_z is None else s._domain(s.center_z, False)
+
+
+def face_z(s):
+    return None if s.face_z is None else s._domain(s.face_z, True)
+
+
 def layer_pressure(s): return s._domain(s.buffers["layerdata"][:, :, 1], False)
 def layer_temperature(s): return s._domain(s.buffers["layerdata"][:, :, 2], False)
 def layer_relative_humidity(s): return s._domain(s.buffers["layerdata"][:, :, 3], False)

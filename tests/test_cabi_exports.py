@@ -87,3 +87,18 @@ def test_solver_fails_loudly_without_cuda():
     with pytest.raises(RuntimeError):
         R.RRTMGPSolver(R.RRTMGPGridParams(FT=np.float32, domain_nlay=8, ncol=2), R.ClearSkyRadiation(),
                        R.default_parameters(), b"")
+
+
+def test_aerosol_and_gas_naming_helpers():
+    """`aerosol_names` / `aerosol_index` / `aerosol_index_map` / `canonical_aerosol_name` (src/api/aerosols.jl) and
+    `gas_names_sw` (src/api/getters.jl:566-588); the ingestion module carries the same aerosol map
+    (ext/lookup_constructors.jl:47-58)."""
+    import rrtmgp_b200 as R
+    assert R.aerosol_names()[0] == "dust1" and len(R.aerosol_names()) == 15
+    assert R.aerosol_index("sea_salt3") == 13 and R.aerosol_index_map() == R.tables.AEROSOL_INDEX
+    assert R.canonical_aerosol_name("sulfate") == "sulfate"
+    with pytest.raises(KeyError, match="known names"):
+        R.aerosol_index("soot")
+    names = R.gas_names_sw()
+    assert len(names) == 21 and set(R.synthetic.GAS_NAMES) | {"h2o_self", "h2o_frgn"} == set(names)
+    assert R.requires_z("BestFit") and R.requires_z("HydrostaticBottom") and not R.requires_z("UniformP")

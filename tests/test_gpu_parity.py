@@ -583,3 +583,38 @@ def test_lw_noscat_fast_path_tall_columns_f32(real_pack, nlay, n_angles):
     e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
     _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
     np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(np.float32))
+
+
+def test_table_range_and_altitude_getters(real_pack):
+    """`get_p_min` / `get_t_min` / `get_t_max` (grid_adaptation.jl:24-56) report the table ranges `clip!` uses;
+    `center_z` / `face_z` (getters.jl:255-262) return what the constructor was given."""
+    from helpers import make_solver
+    st = R.synthetic.make_atmosphere(8, 16)
+    s = make_solver(real_pack, st, np.float32)
+    arrays = R.lutpack.unpack_luts(real_pack)
+    assert R.get_p_min(s) == pytest.approx(arrays["lw/params"][1], rel=1e-6)      # held in the solver's precision
+    assert R.get_t_min(s) == 160.0 and R.get_t_max(s) == 355.0
+    assert R.center_z(s) is None and R.face_z(s) is None
+    zf = np.tile(np.linspace(0.0, 3.0e4, 17), (8, 1))
+    zc = 0.5 * (zf[:, 1:] + zf[:, :-1])
+    gp = R.RRTMGPGridParams(FT=np.float32, domain_nlay=16, ncol=8)
+    s2 = R.RRTMGPSolver(gp, R.ClearSkyRadiation(), R.default_parameters(), real_pack, interpolation="BestFit",
+                        bottom_extrapolation="HydrostaticBottom", center_z=zc, face_z=zf)
+    np.testing.assert_allclose(R.center_z(s2).cpu().numpy(), zc, rtol=1e-6)
+    np.testing.assert_allclose(R.face_z(s2).cpu().numpy(), zf, rtol=1e-6)
+
+
+def test_spectral_fluxes_fast_path_tall_columns_f32(real_pack):
+    """Per-band fluxes in the 8-warp geometry (columns taller than 64 layers)."""
+    st = R.synthetic.make_atmosphere(64, 72, cld_frac=None, cos_zenith=None)
+    kw = dict(method="all_sky", aerosols=True, seed=8)
+    e = run_engine(real_pack, st, np.float32, spectral=True, **kw)
+    o = run_oracle(real_pack, st, np.float64, spectral=True, **kw)
+    o32 = run_oracle(real_pack, st, np.float32, spectral=True, **kw)
+    for k, tol in (("lw_band_up", F32_LW), ("lw_band_dn", F32_LW), ("sw_band_up", F32_SW_CLOUDY), ("sw_band_dn", F32_SW_CLOUDY)):
+        assert maxdiff(e[k], o[k]) <= max(tol, 1.5 * maxdiff(o32[k], o[k])), (k, maxdiff(e[k], o[k]))
+    np.testing.assert_allclose(e["lw_band_up"].sum(0), e["lw_up"], rtol=2e-6)
+    np.testing.assert_allclose(e["sw_band_dn"].sum(0), e["sw_dn"], rtol=2e-6, atol=1e-4)
+    plain = run_engine(real_pack, st, np.float32, **kw)
+    for k in FLUX_KEYS:
+        np.testing.assert_array_equal(e[k], plain[k], err_msg=k)
