@@ -12,12 +12,12 @@ template <typename FT> int plan_smem(int mode, SolveParams<FT>& P) {
     const int nlay = P.nlay, nlev = nlay + 1, maxb = P.lut.maxb;
     const int nv = mode == MODE_LW_2STREAM ? 4 : 5;
     P.rec_words = 4 + P.lut.nminor_max + 6;
-    P.rec_row = maxb * P.rec_words;
+    P.rec_row = maxb * P.rec_words | 1;   // odd row stride: phase 1 writes records with lane = layer (scalar accesses only here)
     int off = 0;
     P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
     P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(FT), 16);
     P.off_recj = off; off = align_up(off + nlay * maxb * (int)sizeof(int), 16);
-    P.off_rec = off;  off = align_up(off + nlay * maxb * P.rec_words * (int)sizeof(FT), 16);
+    P.off_rec = off;  off = align_up(off + nlay * P.rec_row * (int)sizeof(FT), 16);
     P.off_plk = off;  off = align_up(off + maxb * 2 * nlev * (int)sizeof(FT), 16);
     P.off_store = off; off = align_up(off + nlev * nv * 32 * (int)sizeof(FT), 128);
     P.warp_bytes = off;
