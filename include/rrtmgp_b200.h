@@ -156,6 +156,18 @@ int rrtmgp_b200_set_level_interpolation(rrtmgp_b200_handle_t* h, int32_t interpo
 
 /* prepare_atmosphere!(s) (update_fluxes.jl:252-281): level interpolation, boundary layer fill, clip!, col_dry; in place. */
 int rrtmgp_b200_prepare_atmosphere(rrtmgp_b200_handle_t* h, void* stream);
+
+/* The steps of prepare_atmosphere! one by one, for hosts that call the public functions of
+ * src/api/grid_adaptation.jl themselves; `steps` is an OR of the bits below and the selected steps run in
+ * prepare_atmosphere!'s order.  INTERPOLATE_LEVELS is a no-op unless set_level_interpolation chose a scheme, and
+ * BOUNDARY_LAYER unless the handle has an isothermal boundary layer (as in update_fluxes.jl:256-270). */
+typedef enum {
+    RRTMGP_B200_STEP_INTERPOLATE_LEVELS = 1,   /* interpolate_levels!            grid_adaptation.jl:87-113  */
+    RRTMGP_B200_STEP_BOUNDARY_LAYER = 2,       /* add_isothermal_boundary_layer! grid_adaptation.jl:135-195 */
+    RRTMGP_B200_STEP_CLIP = 4,                 /* clip!                          grid_adaptation.jl:232-258 */
+    RRTMGP_B200_STEP_CONCENTRATIONS = 8        /* update_concentrations!         grid_adaptation.jl:278-293 */
+} rrtmgp_b200_prepare_step;
+int rrtmgp_b200_prepare_steps(rrtmgp_b200_handle_t* h, uint32_t steps, void* stream);
 /* update_lw_fluxes!(s) / update_sw_fluxes!(s) / update_net_fluxes!(s) (update_fluxes.jl:12-16,74-78,165-194).
  * `have_seed == 0` mirrors `seedval = nothing`: an internal per-call counter keys the McICA draws. */
 int rrtmgp_b200_update_lw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream);

@@ -130,6 +130,14 @@ end
 prepare_atmosphere!(e::B200Engine) =
     (check(ccall((:rrtmgp_b200_prepare_atmosphere, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, CUDA.stream().handle)); nothing)
 
+# the steps of prepare_atmosphere! one by one (src/api/grid_adaptation.jl:87-113, 135-195, 232-258, 278-293)
+prepare_steps!(e::B200Engine, steps) =
+    (check(ccall((:rrtmgp_b200_prepare_steps, LIB), Cint, (Ptr{Cvoid}, UInt32, Ptr{Cvoid}), e.handle, UInt32(steps), CUDA.stream().handle)); nothing)
+interpolate_levels!(e::B200Engine) = prepare_steps!(e, 1)
+add_isothermal_boundary_layer!(e::B200Engine) = prepare_steps!(e, 2)
+clip!(e::B200Engine) = prepare_steps!(e, 4)
+update_concentrations!(e::B200Engine) = prepare_steps!(e, 8)
+
 # heating_rate(s) (src/api/standalone.jl:106-124): allocates and returns a fresh (nlay, ncol) array
 function heating_rate(e::B200Engine, s::RRTMGPSolver)
     nlay = s.grid_params.nlay - Int(s.grid_params.isothermal_boundary_layer)

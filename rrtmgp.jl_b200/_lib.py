@@ -17,6 +17,7 @@ OK, ERR_INVALID_ARG, ERR_BAD_LUT_PACK, ERR_NOT_READY, ERR_CUDA, ERR_UNSUPPORTED 
 CLEAR_SKY, ALL_SKY, ALL_SKY_WITH_CLEAR = 0, 1, 2
 TWO_STREAM, ONE_SCALAR = 0, 1
 VMR_GM, VMR_FULL = 0, 1
+STEP_INTERPOLATE_LEVELS, STEP_BOUNDARY_LAYER, STEP_CLIP, STEP_CONCENTRATIONS = 1, 2, 4, 8
 
 
 class Config(C.Structure):
@@ -53,7 +54,7 @@ BOTTOM_EXTRAPOLATIONS = {"SameAsInterpolation": 0, "UseSurfaceTempAtBottom": 1, 
 
 # every symbol include/rrtmgp_b200.h declares
 EXPORTS = ("rrtmgp_b200_create", "rrtmgp_b200_destroy", "rrtmgp_b200_load_luts", "rrtmgp_b200_lut_info",
-           "rrtmgp_b200_bind", "rrtmgp_b200_prepare_atmosphere", "rrtmgp_b200_update_lw_fluxes",
+           "rrtmgp_b200_bind", "rrtmgp_b200_prepare_atmosphere", "rrtmgp_b200_prepare_steps", "rrtmgp_b200_update_lw_fluxes",
            "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_net_fluxes", "rrtmgp_b200_update_fluxes",
            "rrtmgp_b200_update_fluxes_range",
            "rrtmgp_b200_set_level_interpolation", "rrtmgp_b200_heating_rate",
@@ -87,6 +88,7 @@ def lib():
         L.rrtmgp_b200_lut_info.argtypes = [H, C.POINTER(LutInfo)]
         L.rrtmgp_b200_bind.argtypes = [H, C.POINTER(Buffers)]
         L.rrtmgp_b200_prepare_atmosphere.argtypes = [H, C.c_void_p]
+        L.rrtmgp_b200_prepare_steps.argtypes = [H, C.c_uint32, C.c_void_p]
         for n in ("rrtmgp_b200_update_lw_fluxes", "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_fluxes"):
             getattr(L, n).argtypes = [H, C.c_uint64, C.c_int, C.c_void_p]
         L.rrtmgp_b200_update_net_fluxes.argtypes = [H, C.c_void_p]

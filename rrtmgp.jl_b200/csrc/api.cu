@@ -142,7 +142,7 @@ __global__ void heating_rate_kernel(const FT* flux_net, const FT* p_lev, FT* hr,
 // clip! (grid_adaptation.jl:232-258) + compute_col_gas_kernel! (gas_optics.jl:16-41); thread per (col, level)
 template <typename FT>
 __global__ void prepare_kernel(rrtmgp_b200_buffers_t B, long long col0, int ncol, int nlay, int ngas, int vmr_kind, int idx_h2o, FT p_min,
-                               FT t_min, FT t_max, FT grav, FT m_dry, FT m_h2o, FT avogad) {
+                               FT t_min, FT t_max, FT grav, FT m_dry, FT m_h2o, FT avogad, int do_clip, int do_col) {
     const int nlev = nlay + 1;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)ncol * nlev) return;
@@ -151,19 +151,27 @@ __global__ void prepare_kernel(rrtmgp_b200_buffers_t B, long long col0, int ncol
     const long long col = col0 + lcol;
     FT* p_lev = (FT*)B.p_lev + (size_t)col * nlev;
     FT* t_lev = (FT*)B.t_lev + (size_t)col * nlev;
-    const FT p_here = rmax(p_lev[lev], p_min);
+    // (a thread reads its own level and the one above; with do_clip both are clipped here exactly as the thread that
+    // owns the upper level will store it, so the column amount sees clipped pressures without a second pass)
+    const FT p_here = do_clip ? rmax(p_lev[lev], p_min) : p_lev[lev];
     FT p_above = FT(0);
-    if (lev < nlay) p_above = rmax(p_lev[lev + 1], p_min);
-    p_lev[lev] = p_here;
-    t_lev[lev] = rmin(rmax(t_lev[lev], t_min), t_max);
+    if (lev < nlay) p_above = do_clip ? rmax(p_lev[lev + 1], p_min) : p_lev[lev + 1];
+    if (do_clip) {
+        p_lev[lev] = p_here;
+        t_lev[lev] = rmin(rmax(t_lev[lev], t_min), t_max);
+    }
     if (lev < nlay) {
         size_t k = (size_t)col * nlay + lev;
         FT* ld = (FT*)B.layerdata + k * 4;
         FT* h2o = vmr_kind == RRTMGP_B200_VMR_GM ? (FT*)B.vmr_h2o + k : (FT*)B.vmr + k * ngas + (idx_h2o - 1);
-        FT v = rmax(*h2o, FT(0));
-        *h2o = v;
-        ld[1] = rmax(ld[1], p_min);
-        ld[2] = rmin(rmax(ld[2], t_min), t_max);
+        FT v = *h2o;
+        if (do_clip) {
+            v = rmax(v, FT(0));
+            *h2o = v;
+            ld[1] = rmax(ld[1], p_min);
+            ld[2] = rmin(rmax(ld[2], t_min), t_max);
+        }
+        if (!do_col) return;
         const FT helmert2 = FT(0.02586), m2_to_cm2 = FT(100 * 100);
         FT g0 = grav;
         if (B.lat) g0 = grav - helmert2 * rcos(FT(2) * Num<FT>::pi() * ((const FT*)B.lat)[col] / FT(180));
@@ -331,11 +339,14 @@ int solve_sw_t(rrtmgp_b200_handle* h, unsigned long long seed, bool fuse_net, lo
     return RRTMGP_B200_OK;
 }
 
-template <typename FT> int prepare_t(rrtmgp_b200_handle* h, long long c0, int count, cudaStream_t s) {
+constexpr unsigned kAllPrepareSteps = RRTMGP_B200_STEP_INTERPOLATE_LEVELS | RRTMGP_B200_STEP_BOUNDARY_LAYER |
+                                      RRTMGP_B200_STEP_CLIP | RRTMGP_B200_STEP_CONCENTRATIONS;
+
+template <typename FT> int prepare_t(rrtmgp_b200_handle* h, long long c0, int count, cudaStream_t s, unsigned steps = kAllPrepareSteps) {
     const rrtmgp_b200_config_t& c = h->cfg;
     const LutStore& L = h->luts;
     const int idx_h2o = luts_of<FT>(h).lw.idx_h2o;
-    if (h->interpolation != RRTMGP_B200_NO_INTERPOLATION) {   // update_fluxes.jl:256-264
+    if ((steps & RRTMGP_B200_STEP_INTERPOLATE_LEVELS) && h->interpolation != RRTMGP_B200_NO_INTERPOLATION) {   // update_fluxes.jl:256-264
         const int nlay_dom = c.nlay - (c.isothermal_boundary_layer ? 1 : 0);
         const long long nf = (long long)count * (nlay_dom + 1);
         interpolate_levels_kernel<FT><<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(
@@ -343,16 +354,19 @@ template <typename FT> int prepare_t(rrtmgp_b200_handle* h, long long c0, int co
             (const FT*)h->face_z, (FT)c.grav, (FT)h->cp_d, (FT)h->r_d);
         ++h->last_launches;
     }
-    if (c.isothermal_boundary_layer) {
+    if ((steps & RRTMGP_B200_STEP_BOUNDARY_LAYER) && c.isothermal_boundary_layer) {
         boundary_layer_kernel<FT><<<(count + 127) / 128, 128, 0, s>>>(h->buf, c0, count, c.nlay, c.ngas, c.vmr_kind, (FT)L.p_ref_min);
         ++h->last_launches;
     }
-    const long long n = (long long)count * (c.nlay + 1);
-    prepare_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->buf, c0, count, c.nlay, c.ngas, c.vmr_kind, idx_h2o,
-                                                                  luts_of<FT>(h).lw.p_ref_min, luts_of<FT>(h).lw.t_ref_min,
-                                                                  luts_of<FT>(h).lw.t_ref_max, (FT)c.grav, (FT)c.molmass_dryair,
-                                                                  (FT)c.molmass_water, (FT)c.avogad);
-    ++h->last_launches;
+    const int do_clip = (steps & RRTMGP_B200_STEP_CLIP) ? 1 : 0, do_col = (steps & RRTMGP_B200_STEP_CONCENTRATIONS) ? 1 : 0;
+    if (do_clip || do_col) {
+        const long long n = (long long)count * (c.nlay + 1);
+        prepare_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->buf, c0, count, c.nlay, c.ngas, c.vmr_kind, idx_h2o,
+                                                                      luts_of<FT>(h).lw.p_ref_min, luts_of<FT>(h).lw.t_ref_min,
+                                                                      luts_of<FT>(h).lw.t_ref_max, (FT)c.grav, (FT)c.molmass_dryair,
+                                                                      (FT)c.molmass_water, (FT)c.avogad, do_clip, do_col);
+        ++h->last_launches;
+    }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RRTMGP_B200_OK : fail_cuda(h, e);
 }
@@ -506,6 +520,16 @@ int rrtmgp_b200_prepare_atmosphere(rrtmgp_b200_handle_t* h, void* stream) {
     DeviceGuard g(h->cfg.device);
     h->last_launches = 0;
     return h->cfg.dtype == 1 ? prepare_t<double>(h, 0, h->cfg.ncol, (cudaStream_t)stream) : prepare_t<float>(h, 0, h->cfg.ncol, (cudaStream_t)stream);
+}
+
+int rrtmgp_b200_prepare_steps(rrtmgp_b200_handle_t* h, uint32_t steps, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    if (steps == 0 || (steps & ~kAllPrepareSteps)) return RRTMGP_B200_ERR_INVALID_ARG;
+    DeviceGuard g(h->cfg.device);
+    h->last_launches = 0;
+    return h->cfg.dtype == 1 ? prepare_t<double>(h, 0, h->cfg.ncol, (cudaStream_t)stream, steps)
+                             : prepare_t<float>(h, 0, h->cfg.ncol, (cudaStream_t)stream, steps);
 }
 
 int rrtmgp_b200_update_lw_fluxes(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {

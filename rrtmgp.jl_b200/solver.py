@@ -380,6 +380,27 @@ def prepare_atmosphere(s: RRTMGPSolver) -> None:
     check(lib().rrtmgp_b200_prepare_atmosphere(s._h, s._stream()), s._h)
 
 
+# the steps of prepare_atmosphere! as the public functions of src/api/grid_adaptation.jl
+def interpolate_levels(s: RRTMGPSolver) -> None:
+    """`interpolate_levels!` (grid_adaptation.jl:87-113); a no-op with `NoInterpolation`."""
+    check(lib().rrtmgp_b200_prepare_steps(s._h, _lib.STEP_INTERPOLATE_LEVELS, s._stream()), s._h)
+
+
+def add_isothermal_boundary_layer(s: RRTMGPSolver) -> None:
+    """`add_isothermal_boundary_layer!` (grid_adaptation.jl:135-195); a no-op without the extra layer."""
+    check(lib().rrtmgp_b200_prepare_steps(s._h, _lib.STEP_BOUNDARY_LAYER, s._stream()), s._h)
+
+
+def clip(s: RRTMGPSolver) -> None:
+    """`clip!` (grid_adaptation.jl:232-258): state into the lookup-table ranges, in place."""
+    check(lib().rrtmgp_b200_prepare_steps(s._h, _lib.STEP_CLIP, s._stream()), s._h)
+
+
+def update_concentrations(s: RRTMGPSolver) -> None:
+    """`update_concentrations!` (grid_adaptation.jl:278-293): dry-air column amounts from `p_lev` and `vmr_h2o`."""
+    check(lib().rrtmgp_b200_prepare_steps(s._h, _lib.STEP_CONCENTRATIONS, s._stream()), s._h)
+
+
 def update_lw_fluxes(s: RRTMGPSolver, seedval=None) -> None:
     seed, have = _seed_args(s, seedval)
     check(lib().rrtmgp_b200_update_lw_fluxes(s._h, seed, have, s._stream()), s._h)

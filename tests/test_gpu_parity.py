@@ -618,3 +618,32 @@ def test_spectral_fluxes_fast_path_tall_columns_f32(real_pack):
     plain = run_engine(real_pack, st, np.float32, **kw)
     for k in FLUX_KEYS:
         np.testing.assert_array_equal(e[k], plain[k], err_msg=k)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_prepare_steps_one_by_one_equal_prepare_atmosphere(real_pack, dtype):
+    """`interpolate_levels!`, `add_isothermal_boundary_layer!`, `clip!`, `update_concentrations!` called one by one
+    (grid_adaptation.jl) leave exactly the state one `prepare_atmosphere!` leaves (update_fluxes.jl:252-281), and
+    `clip!` alone does not touch the column amounts."""
+    from helpers import make_solver
+    st = R.synthetic.make_atmosphere(48, 33, dtype=dtype, with_lat=True)
+    st["layerdata"][:, 3:6, 2] = 120.0          # out-of-range temperatures and pressures for clip!
+    st["p_lev"][:, -1] = 0.2
+    st["layerdata"][:, -1, 1] = 0.3
+    a = make_solver(real_pack, st, dtype, isothermal_boundary_layer=True)
+    b = make_solver(real_pack, st, dtype, isothermal_boundary_layer=True)
+    R.prepare_atmosphere(a)
+    col_dry_before = b.buffers["layerdata"][:, :, 0].clone()
+    R.interpolate_levels(b)
+    R.add_isothermal_boundary_layer(b)
+    R.clip(b)
+    assert bool((b.buffers["layerdata"][:, :-1, 0] == col_dry_before[:, :-1]).all())     # clip! leaves col_dry alone
+    assert float(b.buffers["layerdata"][:, :, 2].min()) >= R.get_t_min(b) and float(b.buffers["p_lev"].min()) >= R.get_p_min(b) * (1 - 1e-6)
+    R.update_concentrations(b)
+    import torch
+    for k in ("layerdata", "p_lev", "t_lev", "vmr_h2o"):
+        assert torch.equal(a.buffers[k], b.buffers[k]), k
+    with pytest.raises(R.RRTMGPB200Error):
+        R._lib.check(R._lib.lib().rrtmgp_b200_prepare_steps(b._h, 0, None))
+    with pytest.raises(R.RRTMGPB200Error):
+        R._lib.check(R._lib.lib().rrtmgp_b200_prepare_steps(b._h, 16, None))
