@@ -192,6 +192,28 @@ int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream)
 int rrtmgp_b200_heating_rate(rrtmgp_b200_handle_t* h, const void* flux_net, void* heating_rate, double cp_d, void* stream);
 
 /* Diagnostics: kernels launched by the last update_* call; last CUDA error string. */
+/* validate_inputs(s) (src/api/validation.jl:56-74; opt-in through `check_values[]`, :14): every bound input
+ * against its physical range -- pressures / temperatures positive and finite, cos_zenith in [-1, 1], TOA flux
+ * >= 0, emissivity and albedos in [0, 1], mixing ratios >= 0.  `*failed` receives an OR of the bits below
+ * (0 = all good).  Unlike every other entry point this one SYNCHRONISES `stream` (it returns a host value), as
+ * the reference's reduction does. */
+typedef enum {
+    RRTMGP_B200_BAD_LEVEL_PRESSURE = 1 << 0,
+    RRTMGP_B200_BAD_LEVEL_TEMPERATURE = 1 << 1,
+    RRTMGP_B200_BAD_LAYER_PRESSURE = 1 << 2,
+    RRTMGP_B200_BAD_LAYER_TEMPERATURE = 1 << 3,
+    RRTMGP_B200_BAD_SURFACE_TEMPERATURE = 1 << 4,
+    RRTMGP_B200_BAD_COS_ZENITH = 1 << 5,
+    RRTMGP_B200_BAD_TOA_SW_FLUX_DN = 1 << 6,
+    RRTMGP_B200_BAD_SURFACE_EMISSIVITY = 1 << 7,
+    RRTMGP_B200_BAD_DIRECT_SW_SURFACE_ALBEDO = 1 << 8,
+    RRTMGP_B200_BAD_DIFFUSE_SW_SURFACE_ALBEDO = 1 << 9,
+    RRTMGP_B200_BAD_VMR_H2O = 1 << 10,
+    RRTMGP_B200_BAD_VMR_O3 = 1 << 11,
+    RRTMGP_B200_BAD_VMR = 1 << 12
+} rrtmgp_b200_invalid_input;
+int rrtmgp_b200_validate_inputs(rrtmgp_b200_handle_t* h, uint32_t* failed, void* stream);
+
 int rrtmgp_b200_last_launch_count(const rrtmgp_b200_handle_t* h);
 const char* rrtmgp_b200_last_cuda_error(const rrtmgp_b200_handle_t* h);
 const char* rrtmgp_b200_strerror(int status);

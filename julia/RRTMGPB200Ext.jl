@@ -138,6 +138,19 @@ add_isothermal_boundary_layer!(e::B200Engine) = prepare_steps!(e, 2)
 clip!(e::B200Engine) = prepare_steps!(e, 4)
 update_concentrations!(e::B200Engine) = prepare_steps!(e, 8)
 
+# validate_inputs(s) (src/api/validation.jl:56-74); synchronises the stream (it returns a host value)
+const INVALID_INPUT_NAMES = (:level_pressure, :level_temperature, :layer_pressure, :layer_temperature, :surface_temperature,
+                             :cos_zenith, :toa_sw_flux_dn, :surface_emissivity, :direct_sw_surface_albedo,
+                             :diffuse_sw_surface_albedo, :vmr_h2o, :vmr_o3, :vmr)
+function validate_inputs(e::B200Engine)
+    failed = Ref{UInt32}(0)
+    check(ccall((:rrtmgp_b200_validate_inputs, LIB), Cint, (Ptr{Cvoid}, Ref{UInt32}, Ptr{Cvoid}), e.handle, failed, CUDA.stream().handle))
+    for (bit, name) in enumerate(INVALID_INPUT_NAMES)
+        (failed[] >> (bit - 1)) & 1 == 1 && error("RRTMGP input validation failed: `$name` contains values outside its physical range (or non-finite values).")
+    end
+    return nothing
+end
+
 # heating_rate(s) (src/api/standalone.jl:106-124): allocates and returns a fresh (nlay, ncol) array
 function heating_rate(e::B200Engine, s::RRTMGPSolver)
     nlay = s.grid_params.nlay - Int(s.grid_params.isothermal_boundary_layer)

@@ -18,6 +18,10 @@ CLEAR_SKY, ALL_SKY, ALL_SKY_WITH_CLEAR = 0, 1, 2
 TWO_STREAM, ONE_SCALAR = 0, 1
 VMR_GM, VMR_FULL = 0, 1
 STEP_INTERPOLATE_LEVELS, STEP_BOUNDARY_LAYER, STEP_CLIP, STEP_CONCENTRATIONS = 1, 2, 4, 8
+# bits of rrtmgp_b200_validate_inputs, named by the getter to inspect (src/api/validation.jl:56-74)
+INVALID_INPUT_NAMES = ("level_pressure", "level_temperature", "layer_pressure", "layer_temperature", "surface_temperature",
+                       "cos_zenith", "toa_sw_flux_dn", "surface_emissivity", "direct_sw_surface_albedo",
+                       "diffuse_sw_surface_albedo", "vmr_h2o", "vmr_o3", "vmr")
 
 
 class Config(C.Structure):
@@ -58,7 +62,7 @@ EXPORTS = ("rrtmgp_b200_create", "rrtmgp_b200_destroy", "rrtmgp_b200_load_luts",
            "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_net_fluxes", "rrtmgp_b200_update_fluxes",
            "rrtmgp_b200_update_fluxes_range",
            "rrtmgp_b200_set_level_interpolation", "rrtmgp_b200_heating_rate",
-           "rrtmgp_b200_compute_relative_humidity", "rrtmgp_b200_last_launch_count",
+           "rrtmgp_b200_compute_relative_humidity", "rrtmgp_b200_validate_inputs", "rrtmgp_b200_last_launch_count",
            "rrtmgp_b200_last_cuda_error", "rrtmgp_b200_strerror", "rrtmgp_b200_abi_version")
 
 
@@ -89,6 +93,7 @@ def lib():
         L.rrtmgp_b200_bind.argtypes = [H, C.POINTER(Buffers)]
         L.rrtmgp_b200_prepare_atmosphere.argtypes = [H, C.c_void_p]
         L.rrtmgp_b200_prepare_steps.argtypes = [H, C.c_uint32, C.c_void_p]
+        L.rrtmgp_b200_validate_inputs.argtypes = [H, C.POINTER(C.c_uint32), C.c_void_p]
         for n in ("rrtmgp_b200_update_lw_fluxes", "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_fluxes"):
             getattr(L, n).argtypes = [H, C.c_uint64, C.c_int, C.c_void_p]
         L.rrtmgp_b200_update_net_fluxes.argtypes = [H, C.c_void_p]

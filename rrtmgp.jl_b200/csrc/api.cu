@@ -196,6 +196,27 @@ __global__ void rel_hum_kernel(rrtmgp_b200_buffers_t B, int ncol, int nlay, int 
     ld[3] = rmax(FT(0.01) * (FT(0.263) * ld[1] * q_tmp) / es, FT(0));
 }
 
+// validate_inputs (validation.jl:28-37, 56-74): mode 0 = positive and finite, 1 = non-negative and finite,
+// 2 = in [0, 1], 3 = in [-1, 1]; element i of the array is x[(i / inner) * stride + offset + i % inner]
+template <typename FT>
+__global__ void validate_kernel(const FT* x, long long n, int inner, long long stride, long long offset, int mode, unsigned bit, unsigned* mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < n) {
+        const FT v = x[(i / inner) * stride + offset + i % inner];
+        const bool finite = v == v && v - v == FT(0);
+        bool ok;
+        switch (mode) {
+            case 0: ok = finite && v > FT(0); break;
+            case 1: ok = finite && v >= FT(0); break;
+            case 2: ok = finite && v >= FT(0) && v <= FT(1); break;
+            default: ok = finite && v >= FT(-1) && v <= FT(1); break;
+        }
+        bad = !ok;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(mask, bit);
+}
+
 // transpose_sum_into! without the transpose (Fluxes.jl:423-435)
 template <typename FT> __global__ void add_kernel(const FT* a, const FT* b, FT* out, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,7 +283,7 @@ void base_params(const rrtmgp_b200_handle* h, SolveParams<FT>& P, bool sw, bool 
     P.n_mu = c.op_lw == RRTMGP_B200_ONE_SCALAR ? c.n_gauss_angles : 1;
     P.col_offset = c.col_offset + c0;
     P.seed = seed;
-    P.work_counter = h->work_counters ? h->work_counters + (h->work_seq++ & 255u) : nullptr;
+    P.work_counter = h->work_counters ? h->work_counters + (h->work_seq++ % 255u) : nullptr;   // slot 255: validate_inputs
     gauss_angles<FT>(P.n_mu, P.Ds, P.wts);
 }
 
@@ -401,6 +422,46 @@ struct DeviceGuard {
 };
 
 }  // namespace
+
+template <typename FT> static int validate_t(rrtmgp_b200_handle* h, uint32_t* failed, cudaStream_t s) {
+    const rrtmgp_b200_config_t& c = h->cfg;
+    const rrtmgp_b200_buffers_t& B = h->buf;
+    unsigned* mask = h->work_counters + 255;   // the last slot of the counter ring is never handed to a kernel launch
+    if (h->work_counters == nullptr) return RRTMGP_B200_ERR_NOT_READY;
+    cudaError_t e = cudaMemsetAsync(mask, 0, sizeof(unsigned), s);
+    if (e != cudaSuccess) return fail_cuda(h, e);
+    h->last_launches = 0;
+    auto run = [&](const void* p, long long n, int inner, long long stride, long long offset, int mode, unsigned bit) {
+        if (p == nullptr || n <= 0) return;   // `_check(f, ::Nothing, name) = true`
+        validate_kernel<FT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const FT*)p, n, inner, stride, offset, mode, bit, mask);
+        ++h->last_launches;
+    };
+    const long long ncol = c.ncol, nlay = c.nlay, nlev = c.nlay + 1;
+    const int nb_lw = h->luts.n_bnd_lw, nb_sw = h->luts.n_bnd_sw;
+    run(B.p_lev, ncol * nlev, 1, 1, 0, 0, RRTMGP_B200_BAD_LEVEL_PRESSURE);
+    run(B.t_lev, ncol * nlev, 1, 1, 0, 0, RRTMGP_B200_BAD_LEVEL_TEMPERATURE);
+    run(B.layerdata, ncol * nlay, 1, 4, 1, 0, RRTMGP_B200_BAD_LAYER_PRESSURE);        // layerdata[..][1] = p_lay
+    run(B.layerdata, ncol * nlay, 1, 4, 2, 0, RRTMGP_B200_BAD_LAYER_TEMPERATURE);     // layerdata[..][2] = t_lay
+    run(B.t_sfc, ncol, 1, 1, 0, 0, RRTMGP_B200_BAD_SURFACE_TEMPERATURE);
+    run(B.cos_zenith, ncol, 1, 1, 0, 3, RRTMGP_B200_BAD_COS_ZENITH);
+    run(B.toa_flux, ncol, 1, 1, 0, 1, RRTMGP_B200_BAD_TOA_SW_FLUX_DN);
+    run(B.sfc_emis, ncol * nb_lw, 1, 1, 0, 2, RRTMGP_B200_BAD_SURFACE_EMISSIVITY);
+    run(B.sfc_alb_direct, ncol * nb_sw, 1, 1, 0, 2, RRTMGP_B200_BAD_DIRECT_SW_SURFACE_ALBEDO);
+    run(B.sfc_alb_diffuse, ncol * nb_sw, 1, 1, 0, 2, RRTMGP_B200_BAD_DIFFUSE_SW_SURFACE_ALBEDO);
+    if (c.vmr_kind == RRTMGP_B200_VMR_GM) {   // _check_vmr (validation.jl:39-45)
+        run(B.vmr_h2o, ncol * nlay, 1, 1, 0, 1, RRTMGP_B200_BAD_VMR_H2O);
+        run(B.vmr_o3, ncol * nlay, 1, 1, 0, 1, RRTMGP_B200_BAD_VMR_O3);
+        run(B.vmr, c.ngas, 1, 1, 0, 1, RRTMGP_B200_BAD_VMR);
+    } else {
+        run(B.vmr, ncol * nlay * c.ngas, 1, 1, 0, 1, RRTMGP_B200_BAD_VMR);
+    }
+    unsigned host = 0;
+    e = cudaMemcpyAsync(&host, mask, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail_cuda(h, e);
+    *failed = host;
+    return RRTMGP_B200_OK;
+}
 
 extern "C" {
 
@@ -645,6 +706,14 @@ int rrtmgp_b200_compute_relative_humidity(rrtmgp_b200_handle_t* h, void* stream)
                                                                       (float)c.molmass_water / (float)c.molmass_dryair);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RRTMGP_B200_OK : fail_cuda(h, e);
+}
+
+int rrtmgp_b200_validate_inputs(rrtmgp_b200_handle_t* h, uint32_t* failed, void* stream) {
+    if (failed == nullptr) return RRTMGP_B200_ERR_INVALID_ARG;
+    int st = ready(h);
+    if (st) return st;
+    DeviceGuard g(h->cfg.device);
+    return h->cfg.dtype == 1 ? validate_t<double>(h, failed, (cudaStream_t)stream) : validate_t<float>(h, failed, (cudaStream_t)stream);
 }
 
 int rrtmgp_b200_last_launch_count(const rrtmgp_b200_handle_t* h) { return h ? h->last_launches : 0; }

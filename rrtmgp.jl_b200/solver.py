@@ -284,6 +284,8 @@ def _seed_args(s: RRTMGPSolver, seedval):
 
 def update_fluxes(s: RRTMGPSolver, seedval=None) -> None:
     """`update_fluxes!(s, seedval)` (update_fluxes.jl:223-233): async on the current CUDA stream."""
+    if check_values.value:   # update_fluxes.jl:224
+        validate_inputs(s)
     seed, have = _seed_args(s, seedval)
     check(lib().rrtmgp_b200_update_fluxes(s._h, seed, have, s._stream()), s._h)
 
@@ -378,6 +380,25 @@ class HostPipeline:
 
 def prepare_atmosphere(s: RRTMGPSolver) -> None:
     check(lib().rrtmgp_b200_prepare_atmosphere(s._h, s._stream()), s._h)
+
+
+class _Toggle:
+    """`RRTMGP.check_values[]` (src/api/validation.jl:14): `check_values.value = True` makes `update_fluxes` call
+    `validate_inputs` before each solve.  Off by default; the check synchronises the stream."""
+    value = False
+
+
+check_values = _Toggle()
+
+
+def validate_inputs(s: RRTMGPSolver) -> None:
+    """`validate_inputs(s)` (src/api/validation.jl:56-74): raises on the first input outside its physical range."""
+    failed = C.c_uint32(0)
+    check(lib().rrtmgp_b200_validate_inputs(s._h, C.byref(failed), s._stream()), s._h)
+    for bit, name in enumerate(_lib.INVALID_INPUT_NAMES):
+        if failed.value & (1 << bit):
+            raise ValueError(f"RRTMGP input validation failed: `{name}` contains values outside its physical range "
+                             "(or non-finite values). Inspect the corresponding getter on the solver.")
 
 
 # the steps of prepare_atmosphere! as the public functions of src/api/grid_adaptation.jl

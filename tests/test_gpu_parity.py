@@ -647,3 +647,34 @@ def test_prepare_steps_one_by_one_equal_prepare_atmosphere(real_pack, dtype):
         R._lib.check(R._lib.lib().rrtmgp_b200_prepare_steps(b._h, 0, None))
     with pytest.raises(R.RRTMGPB200Error):
         R._lib.check(R._lib.lib().rrtmgp_b200_prepare_steps(b._h, 16, None))
+
+
+def test_validate_inputs_names_the_offending_getter(real_pack):
+    """`validate_inputs(s)` (src/api/validation.jl:56-74) and the `check_values` toggle (:14; update_fluxes.jl:224)."""
+    import torch
+    from helpers import make_solver
+    st = R.synthetic.make_atmosphere(40, 16)
+    s = make_solver(real_pack, st, np.float32)
+    R.validate_inputs(s)                                   # a sane state passes
+    cases = [("cos_zenith", "cos_zenith", 1.5), ("toa_flux", "toa_sw_flux_dn", -1.0), ("sfc_emis", "surface_emissivity", 1.2),
+             ("sfc_alb_direct", "direct_sw_surface_albedo", -0.1), ("t_lev", "level_temperature", float("nan")),
+             ("p_lev", "level_pressure", 0.0), ("t_sfc", "surface_temperature", float("inf")), ("vmr_o3", "vmr_o3", -1e-9)]
+    for key, name, bad in cases:
+        keep = s.buffers[key].clone()
+        s.buffers[key].view(-1)[-1] = bad                  # the very last element: every block is inspected
+        with pytest.raises(ValueError, match=f"`{name}`"):
+            R.validate_inputs(s)
+        s.buffers[key].copy_(keep)
+    keep = s.buffers["layerdata"].clone()
+    s.buffers["layerdata"][3, 5, 2] = -5.0                 # t_lay lives in layerdata[..., 2]
+    with pytest.raises(ValueError, match="`layer_temperature`"):
+        R.validate_inputs(s)
+    R.check_values.value = True
+    try:
+        with pytest.raises(ValueError, match="`layer_temperature`"):
+            R.update_fluxes(s, 1)
+    finally:
+        R.check_values.value = False
+    s.buffers["layerdata"].copy_(keep)
+    R.update_fluxes(s, 1)
+    torch.cuda.synchronize()
