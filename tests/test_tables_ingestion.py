@@ -176,3 +176,73 @@ def test_clear_sky_pack_and_ln_p_ref_run_through_the_oracle(artifact_dir, small_
     b = Oracle(R.lutpack.pack_luts(arrays), np.float64).update_fluxes(st, method="clear_sky", aerosols=False)
     for k in ("lw_up", "lw_dn", "sw_up", "sw_dn", "net"):
         np.testing.assert_allclose(a[k], b[k], rtol=1e-11, atol=1e-11, err_msg=k)
+
+
+# ---- the contributor reorder against a loop-for-loop restatement on random band layouts -------------------------
+def _reorder_by_the_book(n_bnd, bnd_lims_gpt, lims):
+    """`lookup_constructors.jl:218-297` restated index for index with 1-based arrays (slot 0 unused), kept apart
+    from the vectorised `tables._minor` so the two can disagree."""
+    n_gpt = int(bnd_lims_gpt[1][-1])
+    n_int = len(lims[0])
+    gpt2bnd = [0] * (n_gpt + 1)
+    for i in range(1, n_bnd + 1):
+        for g in range(bnd_lims_gpt[0][i - 1], bnd_lims_gpt[1][i - 1] + 1):
+            gpt2bnd[g] = i
+    bnd = [0] * (n_int + 1)
+    sh = [0] * (n_int + 1)
+    for i in range(1, n_int + 1):
+        bnd[i] = gpt2bnd[lims[0][i - 1]]
+        if i > 1:
+            sh[i] = sh[i - 1] + lims[1][i - 2] - lims[0][i - 2] + 1
+    bnd_st = [0] * (n_bnd + 2)
+    bnd_st[1] = 1
+    for ib in range(2, n_bnd + 2):
+        loc = None
+        for i in range(1, n_int + 1):
+            if bnd[i] == ib - 1:
+                loc = i                      # findlast
+        bnd_st[ib] = bnd_st[ib - 1] if loc is None else loc + 1
+    gpt_st = [1] * (n_gpt + 2)
+    reorder = []
+    for ib in range(1, n_bnd + 1):
+        n = bnd_st[ib + 1] - bnd_st[ib]
+        for loc_in_bnd, igpt in enumerate(range(bnd_lims_gpt[0][ib - 1], bnd_lims_gpt[1][ib - 1] + 1), start=1):
+            gpt_st[igpt + 1] = gpt_st[igpt] + n
+            for i in range(bnd_st[ib], bnd_st[ib + 1]):
+                reorder.append(sh[i] + loc_in_bnd)
+    return bnd_st[1:], gpt_st[1:], reorder
+
+
+def test_minor_reorder_matches_the_loops_on_random_layouts():
+    from hypothesis import given, settings, strategies as hs
+
+    @settings(max_examples=60, deadline=None)
+    @given(hs.lists(hs.integers(1, 6), min_size=1, max_size=7), hs.data())
+    def run(gpts, data):
+        n_bnd = len(gpts)
+        hi = np.cumsum(gpts)
+        lo = hi - np.array(gpts) + 1
+        counts = [data.draw(hs.integers(0, 3)) for _ in range(n_bnd)]      # intervals per band, bands may have none
+        lims = [[], []]
+        for b in range(n_bnd):
+            for _ in range(counts[b]):
+                lims[0].append(int(lo[b])); lims[1].append(int(hi[b]))
+        n_int = len(lims[0])
+        n_contrib = int(sum(c * g for c, g in zip(counts, gpts)))
+        if n_int == 0:
+            return
+        chars = lambda names: np.array([list(n.ljust(8)) for n in names], dtype="S1")
+        k = np.arange(1, n_contrib + 1, dtype=np.float64)[None, None, :] * np.ones((2, 3, 1))   # file order (T, eta, contrib)
+        ds = T.Dataset({"contributors_lower": n_contrib},
+                       {"minor_gases_lower": chars(["co2"] * n_int), "scaling_gas_lower": chars([""] * n_int),
+                        "minor_limits_gpt_lower": np.array(lims, dtype=np.int32).T.copy(),
+                        "kminor_lower": k, "minor_scales_with_density_lower": np.zeros(n_int, np.int32),
+                        "scale_by_complement_lower": np.zeros(n_int, np.int32)})
+        gpt2bnd = np.concatenate([[b + 1] * g for b, g in enumerate(gpts)])
+        m = T._minor(ds, "lower", {"co2": 2}, gpt2bnd, np.array([lo, hi]))
+        bnd_st, gpt_st, reorder = _reorder_by_the_book(n_bnd, [lo.tolist(), hi.tolist()], lims)
+        np.testing.assert_array_equal(m["bnd_st"], bnd_st)
+        np.testing.assert_array_equal(m["gpt_st"], gpt_st)
+        np.testing.assert_array_equal(m["kminor"][0, 0], reorder)      # slice c carries the value c
+
+    run()
