@@ -1,5 +1,5 @@
-// Blackwell-native fast path of the two-stream kernels: Float32, nlay <= 95, real-table shape
-// (n_eta = 9, n_T = 14, 16-g-point bands, n_gpt and the number of minor-slot groups template constants).
+// Blackwell-native fast path of the two-stream kernels and of the no-scattering longwave kernel: Float32, nlay <= 95,
+// real-table shape (n_eta = 9, n_T = 14, 16-g-point bands, n_gpt and the number of minor-slot groups template constants).
 //
 //  * PERSISTENT: one CTA of 12 warps per SM (8 for columns taller than 64 layers, FastGeom); warp = column,
 //    lane = g-point (as in solver.cuh).  Columns come
@@ -26,6 +26,11 @@
 //    source-independent two-stream coefficients of layer k-1, then interpolates layer k and closes layer k-1;
 //    record rebuilds and g-point reductions sit between tiles of <= 16 iterations, nothing branches inside.
 //  * G-POINT REDUCTION through a shared staging tile read transposed (lane = level) with 128-bit loads.
+//  * SECOND SWEEPS read the level store 8 levels at a time (one tcgen05.ld.x16 for the (A, B) pairs, one .x8 or eight
+//    LDS for the albedos) instead of a TMEM round trip per level.
+//  * BAND-RECORD ROWS are 4 * odd words (solver_launch.cuh): phase 1 writes them with lane = layer, 128-bit stores.
+//  * NO-SCATTERING LW (MODE_LW_NOSCAT, 1-4 Gauss angles): marched from the top, the down sweep of every angle in the
+//    pass that does the gas optics; (tau, B_lay pfrac, top-level source) per layer in the level store for the up sweep.
 //  * SW adding marched from the TOP (reflectance/source of everything ABOVE a level),
 //    algebraically identical to shortwave_2stream.jl:300-392, so the direct beam, the layer
 //    coefficients and the first recurrence share one sweep; see DESIGN.md.
