@@ -32,12 +32,20 @@ sys.path.insert(0, ROOT)
 METRIC = "columns/sec for all-sky update_fluxes! (ncol=1e5, nlay=64) at 1/2/4/8 B200"
 PARAMS = dict(grav=9.80665, molmass_dryair=0.028964, molmass_water=0.018016)
 ALGO_FLOPS_PER_COL = 6.8e6      # SURVEY.md §8d (+-30 %)
-FP32_PEAK_TFLOPS = 74.4         # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
+FP32_NOMINAL_TFLOPS = 74.4      # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal) -- reported, not used as the peak
 
 
 def workload_name(ncol, nlay):
     return (f"all_sky_with_aerosols: ncol={ncol}/GPU nlay={nlay} Float32, 256 LW + 224 SW g-points, two-stream LW+SW, "
             "cld_frac=1 (McICA), 15-species aerosols, cos_zenith=0.86, synthetic LUT pack seed 7")
+
+
+def config_of(ncol, nlay, world):
+    """The `config` object of both arms (engine and `--impl reference`): same keys, same workload string."""
+    in_bytes = ncol * ((nlay * 4 + nlay * 2 + nlay * 5 + 2 * nlay * 15) * 4 + 400)
+    return {"workload": workload_name(ncol, nlay), "global_columns": world * ncol,
+            "parallelism": f"column shards x{world}" + (", NCCL all-gather of 8 flux views" if world > 1 else ""),
+            "l2_policy": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"}
 
 
 def peaks():
@@ -167,7 +175,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "columns/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.ncol, args.nlay)},
+            "config": config_of(args.ncol, args.nlay, max(world, 1)),
             "cpu_baseline": {"value": v, "unit": "columns/s", "cores": cores, "kind": "port",
                              "sample": f"{ncol_s} of {args.ncol} columns per step (cost is linear in ncol); "
                                        "C++ restatement of the Julia reference, OpenMP over columns"},
@@ -293,9 +301,17 @@ def main():
                 "note": "fused path is FP32/LUT-gather bound by construction (SURVEY.md §8d): the HBM fraction is "
                         "<< 1; see roofline_fp32"}
     cols_per_s_gpu = ncol / ((ms_prep + ms_lw + ms_sw) * 1e-3)
-    roofline_fp32 = {"bound": "fp32", "achieved": cols_per_s_gpu * ALGO_FLOPS_PER_COL / 1e12, "peak": FP32_PEAK_TFLOPS,
-                     "unit": "TFLOP/s", "frac": cols_per_s_gpu * ALGO_FLOPS_PER_COL / 1e12 / FP32_PEAK_TFLOPS,
-                     "peak_source": "nominal 148 SM x 128 x 2 x 1.965 GHz", "algorithmic_flops_per_column": ALGO_FLOPS_PER_COL}
+    # FP32 peak MEASURED in this run (rrtmgp_b200_measure_fp32_peak: independent scalar FFMA / packed FFMA2 streams on
+    # every SM); the fused kernels are scalar FP32, so the scalar-FFMA figure is the denominator
+    import ctypes
+    ffma, ffma2 = ctypes.c_double(0), ctypes.c_double(0)
+    R._lib.check(R._lib.lib().rrtmgp_b200_measure_fp32_peak(local_rank, ctypes.byref(ffma), ctypes.byref(ffma2)))
+    fp32_achieved = cols_per_s_gpu * ALGO_FLOPS_PER_COL / 1e12
+    roofline_fp32 = {"bound": "fp32", "achieved": fp32_achieved, "peak": ffma.value, "unit": "TFLOP/s",
+                     "frac": fp32_achieved / ffma.value,
+                     "peak_source": "measured in this run: scalar FFMA stream, 16 warps/SM (rrtmgp_b200_measure_fp32_peak)",
+                     "peak_ffma2": ffma2.value, "frac_of_ffma2_peak": fp32_achieved / ffma2.value,
+                     "peak_nominal": FP32_NOMINAL_TFLOPS, "algorithmic_flops_per_column": ALGO_FLOPS_PER_COL}
 
     # The two limits that actually bind: warp-instruction issue (4 schedulers x 1 instr/clk per SM) and
     # the L1 data pipe (one 128-byte wavefront/clk per SM, shared + global).  Counts per launch are properties of
@@ -347,8 +363,8 @@ def main():
         for name, key, arr in (("cos_zenith~U(-0.2,1)", "cos_zenith", rng.uniform(-0.2, 1.0, ncol)),
                                ("cld_frac~U(0,1)", "cld_frac", np.where(base_cf.cpu().numpy() > 0, rng.uniform(0.0, 1.0, (ncol, nlay)), 0.0))):
             s.buffers[key].copy_(torch.as_tensor(arr.astype(np.float32)))
-            ms = time_call(lambda i: R.update_fluxes(s, 300 + i), 3)
-            variants[name] = {"value": ncol / (ms * 1e-3), "unit": "columns/s", "ms_per_step": ms}
+            ms_v = time_call(lambda i: R.update_fluxes(s, 300 + i), 3)
+            variants[name] = {"value": ncol / (ms_v * 1e-3), "unit": "columns/s", "ms_per_step": ms_v}
             s.buffers["cos_zenith"].copy_(base_cz); s.buffers["cld_frac"].copy_(base_cf)
 
     cpu_baseline = None
@@ -370,9 +386,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(ncol, nlay), "global_columns": world * ncol,
-                           "parallelism": f"column shards x{world}" + (", NCCL all-gather of 8 flux views" if world > 1 else ""),
-                           "l2_policy": f"inputs {ncol * (in_common + 400) / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
+                "config": config_of(ncol, nlay, world),
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_fp32": roofline_fp32, "roofline_issue": roofline_issue, "cpu_baseline": cpu_baseline,
                 "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants}

@@ -214,6 +214,11 @@ typedef enum {
 } rrtmgp_b200_invalid_input;
 int rrtmgp_b200_validate_inputs(rrtmgp_b200_handle_t* h, uint32_t* failed, void* stream);
 
+/* Measurement aid (no reference counterpart): FP32 CUDA-core peak of `device` from a stream of
+ * independent scalar FFMA and of packed FFMA2, in TFLOP/s -- the denominator bench.py reports `roofline_fp32` against.
+ * Synchronous; a few milliseconds. */
+int rrtmgp_b200_measure_fp32_peak(int32_t device, double* ffma_tflops, double* ffma2_tflops);
+
 int rrtmgp_b200_last_launch_count(const rrtmgp_b200_handle_t* h);
 const char* rrtmgp_b200_last_cuda_error(const rrtmgp_b200_handle_t* h);
 const char* rrtmgp_b200_strerror(int status);

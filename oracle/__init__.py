@@ -87,6 +87,7 @@ def lib():
         _lib.oracle_gray_heating_rate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double, vp]
         _lib.oracle_gray_update_profile.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] + [vp] * 7
         _lib.oracle_interpolate_levels.argtypes = [C.c_int] * 6 + [vp] * 5 + [C.c_double] * 3 + [vp] * 2
+        _lib.oracle_compute_relative_humidity.argtypes = [C.c_int] * 3 + [vp] * 3 + [C.c_double] * 2 + [vp]
     return _lib
 
 
@@ -295,3 +296,16 @@ def interpolate_levels(p_lay, t_lay, t_sfc, interpolation, bottom_extrapolation=
                                     _ptr(center_z), _ptr(face_z), float(dt.type(params["grav"])), float(dt.type(cp_d)),
                                     float(dt.type(r_d)), _ptr(p_lev), _ptr(t_lev))
     return p_lev, t_lev
+
+
+def compute_relative_humidity(p_lay, t_lay, vmr_h2o, params=DEFAULT_PARAMS):
+    """`compute_relative_humidity!` (src/optics/column_amounts.jl:52-76, kernel gas_optics.jl:58-80); arrays
+    [ncol][nlay] in the precision of `p_lay`."""
+    dt = p_lay.dtype
+    c = lambda a: np.ascontiguousarray(a, dtype=dt)
+    p_lay, t_lay, vmr_h2o = c(p_lay), c(t_lay), c(vmr_h2o)
+    ncol, nlay = p_lay.shape
+    rh = np.zeros((ncol, nlay), dtype=dt)
+    lib().oracle_compute_relative_humidity(int(dt == np.float64), ncol, nlay, _ptr(p_lay), _ptr(t_lay), _ptr(vmr_h2o),
+                                           params["molmass_water"], params["molmass_dryair"], _ptr(rh))
+    return rh

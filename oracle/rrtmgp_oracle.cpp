@@ -1154,6 +1154,22 @@ template <class FT> void prepare_atmosphere(const Lookups<FT>& L, Ctx<FT>& c, co
     }
 }
 
+// compute_relative_humidity! (src/optics/column_amounts.jl:52-76) with compute_relative_humidity_kernel!
+// (src/optics/gas_optics.jl:58-80).  Arrays [ncol][nlay]; `mwd` = molmass_water / molmass_dryair formed in FT.
+template <class FT>
+void compute_relative_humidity(int ncol, int nlay, const FT* p_lay, const FT* t_lay, const FT* vmr_h2o, FT molmass_water,
+                               FT molmass_dryair, FT* rh) {
+    const FT mwd = molmass_water / molmass_dryair;   // column_amounts.jl:62
+    const FT t_ref = FT(273.16), q_lay_min = FT(1e-7);   // :63-64
+    for (size_t k = 0; k < (size_t)ncol * nlay; ++k) {
+        FT mmr_h2o = vmr_h2o[k] * mwd;                   // gas_optics.jl:70
+        FT q_lay = mmr_h2o / (FT(1) + mmr_h2o);
+        FT q_tmp = std::max(q_lay_min, q_lay);
+        FT es_tmp = std::exp((FT(17.67) * (t_lay[k] - t_ref)) / (t_lay[k] - FT(29.65)));
+        rh[k] = std::max(FT(0.01) * (FT(0.263) * p_lay[k] * q_tmp) / es_tmp, FT(0));
+    }
+}
+
 template <class FT> struct OracleHandle { Lookups<FT> L; };
 
 template <class FT> Ctx<FT> make_ctx(const OracleState* st) {
@@ -1585,5 +1601,14 @@ void oracle_interpolate_levels(int is_f64, int ncol, int nlay, int stride, int i
         interpolate_levels<float>(ncol, nlay, stride, interpolation, bottom, (const float*)p_lay, (const float*)t_lay,
                                   (const float*)t_sfc, (const float*)center_z, (const float*)face_z, grav, cp_d, r_d,
                                   (float*)p_lev, (float*)t_lev);
+}
+void oracle_compute_relative_humidity(int is_f64, int ncol, int nlay, const void* p_lay, const void* t_lay, const void* vmr_h2o,
+                                      double molmass_water, double molmass_dryair, void* rh) {
+    if (is_f64)
+        compute_relative_humidity<double>(ncol, nlay, (const double*)p_lay, (const double*)t_lay, (const double*)vmr_h2o,
+                                          molmass_water, molmass_dryair, (double*)rh);
+    else
+        compute_relative_humidity<float>(ncol, nlay, (const float*)p_lay, (const float*)t_lay, (const float*)vmr_h2o,
+                                         (float)molmass_water, (float)molmass_dryair, (float*)rh);
 }
 }  // extern "C"

@@ -62,7 +62,8 @@ EXPORTS = ("rrtmgp_b200_create", "rrtmgp_b200_destroy", "rrtmgp_b200_load_luts",
            "rrtmgp_b200_update_sw_fluxes", "rrtmgp_b200_update_net_fluxes", "rrtmgp_b200_update_fluxes",
            "rrtmgp_b200_update_fluxes_range",
            "rrtmgp_b200_set_level_interpolation", "rrtmgp_b200_heating_rate",
-           "rrtmgp_b200_compute_relative_humidity", "rrtmgp_b200_validate_inputs", "rrtmgp_b200_last_launch_count",
+           "rrtmgp_b200_compute_relative_humidity", "rrtmgp_b200_validate_inputs", "rrtmgp_b200_measure_fp32_peak",
+           "rrtmgp_b200_last_launch_count",
            "rrtmgp_b200_last_cuda_error", "rrtmgp_b200_strerror", "rrtmgp_b200_abi_version")
 
 
@@ -101,6 +102,7 @@ def lib():
         L.rrtmgp_b200_compute_relative_humidity.argtypes = [H, C.c_void_p]
         L.rrtmgp_b200_set_level_interpolation.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.rrtmgp_b200_heating_rate.argtypes = [H, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.rrtmgp_b200_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rrtmgp_b200_last_launch_count.argtypes = [H]
         L.rrtmgp_b200_last_cuda_error.argtypes = [H]
         L.rrtmgp_b200_last_cuda_error.restype = C.c_char_p

@@ -525,16 +525,30 @@ int rrtmgp_b200_load_luts(rrtmgp_b200_handle_t* h, const void* pack, size_t nbyt
     int st = load_lut_pack(h->luts, pack, nbytes, h->cfg.dtype == 1, &err);
     if (st == RRTMGP_B200_ERR_CUDA && err) std::snprintf(h->cuda_err, sizeof(h->cuda_err), "%s", err);
     if (st != RRTMGP_B200_OK) return st;
-    if (h->luts.ngas > h->cfg.ngas) return RRTMGP_B200_ERR_INVALID_ARG;   // vmr gas axis shorter than the tables'
+    // Every failure below leaves the handle WITHOUT tables (`ready()` keeps refusing), so a caller that ignores the
+    // status cannot reach the kernels with tables they would index out of bounds.
+    auto refuse = [&](int code) { free_lut_store(h->luts); return code; };
+    if (h->luts.ngas > h->cfg.ngas) return refuse(RRTMGP_B200_ERR_INVALID_ARG);   // vmr gas axis shorter than the tables'
     // a pack without the cloud / aerosol sections only serves the methods that never read them
     // (lookup_tables, ext/RRTMGPNCDatasetsExt.jl:26-133, loads exactly what the method needs)
-    const bool has_cld = h->cfg.dtype == 1 ? h->luts.f64.cld_lw.liqdata != nullptr : h->luts.f32.cld_lw.liqdata != nullptr;
-    const bool has_aer = h->cfg.dtype == 1 ? h->luts.f64.aero_lw.dust != nullptr : h->luts.f32.aero_lw.dust != nullptr;
-    if ((h->cfg.method >= RRTMGP_B200_ALL_SKY && !has_cld) || (h->cfg.aerosol_radiation && !has_aer)) {
-        free_lut_store(h->luts);
-        return RRTMGP_B200_ERR_BAD_LUT_PACK;
-    }
-    if (h->luts.f32.lw.n_eta > 16 || h->luts.f64.lw.n_eta > 16) return RRTMGP_B200_ERR_UNSUPPORTED;
+    const bool f64 = h->cfg.dtype == 1;
+    const bool has_cld = f64 ? h->luts.f64.cld_lw.liqdata != nullptr : h->luts.f32.cld_lw.liqdata != nullptr;
+    const bool has_aer = f64 ? h->luts.f64.aero_lw.dust != nullptr : h->luts.f32.aero_lw.dust != nullptr;
+    if ((h->cfg.method >= RRTMGP_B200_ALL_SKY && !has_cld) || (h->cfg.aerosol_radiation && !has_aer))
+        return refuse(RRTMGP_B200_ERR_BAD_LUT_PACK);
+    // limits of the fields the kernels bit-pack (solver.cuh): eta cell in 4 bits, T / p node in 8 bits each,
+    // cloud size interval in 8 bits, MERRA size bin in 3 bits
+    auto limits_ok = [&](auto& L) {
+        for (auto* g : {&L.lw, &L.sw})
+            if (g->n_eta > 16 || g->n_eta < 2 || g->n_t > 255 || g->n_t < 2 || g->n_p > 255 || g->n_p_ref < 2) return false;
+        for (auto* c : {&L.cld_lw, &L.cld_sw})
+            if (c->liqdata != nullptr && (c->nsize_liq > 255 || c->nsize_ice > 255 || c->nsize_liq < 2 || c->nsize_ice < 2 ||
+                                          c->nrghice < h->cfg.ice_rgh)) return false;
+        for (auto* a : {&L.aero_lw, &L.aero_sw})
+            if (a->dust != nullptr && (a->nbin > 7 || a->nbin < 1 || a->nrh < 2)) return false;
+        return true;
+    };
+    if (!(f64 ? limits_ok(h->luts.f64) : limits_ok(h->luts.f32))) return refuse(RRTMGP_B200_ERR_UNSUPPORTED);
     return RRTMGP_B200_OK;
 }
 

@@ -2,10 +2,13 @@
 // reference routine it computes (file:line in CliMA/RRTMGP.jl v1.0.0).
 //
 // Precision policy.  Float64 kernels use IEEE division / sqrt and the full-precision libdevice
-// exp / expm1 / log throughout.  Float32 kernels keep IEEE arithmetic for the once-per-column
-// and once-per-(layer, band) work (phase 0 / phase 1) but use the SFU approximations
-// (ex2.approx, rcp.approx, sqrt.approx: <= 2 ulp) inside the per-(layer, g-point) loop, where
-// a full-precision IEEE divide costs ~15 instructions with a divergent slow path.  The guard
+// exp / expm1 / log throughout.  Float32 kernels use IEEE division (`pdiv`) for everything in
+// phase 0 -- in particular every quotient that is truncated to a table index (jt, jpress, cloud
+// size interval, Planck interval), so the indices equal the reference's Float32 path -- and
+// full-precision exp / log there; the SFU approximations (`hdiv` = div.approx.ftz, ex2.approx,
+// sqrt.approx: <= 2 ulp) serve the per-(layer, band) fractions of phase 1, which only enter
+// continuous piecewise-linear interpolations, and the per-(layer, g-point) loop, where a
+// full-precision IEEE divide costs ~15 instructions with a divergent slow path.  The guard
 // constants of src/Numerics.jl are kept exactly; 1 - exp(-x) keeps its small-x accuracy (the
 // reason the reference uses expm1, longwave_2stream.jl:168-170) through a series below x = 0.25.
 // Parity against the Float64 oracle is asserted in tests/test_gpu_parity.py with the
@@ -52,6 +55,9 @@ template <typename FT> __device__ __forceinline__ FT rmax(FT a, FT b) { return a
 template <typename FT> __device__ __forceinline__ FT rmin(FT a, FT b) { return a < b ? a : b; }
 template <typename FT> __device__ __forceinline__ FT rabs(FT a) { return a < FT(0) ? -a : a; }
 
+// IEEE division (phase 0: table indices and everything else computed once per (column, layer))
+__device__ __forceinline__ float pdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double pdiv(double a, double b) { return a / b; }
 // hot-loop forms
 __device__ __forceinline__ double hdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ double hsqrt(double x) { return sqrt(x); }
@@ -118,7 +124,7 @@ template <bool S, typename T> __device__ __forceinline__ T ldt(const T* p) {
 template <bool S = false, typename FT> __device__ __forceinline__ int loc_lower_eq(FT xi, FT dx, int n, const FT* __restrict__ x) {
     if (xi <= ldt<S>(x)) return 1;
     if (xi >= ldt<S>(x + n - 1)) return n - 1;
-    int j = (int)hdiv(xi - ldt<S>(x), dx) + 1;
+    int j = (int)pdiv(xi - ldt<S>(x), dx) + 1;
     return j < n - 1 ? j : n - 1;
 }
 // ---- optics_utils.jl:34-44 split into "locate" (per level) and "evaluate" (per band) ----
@@ -129,7 +135,7 @@ __device__ __forceinline__ void interp1d_eq_locate(FT xi, const FT* __restrict__
     if (xi > ldt<S>(x + n - 1)) { loc = n; factor = FT(0); return; }
     FT dx = ldt<S>(x + 1) - ldt<S>(x);
     loc = loc_lower_eq<S>(xi, dx, n, x);
-    factor = hdiv(xi - ldt<S>(x + loc - 1), dx);
+    factor = pdiv(xi - ldt<S>(x + loc - 1), dx);
 }
 template <bool S = false, typename FT>
 __device__ __forceinline__ FT interp1d_eq_eval(int loc, FT factor, const FT* __restrict__ y, int n) {
@@ -147,7 +153,7 @@ __device__ __forceinline__ void interp1d_loc_factor(FT xi, const FT* __restrict_
     else
         for (int i = 1; i <= n; ++i)
             if (xi < ldt<S>(x + i - 1)) { loc = i - 1; break; }
-    factor = hdiv(xi - ldt<S>(x + loc - 1), ldt<S>(x + loc) - ldt<S>(x + loc - 1));
+    factor = pdiv(xi - ldt<S>(x + loc - 1), ldt<S>(x + loc) - ldt<S>(x + loc - 1));
 }
 
 // ---- longwave_2stream.jl:149-222 ----

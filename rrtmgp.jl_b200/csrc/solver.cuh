@@ -88,12 +88,12 @@ template <> __device__ __forceinline__ double int_as_ft<double>(int i) { return 
 // cloud_optics.jl:154-192 / :207-244, split into "locate" (per layer) and "evaluate" (per band)
 template <typename FT>
 __device__ __forceinline__ void cld_locate(int nsize, FT lwr, FT upr, FT re, int& loc, FT& fac) {
-    FT dr = hdiv(upr - lwr, FT(nsize - 1));
+    FT dr = pdiv(upr - lwr, FT(nsize - 1));
     re = rmax(rmin(re, upr), lwr);
-    loc = (int)hdiv(re - lwr, dr) + 1;
+    loc = (int)pdiv(re - lwr, dr) + 1;
     loc = loc < nsize - 1 ? loc : nsize - 1;
     loc = loc > 1 ? loc : 1;
-    fac = hdiv(re - lwr - (loc - 1) * dr, dr);
+    fac = pdiv(re - lwr - (loc - 1) * dr, dr);
 }
 template <bool S = false, typename FT>
 __device__ __forceinline__ void cld_eval(int nsize, const FT* __restrict__ tbl, int loc, FT fac, FT path, FT& tau,
@@ -268,19 +268,19 @@ struct Warp {
             int tropo = p_lay > L.p_ref_tropo ? 1 : 2;
             FT dT = ldt<FUSED>(t_ref + 1) - ldt<FUSED>(t_ref);
             int jt = loc_lower_eq<FUSED>(t_lay, dT, n_t, t_ref);
-            FT ft = hdiv(t_lay - ldt<FUSED>(t_ref + jt - 1), dT);
+            FT ft = pdiv(t_lay - ldt<FUSED>(t_ref + jt - 1), dT);
             FT dlnp = ldt<FUSED>(ln_p_ref) - ldt<FUSED>(ln_p_ref + 1);
             FT lp = rlog(p_lay);
-            int jpress = (int)hdiv(ldt<FUSED>(ln_p_ref) - lp, dlnp) + 1;
+            int jpress = (int)pdiv(ldt<FUSED>(ln_p_ref) - lp, dlnp) + 1;
             jpress = jpress > 1 ? jpress : 1;
             jpress = (jpress < L.n_p_ref - 1 ? jpress : L.n_p_ref - 1) + 1;
-            FT fp = hdiv(ldt<FUSED>(ln_p_ref + jpress - 2) - lp, dlnp);
+            FT fp = pdiv(ldt<FUSED>(ln_p_ref + jpress - 2) - lp, dlnp);
             int jp = jpress + tropo - 1;
             FT h2o = get_vmr(P, L.idx_h2o, k, col, FUSED ? svmr : nullptr);
             own_h2o[j] = h2o;
             if (FUSED && P.ngas >= 3) own_g3[j] = get_vmr(P, 3, k, col);
             own_cdry[j] = col_dry;
-            own_dens[j] = hdiv(FT(0.01) * p_lay, t_lay);
+            own_dens[j] = pdiv(FT(0.01) * p_lay, t_lay);
             int aero_on = 0;
             if (use_aero) {   // aerosol_optics.jl:464-483, :438-451, optics_utils.jl:51-62
                 const FT* am = P.io.aero_mass + ((size_t)col * nlay + k) * 15;

@@ -62,3 +62,54 @@ def run_oracle(pack, state, dtype, *, seed=0, isothermal_boundary_layer=False, *
 
 def maxdiff(a, b):
     return float(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Float32 parity gate + ledger.  Bar = the reference's own Float32<->Float64 CI thresholds
+# (test/float32_consistency.jl:53-62), judged against the Float64 oracle.  The ONLY exception, decided per
+# column: where the reference's own Float32 arithmetic (the Float32 oracle) is above the threshold in that same
+# column, the engine may be up to 1.5x the Float32 oracle's error there.  Every comparison is recorded in
+# LEDGER (written to profiles/parity_ledger.json by conftest.py) with the achieved error, the threshold, the
+# Float32 oracle's error, which bar bound and how many columns used the exception.
+# ---------------------------------------------------------------------------------------------------------
+LEDGER = []
+
+
+def _per_column(a, b, col_axis):
+    d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))
+    axes = tuple(i for i in range(d.ndim) if i != col_axis)
+    return d.max(axis=axes) if axes else d
+
+
+def gate_f32(key, eng, ref64, tol, ref32=None, *, col_axis=0, note=""):
+    """Asserts one flux array of the Float32 engine against the Float64 oracle; returns the ledger row."""
+    import os
+    err = _per_column(eng, ref64, col_axis)
+    r32 = _per_column(ref32, ref64, col_axis) if ref32 is not None else None
+    over = err > tol
+    excused = np.zeros_like(over)
+    if r32 is not None:
+        excused = over & (r32 > tol) & (err <= 1.5 * r32)
+    bad = over & ~excused
+    worst = int(np.argmax(err))
+    row = {"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "key": key, "note": note,
+           "columns": int(err.size), "threshold": float(tol), "engine_max_err": float(err.max()),
+           "engine_max_err_column": worst,
+           "f32_oracle_max_err": None if r32 is None else float(r32.max()),
+           "f32_oracle_err_same_column": None if r32 is None else float(r32[worst]),
+           "columns_over_threshold": int(over.sum()), "columns_excused_by_f32_oracle": int(excused.sum()),
+           "bar": "threshold" if not over.any() else "1.5 x f32-oracle error in the same column",
+           "passed": not bool(bad.any())}
+    LEDGER.append(row)
+    assert not bad.any(), (key, float(err[bad].max()), tol, None if r32 is None else float(r32[bad].max()))
+    return row
+
+
+def gate_f64(key, eng, ref64, rel=1e-9, note=""):
+    import os
+    scale = max(1.0, float(np.abs(ref64).max()))
+    err = maxdiff(eng, ref64)
+    LEDGER.append({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "key": key, "note": note,
+                   "threshold": rel * scale, "engine_max_err": err, "bar": f"{rel:g} relative (Float64 engine vs Float64 oracle)",
+                   "passed": err <= rel * scale})
+    assert err <= rel * scale, (key, err, rel * scale)
