@@ -41,10 +41,15 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
 
 // groups of four minor-absorber slots per band: 1 (synthetic pack) or 2 (up to 8 / 7 + Rayleigh, real tables)
 
-// RRTMGP_B200_KERNEL=generic forces the shared-memory kernels of solver.cuh (experiments / A-B tests).
+// RRTMGP_B200_KERNEL=generic forces the shared-memory kernels of solver.cuh, =fused the single-role fast kernels of
+// solver_fast.cuh instead of the warp-specialised ones of solver_ws.cuh (experiments / A-B tests).
 static bool fast_enabled() {
     const char* e = std::getenv("RRTMGP_B200_KERNEL");
     return !(e && !std::strcmp(e, "generic"));
+}
+static bool ws_enabled() {
+    const char* e = std::getenv("RRTMGP_B200_KERNEL");
+    return !(e && !std::strcmp(e, "fused"));
 }
 
 // Fast path: Float32, nlay <= 95, real-table shape. Returns -1 when not applicable.
@@ -55,6 +60,14 @@ template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_op
     if (P.io.band_up != nullptr && !L.bands_of_16) return -1;   // per-band sums = half-row sums only for aligned 16-g-point bands
     if (L.n_eta != 9 || L.n_t != 14 || L.maxb != 2 || L.n_minor_groups > 2 || (L.n_gpt % 32) != 0) return -1;
     const bool ng1 = L.n_minor_groups == 1;
+    if (ws_enabled() && P.nlay <= kWsMaxLay) {   // warp-specialised pipeline (gas warps -> RT warps)
+        int t = -1;
+        if (mode == MODE_LW_2STREAM && L.n_gpt == 256 && L.kmaj_pf != nullptr)
+            t = ng1 ? launch_ws_lw_ng1(P, max_smem_optin, s) : launch_ws_lw_ng2(P, max_smem_optin, s);
+        else if (mode == MODE_SW_2STREAM && L.n_gpt == 224)
+            t = ng1 ? launch_ws_sw_ng1(P, max_smem_optin, s) : launch_ws_sw_ng2(P, max_smem_optin, s);
+        if (t >= 0) return t;
+    }
     if (mode == MODE_LW_2STREAM && L.n_gpt == 256 && L.kmaj_pf != nullptr)
         return ng1 ? launch_fast_lw_ng1(P, max_smem_optin, s) : launch_fast_lw_ng2(P, max_smem_optin, s);
     if (mode == MODE_LW_NOSCAT && L.n_gpt == 256 && L.kmaj_pf != nullptr) {

@@ -3,6 +3,7 @@
 // parallelises; solver.cu dispatches to their entry points.
 #pragma once
 #include "solver_fast.cuh"
+#include "solver_ws.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -20,6 +21,11 @@ int launch_fast_noscat1_ng1(SolveParams<float>& P, int max_smem_optin, cudaStrea
 int launch_fast_noscat1_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
 int launch_fast_noscat4_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);   // two to four angles
 int launch_fast_noscat4_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+// warp-specialised two-stream kernels (solver_ws.cuh), nlay <= 64
+int launch_ws_lw_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_ws_lw_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_ws_sw_ng1(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
+int launch_ws_sw_ng2(SolveParams<float>& P, int max_smem_optin, cudaStream_t s);
 
 // Shared-memory plan of the fast kernels: band records + high-level albedos + staging tile + accumulators.
 template <int WARPS>
@@ -117,6 +123,74 @@ static int launch_fast_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_
         return P.io.band_up != nullptr ? launch_fast_sp<MODE, NGPT, NG, true, 12, NMU>(P, max_smem_optin, s)
                                        : launch_fast_sp<MODE, NGPT, NG, false, 12, NMU>(P, max_smem_optin, s);
     }
+}
+
+// ---- warp-specialised kernels: per (gas warp, RT warp) pair the gas warp's Warp<> layout, the hand-off ring, the
+// RT warp's staging tile and accumulators; CTA-shared tail as in plan_smem_fast ----
+static int plan_smem_ws(SolveParams<float>& P, WsSmem& F, int max_smem_optin) {
+    const int nlay = P.nlay, nlev = nlay + 1, maxb = 2;
+    const int nrec = nlay < 32 ? nlay : 32;
+    P.rec_words = 20 + 4 * P.lut.n_minor_groups;
+    P.rec_row = maxb * P.rec_words;
+    if (((P.rec_row >> 2) & 1) == 0) P.rec_row += 4;          // row of 4 * odd words (see plan_smem_fast)
+    int off = 0;
+    P.off_colj = off; off = align_up(off + nlay * (int)sizeof(int), 16);
+    P.off_colp = off; off = align_up(off + nlay * 4 * (int)sizeof(float), 16);
+    P.off_recj = off;
+    P.off_rec = off;  off = align_up(off + nrec * P.rec_row * (int)sizeof(float), 16);
+    P.off_plk = off;  off = align_up(off + maxb * (nlev + 1) * (int)sizeof(float), 16);
+    P.off_store = off;
+    F.off_ring = off;  off = align_up(off + kWsStages * kWsStageF4 * 16, 128);
+    F.off_stage = off; off = align_up(off + 16 * kStageStride * (int)sizeof(float), 16);
+    F.off_acc = off;   off = align_up(off + 3 * kWsAccStride * (int)sizeof(float), 128);
+    F.off_bacc = -1;
+    if (P.io.band_up != nullptr) { F.off_bacc = off; off = align_up(off + 4 * kWsAccStride * (int)sizeof(float), 128); }
+    P.warp_bytes = off;                                        // bytes per pair
+    int tail = kWsPairs * off;
+    F.off_vmr = tail;  tail = align_up(tail + (P.ngas > 0 ? P.ngas : 1) * (int)sizeof(float), 128);
+    F.off_blob = tail;
+    int room = max_smem_optin - 1024 - tail;                   // 1024: static shared memory (mbarriers, mailboxes)
+    if (const char* e = std::getenv("RRTMGP_B200_STAGE_BYTES")) room = std::min(room, std::atoi(e));
+    F.staged_bytes = 0;
+    for (int i = 0; i < P.lut.n_blob_cut; ++i)
+        if (P.lut.blob_cut[i] <= room) F.staged_bytes = P.lut.blob_cut[i];
+    return tail + F.staged_bytes;
+}
+
+template <int MODE, int NGPT, int NG, bool HAS_CLD, bool HAS_AER, bool SPECTRAL>
+static int launch_ws_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t stream) {
+    WsSmem F;
+    const size_t smem = (size_t)plan_smem_ws(P, F, max_smem_optin);
+    if ((int)smem > max_smem_optin - 1024) return -1;
+    auto kern = solve_kernel_ws<MODE, NGPT, NG, HAS_CLD, HAS_AER, SPECTRAL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (P.work_counter == nullptr) return -1;
+    e = cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return (int)e;
+    const int need = (P.ncol + kWsPairs - 1) / kWsPairs;
+    const int sms = sm_count_of_current_device();
+    const int grid = need < sms ? need : sms;   // persistent: one CTA per SM
+    kern<<<grid, kWsPairs * 64, smem, stream>>>(P, F);
+    return (int)cudaGetLastError();
+}
+
+template <int MODE, int NGPT, int NG>
+static int launch_ws_ng(SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
+    if (P.nlay > kWsMaxLay) return -1;
+    const bool c = P.use_cloud != 0, a = P.use_aero != 0, sp = P.io.band_up != nullptr;
+#define RB_WS(C, A, S) return launch_ws_t<MODE, NGPT, NG, C, A, S>(P, max_smem_optin, s)
+    if (sp) {
+        if (c && a) RB_WS(true, true, true);
+        if (c) RB_WS(true, false, true);
+        if (a) RB_WS(false, true, true);
+        RB_WS(false, false, true);
+    }
+    if (c && a) RB_WS(true, true, false);
+    if (c) RB_WS(true, false, false);
+    if (a) RB_WS(false, true, false);
+    RB_WS(false, false, false);
+#undef RB_WS
 }
 
 }  // namespace rb
