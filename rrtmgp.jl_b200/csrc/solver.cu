@@ -41,15 +41,16 @@ static int launch_mode(SolveParams<FT>& P, int max_smem_optin, cudaStream_t stre
 
 // groups of four minor-absorber slots per band: 1 (synthetic pack) or 2 (up to 8 / 7 + Rayleigh, real tables)
 
-// RRTMGP_B200_KERNEL=generic forces the shared-memory kernels of solver.cuh, =fused the single-role fast kernels of
-// solver_fast.cuh instead of the warp-specialised ones of solver_ws.cuh (experiments / A-B tests).
+// RRTMGP_B200_KERNEL=generic forces the shared-memory kernels of solver.cuh; =ws selects the warp-specialised
+// pipeline of solver_ws.cuh instead of the single-role fast kernels of solver_fast.cuh (measured slower on B200,
+// profiles/r2c_*: kept as a parity-tested experiment).
 static bool fast_enabled() {
     const char* e = std::getenv("RRTMGP_B200_KERNEL");
     return !(e && !std::strcmp(e, "generic"));
 }
 static bool ws_enabled() {
     const char* e = std::getenv("RRTMGP_B200_KERNEL");
-    return !(e && !std::strcmp(e, "fused"));
+    return e && !std::strcmp(e, "ws");
 }
 
 // Fast path: Float32, nlay <= 95, real-table shape. Returns -1 when not applicable.

@@ -3,17 +3,18 @@
 //
 //   gas warps (8..15)   everything that ends in (tau, ssa, g[, Planck source]) of a (layer, g-point) cell: phase 0 /
 //                       phase 1 / McICA of solver.cuh, the k-distribution corner gathers and the trilinear
-//                       interpolation (gas_optics.jl:176-320, optics_utils.jl:85-181), the cloud / aerosol increment
-//                       and -- longwave -- the level sources (compute_optical_props.jl:157-195).  Layers are
-//                       independent here, so the gathers of layer k+1 are in flight while layer k is interpolated.
-//   RT warps (0..7)     the two-stream coefficients and the adding recurrences (longwave_2stream.jl:149-334,
+//                       interpolation (gas_optics.jl:176-320, optics_utils.jl:85-181) and the cloud / aerosol
+//                       increment.  Layers are independent here, so the gathers of layer k+1 are in flight while
+//                       layer k is interpolated.
+//   RT warps (0..7)     the longwave level sources (compute_optical_props.jl:157-195), the two-stream coefficients
+//                       and the adding recurrences (longwave_2stream.jl:149-334,
 //                       shortwave_2stream.jl:189-392), the g-point reductions and the (nlev, ncol) epilogue.  Their
 //                       level store is tensor memory only: 2 warps per TMEM lane quadrant, 256 columns each, so all
 //                       three values of all 64 levels fit and the shared-memory albedo spill of solver_fast.cuh is gone.
 //
 // Gas warp 8 + i feeds RT warp i through a shared-memory ring: stage = the (up to) four layers 4s..4s+3 of the block
-// in hand, one float4 per (layer, lane) + one header row, `kWsStages` stages deep, full / empty mbarriers (all 32
-// lanes arrive).  The column index travels through a two-deep mailbox with its own mbarrier pair; gas warps own the
+// in hand, one float4 per (layer, lane) + two header rows (longwave: Planck function of the band at the stage's
+// levels), `kWsStages` stages deep, full / empty mbarriers (all 32 lanes arrive).  The column index travels through a two-deep mailbox with its own mbarrier pair; gas warps own the
 // atomic column queue.  Registers are re-balanced with setmaxnreg (RT 104, gas 152 = the whole register file).
 //
 // Why not TMA for the corner gathers (north star): measured on B200
@@ -21,6 +22,12 @@
 // whatever its size up to 512 B, so the 8-12 requests a (layer, 32 g-points) step needs take 105-135 clocks against
 // 69 clocks for the same 4 KB through per-lane LDG -- and the whole fused step took 113.  TMA stays where it fits: the
 // one-off bulk staging of the small tables (solver_fast.cuh).
+//
+// STATUS (measured, profiles/r2b_*, r2c_*): parity-green on the whole GPU suite, but SLOWER than the single-role
+// kernels of solver_fast.cuh on B200 -- 27.3 + 22.8 ms against 20.2 + 18.6 ms per 1e5 columns.  The gas role is the
+// bottleneck (141 instructions per (layer, 32 g-points) step against 113 for the RT role, at 8.8 clocks per
+// instruction: its gathers have one layer of cover and two warps per scheduler to hide behind), so the RT warps sleep
+// on the ring 60 % of the time.  Selected with RRTMGP_B200_KERNEL=ws; the default stays solver_fast.cuh.
 #pragma once
 #include "solver_fast.cuh"
 
@@ -31,7 +38,7 @@ constexpr int kWsHL = 4;             // layers per hand-off stage
 constexpr int kWsStages = 3;         // ring depth in stages
 constexpr int kWsMaxLay = 64;
 constexpr int kWsAccStride = kWsMaxLay + 4;
-constexpr int kWsStageF4 = (kWsHL + 1) * 32;   // float4 per stage: four layer rows + one header row
+constexpr int kWsStageF4 = (kWsHL + 2) * 32;   // float4 per stage: four layer rows + two header rows (longwave Planck values)
 constexpr int kWsRegsRT = 104, kWsRegsGas = 152;
 
 struct WsSmem {
@@ -41,6 +48,22 @@ struct WsSmem {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the ring's barriers are addressed by their 32-bit shared-memory address, computed once (the generic -> shared
+// conversion costs an S2R + address arithmetic each time)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {   // with a suspend-time hint: a starved warp sleeps
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
@@ -100,9 +123,8 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
     mbar_wait(&blob_bar, 0);
 
     unsigned char* pbase = smem_raw + (size_t)pair * P.warp_bytes;
-    float4* ring = reinterpret_cast<float4*>(pbase + F.off_ring);    // [kWsStages][kWsHL + 1][32]
-    uint64_t* bar_full = &bars[pair][0];
-    uint64_t* bar_empty = &bars[pair][kWsStages];
+    float4* ring_lane = reinterpret_cast<float4*>(pbase + F.off_ring) + lane;    // [kWsStages][kWsHL + 2][32], this lane's column
+    const uint32_t bar0 = smem_u32(&bars[pair][0]);                   // full[s] at bar0 + 8 s, empty[s] at bar0 + 8 (kWsStages + s)
     uint64_t* col_full = &bars[pair][2 * kWsStages];
     uint64_t* col_empty = &bars[pair][2 * kWsStages + 2];
     const GasLut<FT>& L = P.lut;
@@ -112,13 +134,19 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
         const long long off = reinterpret_cast<const unsigned char*>(g) - L.blob;
         return (off >= 0 && off < F.staged_bytes) ? reinterpret_cast<const int*>(sblob + off) : g;
     };
-    int ring_idx = 0;            // stage of the ring in hand and its phase parity; both roles step them identically
-    uint32_t ring_phase = 0;
-    auto ring_next = [&]() { if (++ring_idx == kWsStages) { ring_idx = 0; ring_phase ^= 1u; } };
+    // The ring stage in hand: its rows, its `full` barrier and the phase parity of the current pass.  Both roles step
+    // through the stages in the same order (stage = layers 4s..4s+3 of a block), so they keep these in lock step.
+    float4* sp = ring_lane;
+    uint32_t bfull = bar0, ring_phase = 0;
+    int ring_idx = 0;
+    auto ring_next = [&]() {
+        if (++ring_idx == kWsStages) { ring_idx = 0; ring_phase ^= 1u; sp = ring_lane; bfull = bar0; }
+        else { sp += kWsStageF4; bfull += 8u; }
+    };
 
     if (is_rt) {
         // =====================================================================================================
-        // RT role: coefficients + adding + reductions + epilogue
+        // RT role: level sources (longwave), coefficients + adding + reductions + epilogue
         // =====================================================================================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsRegsRT));
         const uint32_t tA = tmem_base_smem + ((uint32_t)(warp & 3) << 21) + (uint32_t)((warp >> 2) * 256);
@@ -179,41 +207,59 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
                     continue;
                 }
                 if (LW) {
-                    // longwave_2stream.jl:243-334, adding from the bottom; the hand-off row of layer k is
-                    // (tau, ssa, g, Planck source at the layer's top level), the header (source at level 0, surface Planck)
+                    // longwave_2stream.jl:243-334, adding from the bottom.  Row of layer k: (tau, ssa, g, Planck fraction);
+                    // header rows of a stage: Planck function of the band at levels 4s+1..4s+4, and (stage 0) at level 0 and
+                    // of the surface.  The source at the top level of layer k is the geometric mean across the interface
+                    // (compute_optical_props.jl:187-195), so layer k is closed once row k + 1 has arrived.
                     const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
                     const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : 0.f;
-                    FT lev_bot = 0.f, albedo = 1.f - emis, src = 0.f;
-                    for (int t0 = 0; t0 < nlay; t0 += 16) {                  // tiles of <= 16 layers = <= 4 stages
+                    mbar_wait_a(bfull, ring_phase);
+                    float4 v = sp[0];
+                    FT lev_bot, albedo = 1.f - emis, src;
+                    {
+                        const float4 h = sp[(kWsHL + 1) * 32];
+                        lev_bot = h.x * v.w;                               // source at level 0
+                        src = Num<FT>::pi() * emis * (h.y * v.w);          // surface (compute_optical_props.jl:184-186)
+                    }
+                    const FT* bkp = reinterpret_cast<const FT*>(sp + kWsHL * 32);   // Planck at level k + 1, this lane's band
+                    const float4* vp = sp + 32;                                     // row k + 1
+                    for (int t0 = 0; t0 < nlay; t0 += 16) {                  // tiles of <= 16 layers
                         const int tend = t0 + 16 < nlay ? t0 + 16 : nlay;
-                        for (int s0 = t0; s0 < tend; s0 += kWsHL) {
-                            mbar_wait(&bar_full[ring_idx], ring_phase);
-                            const float4* slot = ring + ring_idx * kWsStageF4 + lane;
-                            if (s0 == 0) {
-                                const float4 h = slot[kWsHL * 32];
-                                lev_bot = h.x;
-                                src = Num<FT>::pi() * emis * h.y;
-                            }
-                            const int send = s0 + kWsHL < nlay ? s0 + kWsHL : nlay;
 #pragma unroll 1
-                            for (int k = s0; k < send; ++k) {
-                                const float4 v = slot[(k - s0) * 32];
-                                const LwCoef C = lw_2stream_coeffs_nosrc(v.x, v.y, v.z);
-                                const FT denom = rcp_approx(1.f - C.Rdif * albedo);
-                                const FT lev_top = v.w;
-                                const FT dB = lev_bot - lev_top;
-                                const FT su = Num<FT>::pi() * (lev_top * C.emis_fac - C.q * dB);
-                                const FT sd = Num<FT>::pi() * (lev_bot * C.emis_fac + C.q * dB);
-                                // level k: F_dn(k) = A F_dn(k+1) + B ; F_up(k) = albedo F_dn(k) + src
-                                tmem_st2(tA + 2 * k, C.Tdif * denom, (C.Rdif * src + sd) * denom);
-                                tmem_st1(tAl + k, albedo);
-                                stage[(k - t0) * kStageStride + lane] = src;
-                                src = su + C.Tdif * denom * (src + albedo * sd);
-                                albedo = C.Rdif + C.Tdif * C.Tdif * albedo * denom;
-                                lev_bot = lev_top;
+                        for (int k = t0; k < tend; ++k) {
+                            const bool stage_end = (k & 3) == 3 || k + 1 == nlay;
+                            const FT bk = *bkp;
+                            float4 vn = v;
+                            uint32_t done_bar = 0;
+                            if (stage_end) {                                 // warp-uniform
+                                done_bar = bfull + 8u * kWsStages;           // `empty` of the stage in hand
+                                if (k + 1 < nlay) {
+                                    ring_next();
+                                    mbar_wait_a(bfull, ring_phase);
+                                    vn = sp[0];
+                                    bkp = reinterpret_cast<const FT*>(sp + kWsHL * 32);
+                                    vp = sp + 32;
+                                }
+                            } else {
+                                vn = *vp;
+                                vp += 32; ++bkp;
                             }
-                            mbar_arrive(&bar_empty[ring_idx]);
-                            ring_next();
+                            const FT inc_k = bk * v.w;
+                            const FT lev_top = k + 1 < nlay ? hsqrt(inc_k * (bk * vn.w)) : inc_k;
+                            const LwCoef C = lw_2stream_coeffs_nosrc(v.x, v.y, v.z);
+                            const FT denom = rcp_approx(1.f - C.Rdif * albedo);
+                            const FT dB = lev_bot - lev_top;
+                            const FT su = Num<FT>::pi() * (lev_top * C.emis_fac - C.q * dB);
+                            const FT sd = Num<FT>::pi() * (lev_bot * C.emis_fac + C.q * dB);
+                            // level k: F_dn(k) = A F_dn(k+1) + B ; F_up(k) = albedo F_dn(k) + src
+                            tmem_st2(tA + 2 * k, C.Tdif * denom, (C.Rdif * src + sd) * denom);
+                            tmem_st1(tAl + k, albedo);
+                            stage[(k - t0) * kStageStride + lane] = src;
+                            src = su + C.Tdif * denom * (src + albedo * sd);
+                            albedo = C.Rdif + C.Tdif * C.Tdif * albedo * denom;
+                            lev_bot = lev_top;
+                            v = vn;
+                            if (stage_end) mbar_arrive_a(done_bar);
                         }
                         __syncwarp();
                         {                                                     // sum_g src of levels t0 .. tend-1
@@ -224,6 +270,7 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
                         }
                         __syncwarp();
                     }
+                    ring_next();                                             // past the block's last stage
                     FT dn = inc;
                     {
                         FT hu, hd;
@@ -286,11 +333,13 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
                         const int ktop = kc + 7 < nlay - 1 ? kc + 7 : nlay - 1;
                         for (int shi = ktop; shi >= kc; shi = (shi & ~3) - 1) {
                             const int slo = shi & ~3;
-                            mbar_wait(&bar_full[ring_idx], ring_phase);
-                            const float4* slot = ring + ring_idx * kWsStageF4 + lane;
+                            mbar_wait_a(bfull, ring_phase);
+                            const float4* vp = sp + (shi & 3) * 32;
+                            FT* stp = stage + ((shi - kc) * 2) * kStageStride + lane;
 #pragma unroll 1
                             for (int k = shi; k >= slo; --k) {
-                                const float4 v = slot[(k & 3) * 32];
+                                const float4 v = *vp;
+                                vp -= 32;
                                 FT Rdir, Tdir, Rdif, Tdif;
                                 sw_2stream_coeffs(v.x, v.y, v.z, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
                                 const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
@@ -298,16 +347,17 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
                                 // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
                                 tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
                                 tmem_st1(tAl + k, beta);
-                                stage[((k - kc) * 2 + 0) * kStageStride + lane] = d;        // d_{k+1}
+                                stp[0] = d;                                       // d_{k+1}
                                 d = sd + Tdif * denom * (d + beta * su);
                                 beta = Rdif + Tdif * Tdif * beta * denom;
                                 tau_cum += v.x;
                                 float ex;
                                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(tau_cum * neg_inv_mu0_l2e));
                                 dir = dir_top * ex;                               // direct flux at level k
-                                stage[((k - kc) * 2 + 1) * kStageStride + lane] = dir;
+                                stp[kStageStride] = dir;
+                                stp -= 2 * kStageStride;
                             }
-                            mbar_arrive(&bar_empty[ring_idx]);
+                            mbar_arrive_a(bfull + 8u * kWsStages);
                             ring_next();
                         }
                         __syncwarp();
@@ -395,12 +445,14 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
         }
     } else {
         // =====================================================================================================
-        // gas role: phase 0 / phase 1 / McICA, corner gathers, interpolation, increments, level sources
+        // gas role: phase 0 / phase 1 / McICA, corner gathers, interpolation, increments
         // =====================================================================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsRegsGas));
-        const FT* major = LW ? L.kmaj_pf : L.kmajor;
-        const float4* minor4 = reinterpret_cast<const float4*>(L.kminor4[0]);
-        const int RW = P.rec_words;
+        constexpr int RW = 20 + 4 * NG;                                   // words per band record (plan_smem_ws)
+        constexpr int RR = (((2 * RW) >> 2) & 1) ? 2 * RW : 2 * RW + 4;   // words per record row
+        // per-lane table bases as opaque 64-bit values: one IMAD.WIDE per gather base instead of a uniform base +
+        // lane offset re-added (and sign-extended) for every address
+        auto opaque = [](const void* p) { unsigned long long v = (unsigned long long)p; asm("" : "+l"(v)); return v; };
         auto next_column = [&]() -> long long {
             unsigned int v = 0;
             if (lane == 0) v = atomicAdd(P.work_counter, 1u);
@@ -479,17 +531,13 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
                 }
                 const int gpt = W.gpt, bl = W.bl;
                 const FT* rec_lane = W.rec + bl * RW;
-                const FT* major_lane = major + (LW ? 2 : 1) * gpt;
-                const float4* minor_lane = minor4 + gpt;
-                const unsigned mask0 = W.mask[0], mask1 = W.mask[1];
+                const unsigned long long major_lane = opaque((LW ? L.kmaj_pf : L.kmajor) + (LW ? 2 : 1) * gpt);
+                const unsigned long long minor_lane = opaque(reinterpret_cast<const float4*>(L.kminor4[0]) + gpt);
 
-                // ---- issue the table gathers of cell (layer k, this g-point) ----
-                auto issue = [&](int k, GasLoads<LW, NG>& G) {
-                    const FT* r = rec_lane + (k & 31) * P.rec_row;
-                    bool cb = false;
-                    if (HAS_CLD) cb = ((k < 32 ? mask0 : mask1) >> (k & 31)) & 1u;
-                    G.s = *reinterpret_cast<const float4*>(r + 8);
-                    G.x = *reinterpret_cast<const float4*>(r + 12 + 4 * NG + (cb ? 4 : 0));
+                // ---- issue the table gathers of the cell whose band-record row is `rk`; `cb` = cloudy (McICA) ----
+                auto issue = [&](const FT* rk, bool cb, GasLoads<LW, NG>& G) {
+                    G.s = *reinterpret_cast<const float4*>(rk + 8);
+                    G.x = *reinterpret_cast<const float4*>(rk + 12 + 4 * NG + (cb ? 4 : 0));
                     const int ia = __float_as_int(G.s.z), ib = __float_as_int(G.s.w);   // (jp-1, jt, je1), (jp-1, jt+1, je2)
                     const int ma = __float_as_int(G.x.w), mb = ma + (ib - ia);          // (jt, je1), (jt+1, je2): MT == KT
                     if (LW) {
@@ -498,21 +546,24 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
                         G.c2[0] = __ldg(pa); G.c2[1] = __ldg(pa + KE); G.c2[2] = __ldg(pa + KP); G.c2[3] = __ldg(pa + KP + KE);
                         G.c2[4] = __ldg(pb); G.c2[5] = __ldg(pb + KE); G.c2[6] = __ldg(pb + KP); G.c2[7] = __ldg(pb + KP + KE);
                     } else {
-                        const FT* pa = major_lane + ia;
-                        const FT* pb = major_lane + ib;
+                        const FT* pa = reinterpret_cast<const FT*>(major_lane) + ia;
+                        const FT* pb = reinterpret_cast<const FT*>(major_lane) + ib;
                         G.c1[0] = __ldg(pa); G.c1[1] = __ldg(pa + KE); G.c1[2] = __ldg(pa + KP); G.c1[3] = __ldg(pa + KP + KE);
                         G.c1[4] = __ldg(pb); G.c1[5] = __ldg(pb + KE); G.c1[6] = __ldg(pb + KP); G.c1[7] = __ldg(pb + KP + KE);
                     }
+                    const float4* qa = reinterpret_cast<const float4*>(minor_lane) + ma;
+                    const float4* qb = reinterpret_cast<const float4*>(minor_lane) + mb;
 #pragma unroll
                     for (int gi = 0; gi < NG; ++gi) {
-                        G.m[4 * gi + 0] = __ldg(minor_lane + ma + gi * MS); G.m[4 * gi + 1] = __ldg(minor_lane + ma + gi * MS + ME);
-                        G.m[4 * gi + 2] = __ldg(minor_lane + mb + gi * MS); G.m[4 * gi + 3] = __ldg(minor_lane + mb + gi * MS + ME);
+                        G.m[4 * gi + 0] = __ldg(qa + gi * MS); G.m[4 * gi + 1] = __ldg(qa + gi * MS + ME);
+                        G.m[4 * gi + 2] = __ldg(qb + gi * MS); G.m[4 * gi + 3] = __ldg(qb + gi * MS + ME);
                     }
                 };
-                // ---- gas + cloud + aerosol optics of the gathered cell (gas_optics.jl:176-320, optics_utils.jl:85-202) ----
-                auto optics = [&](int k, const GasLoads<LW, NG>& G, FT& tau, FT& ssa, FT& g, FT& pfrac) {
-                    const FT* r = rec_lane + (k & 31) * P.rec_row;
-                    const float4 v0 = *reinterpret_cast<const float4*>(r), v1 = *reinterpret_cast<const float4*>(r + 4);
+                // ---- gas + cloud + aerosol optics of the gathered cell (gas_optics.jl:176-320, optics_utils.jl:85-202);
+                //      returns the hand-off row: LW (tau, ssa, g, Planck fraction), SW (tau, ssa, g, 0) ----
+                auto optics = [&](const FT* rk, const GasLoads<LW, NG>& G) -> float4 {
+                    const float4 v0 = *reinterpret_cast<const float4*>(rk), v1 = *reinterpret_cast<const float4*>(rk + 4);
+                    FT tau, ssa, g, pfrac;
                     if (LW) {
                         const float2* c = G.c2;
                         tau = G.s.x * (v0.x * c[0].x + v0.y * c[1].x + v0.z * c[2].x + v0.w * c[3].x) +
@@ -530,7 +581,7 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
 #pragma unroll
                     for (int gi = 0; gi < NG; ++gi) {
                         const float4 m11 = G.m[4 * gi], m21 = G.m[4 * gi + 1], m12 = G.m[4 * gi + 2], m22 = G.m[4 * gi + 3];
-                        const float4 sc = *reinterpret_cast<const float4*>(r + 12 + 4 * gi);
+                        const float4 sc = *reinterpret_cast<const float4*>(rk + 12 + 4 * gi);
                         const FT x0 = w11 * m11.x + w21 * m21.x + w12 * m12.x + w22 * m22.x;
                         const FT x1 = w11 * m11.y + w21 * m21.y + w12 * m12.y + w22 * m22.y;
                         const FT x2 = w11 * m11.z + w21 * m21.z + w12 * m12.z + w22 * m22.z;
@@ -553,71 +604,89 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
                     if (INCR) {   // one fused, unconditional increment (optics_utils.jl:189-202, additive form)
                         const FT tn = tau + G.x.x;
                         const FT w = LW ? G.x.y : tau * ssa + G.x.y;
-                        const FT h = G.x.z;
-                        g = hdiv(h, rmax(FLT_EPSILON, w));
-                        ssa = hdiv(w, rmax(FLT_EPSILON, tn));
+                        g = G.x.z * rcp_approx(rmax(FLT_EPSILON, w));
+                        ssa = w * rcp_approx(rmax(FLT_EPSILON, tn));
                         tau = tn;
                     }
+                    return make_float4(tau, ssa, g, pfrac);
                 };
-                // ---- hand layer k to the RT warp: slot (k & 3) of stage k >> 2 ----
-                FT hdr0 = 0.f, hdr1 = 0.f;
-                auto emit = [&](int k, FT a, FT b, FT c, FT d) {
-                    const bool first = LW ? (k & 3) == 0 : ((k & 3) == 3 || k == nlay - 1);
-                    const bool last = LW ? ((k & 3) == 3 || k == nlay - 1) : (k & 3) == 0;
-                    float4* slot = ring + ring_idx * kWsStageF4 + lane;
-                    if (first) mbar_wait(&bar_empty[ring_idx], ring_phase ^ 1u);
-                    slot[(k & 3) * 32] = make_float4(a, b, c, d);
-                    if (LW && k == 0) slot[kWsHL * 32] = make_float4(hdr0, hdr1, 0.f, 0.f);
-                    if (last) { mbar_arrive(&bar_full[ring_idx]); ring_next(); }
-                };
+                const uint32_t bempty_off = 8u * kWsStages;
                 GasLoads<LW, NG> GA, GB;
                 if (LW) {
-                    // bottom -> top; layer k leaves once pfrac of layer k + 1 is known (its top-level source is the
-                    // geometric mean across the interface, compute_optical_props.jl:187-195)
+                    // bottom -> top, stage by stage (layers 4s..4s+3); the gathers of the next layer are in flight while
+                    // the current one is interpolated
                     const FT* pbk = W.plk + bl * (nlev + 1);
-                    FT tau_p = 0.f, ssa_p = 0.f, g_p = 0.f, pf_p = 0.f;
-                    auto lw_step = [&](int k, FT tau, FT ssa, FT g, FT pf) {
-                        if (k == 0) {
-                            hdr0 = pbk[0] * pf;          // source at level 0
-                            hdr1 = pbk[nlev] * pf;       // surface Planck (compute_optical_props.jl:184-186)
-                        } else {
-                            const FT bk = pbk[k];
-                            emit(k - 1, tau_p, ssa_p, g_p, hsqrt((bk * pf_p) * (bk * pf)));
-                        }
-                        tau_p = tau; ssa_p = ssa; g_p = g; pf_p = pf;
-                    };
                     for (int part = 0; part * 32 < nlay; ++part) {
                         build_records(part);
                         const int lo = part * 32, hi = lo + 32 < nlay ? lo + 32 : nlay;
-                        issue(lo, GA);
-                        for (int k = lo; k < hi; k += 2) {
-                            FT tau, ssa, g, pf;
-                            if (k + 1 < hi) issue(k + 1, GB);
-                            optics(k, GA, tau, ssa, g, pf);
-                            lw_step(k, tau, ssa, g, pf);
-                            if (k + 1 < hi) {
-                                if (k + 2 < hi) issue(k + 2, GA);
-                                optics(k + 1, GB, tau, ssa, g, pf);
-                                lw_step(k + 1, tau, ssa, g, pf);
+                        const FT* rk = rec_lane;
+                        unsigned mw = HAS_CLD ? (part == 0 ? W.mask[0] : W.mask[1]) : 0u;   // bit j = layer lo + j
+                        int k = lo;
+                        if (k + 4 <= hi) issue(rk, mw & 1u, GA);
+                        for (; k + 4 <= hi; k += 4) {
+                            mbar_wait_a(bfull + bempty_off, ring_phase ^ 1u);
+                            issue(rk + RR, (mw >> 1) & 1u, GB);
+                            sp[0] = optics(rk, GA);
+                            issue(rk + 2 * RR, (mw >> 2) & 1u, GA);
+                            sp[32] = optics(rk + RR, GB);
+                            issue(rk + 3 * RR, (mw >> 3) & 1u, GB);
+                            sp[64] = optics(rk + 2 * RR, GA);
+                            if (k + 8 <= hi) issue(rk + 4 * RR, (mw >> 4) & 1u, GA);
+                            sp[96] = optics(rk + 3 * RR, GB);
+                            sp[kWsHL * 32] = make_float4(pbk[k + 1], pbk[k + 2], pbk[k + 3], pbk[k + 4]);
+                            if (k == 0) sp[(kWsHL + 1) * 32] = make_float4(pbk[0], pbk[nlev], 0.f, 0.f);
+                            mbar_arrive_a(bfull);
+                            ring_next();
+                            rk += 4 * RR; mw >>= 4;
+                        }
+                        if (k < hi) {   // the column's top stage when nlay is not a multiple of 4
+                            mbar_wait_a(bfull + bempty_off, ring_phase ^ 1u);
+                            const int k0 = k;
+                            for (; k < hi; ++k) {
+                                issue(rk, mw & 1u, GA);
+                                sp[(k & 3) * 32] = optics(rk, GA);
+                                rk += RR; mw >>= 1;
                             }
+                            const int n1 = nlev;   // pbk has nlev + 1 entries
+                            sp[kWsHL * 32] = make_float4(pbk[k0 + 1], pbk[k0 + 2 < n1 ? k0 + 2 : n1], pbk[k0 + 3 < n1 ? k0 + 3 : n1], pbk[k0 + 4 < n1 ? k0 + 4 : n1]);
+                            if (k0 == 0) sp[(kWsHL + 1) * 32] = make_float4(pbk[0], pbk[nlev], 0.f, 0.f);
+                            mbar_arrive_a(bfull);
+                            ring_next();
                         }
                     }
-                    emit(nlay - 1, tau_p, ssa_p, g_p, pbk[nlay] * pf_p);   // top layer: its own increment (:193-195)
                 } else {
-                    for (int part = (nlay - 1) >> 5; part >= 0; --part) {   // top -> bottom
+                    for (int part = (nlay - 1) >> 5; part >= 0; --part) {   // top -> bottom, stage by stage (layers 4s+3..4s)
                         build_records(part);
-                        const int lo = part * 32, hi = lo + 31 < nlay - 1 ? lo + 31 : nlay - 1;
-                        issue(hi, GA);
-                        for (int k = hi; k >= lo; k -= 2) {
-                            FT tau, ssa, g, pf;
-                            if (k - 1 >= lo) issue(k - 1, GB);
-                            optics(k, GA, tau, ssa, g, pf);
-                            emit(k, tau, ssa, g, 0.f);
-                            if (k - 1 >= lo) {
-                                if (k - 2 >= lo) issue(k - 2, GA);
-                                optics(k - 1, GB, tau, ssa, g, pf);
-                                emit(k - 1, tau, ssa, g, 0.f);
+                        const int lo = part * 32;
+                        int k = lo + 31 < nlay - 1 ? lo + 31 : nlay - 1;
+                        const FT* rk = rec_lane + (k & 31) * RR;
+                        unsigned mw = HAS_CLD ? (part == 0 ? W.mask[0] : W.mask[1]) << (31 - (k & 31)) : 0u;   // bit 31 = layer k
+                        if ((k & 3) != 3) {   // the column's top stage when nlay is not a multiple of 4
+                            mbar_wait_a(bfull + bempty_off, ring_phase ^ 1u);
+                            for (;; --k) {
+                                issue(rk, (mw >> 31) & 1u, GA);
+                                sp[(k & 3) * 32] = optics(rk, GA);
+                                rk -= RR; mw <<= 1;
+                                if ((k & 3) == 0) break;
                             }
+                            --k;
+                            mbar_arrive_a(bfull);
+                            ring_next();
+                        }
+                        if (k >= lo) issue(rk, (mw >> 31) & 1u, GA);
+                        for (; k >= lo; k -= 4) {
+                            mbar_wait_a(bfull + bempty_off, ring_phase ^ 1u);
+                            issue(rk - RR, (mw >> 30) & 1u, GB);
+                            sp[96] = optics(rk, GA);
+                            issue(rk - 2 * RR, (mw >> 29) & 1u, GA);
+                            sp[64] = optics(rk - RR, GB);
+                            issue(rk - 3 * RR, (mw >> 28) & 1u, GB);
+                            sp[32] = optics(rk - 2 * RR, GA);
+                            if (k - 4 >= lo) issue(rk - 4 * RR, (mw >> 27) & 1u, GA);
+                            sp[0] = optics(rk - 3 * RR, GB);
+                            mbar_arrive_a(bfull);
+                            ring_next();
+                            rk -= 4 * RR; mw <<= 4;
                         }
                     }
                     if (aod_here) {

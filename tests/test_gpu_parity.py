@@ -762,3 +762,68 @@ def test_clip_active_vs_oracle(real_pack, dtype):
         _check_f64(e, o)
     else:
         _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+
+
+# ---- warp-specialised pipeline (csrc/solver_ws.cuh, RRTMGP_B200_KERNEL=ws): gas warps -> hand-off ring -> RT warps ----
+@pytest.mark.parametrize("nlay", [2, 3, 8, 17, 32, 33, 40, 63, 64])
+def test_warp_specialised_kernels_runtime_nlay_f32(real_pack, monkeypatch, nlay):
+    """Every stage (4 layers), tile (8 / 16) and record-part (32) boundary of the pipeline, partial cloudiness and a
+    day / night mix: Float32 engine vs Float64 oracle, cloud cover and AOD as in the single-role kernels."""
+    monkeypatch.setenv("RRTMGP_B200_KERNEL", "ws")
+    st = R.synthetic.make_atmosphere(96, nlay, cld_frac=None, cos_zenith=None)
+    kw = dict(method="all_sky", aerosols=True, seed=99)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+    np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(np.float32))
+    np.testing.assert_array_equal(e["cld_cover_sw"].astype(np.float64), o["cld_cover_sw"].astype(np.float32))
+    np.testing.assert_allclose(e["aod_sw_ext"], o["aod_sw_ext"], rtol=2e-5)
+    night = st["cos_zenith"] <= 0
+    assert night.any() and np.abs(e["sw_dn"][night]).max() == 0.0
+
+
+@pytest.mark.parametrize("method,aerosols", [("clear_sky", False), ("all_sky", False), ("clear_sky", True)])
+def test_warp_specialised_kernels_variants_f32(real_pack, monkeypatch, method, aerosols):
+    """The (cloud, aerosol) template variants, an incident longwave flux and metric scaling."""
+    monkeypatch.setenv("RRTMGP_B200_KERNEL", "ws")
+    st = R.synthetic.make_atmosphere(200, 64, cld_frac=None, clouds=method != "clear_sky", aerosols=aerosols)
+    rng = np.random.default_rng(4)
+    st["inc_flux_lw"] = rng.uniform(0.0, 0.02, (256, 200)).astype(np.float32)
+    st["metric_scaling"] = np.linspace(1.0, 1.2, 200 * 65, dtype=np.float32).reshape(200, 65)
+    kw = dict(method=method, aerosols=aerosols, seed=5)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY if method != "clear_sky" else F32_SW_CLEAR, run_oracle(real_pack, st, np.float32, **kw))
+
+
+def test_warp_specialised_kernels_spectral_and_two_minor_groups_f32(monkeypatch):
+    """Per-band fluxes and the two-slot-group tables on the pipeline; broadband results equal a non-spectral run."""
+    monkeypatch.setenv("RRTMGP_B200_KERNEL", "ws")
+    pack = R.synthetic.make_lut_pack(seed=7, dims=R.synthetic.LutDims(minor_lower_lw=6, minor_lower_sw=5))
+    st = R.synthetic.make_atmosphere(96, 64, cld_frac=None, cos_zenith=None)
+    kw = dict(method="all_sky", aerosols=True, seed=8)
+    e = run_engine(pack, st, np.float32, spectral=True, **kw)
+    o = run_oracle(pack, st, np.float64, spectral=True, **kw)
+    o32 = run_oracle(pack, st, np.float32, spectral=True, **kw)
+    for k, tol in (("lw_band_up", F32_LW), ("lw_band_dn", F32_LW), ("sw_band_up", F32_SW_CLOUDY), ("sw_band_dn", F32_SW_CLOUDY)):
+        gate_f32(k, e[k], o[k], tol, o32[k], col_axis=1)
+    np.testing.assert_allclose(e["lw_band_up"].sum(0), e["lw_up"], rtol=2e-6)
+    plain = run_engine(pack, st, np.float32, **kw)
+    for k in FLUX_KEYS:
+        np.testing.assert_array_equal(e[k], plain[k], err_msg=k)
+    _check_f32(plain, o, F32_LW, F32_SW_CLOUDY, o32)
+
+
+def test_warp_specialised_kernels_match_single_role_kernels_f32(real_pack, monkeypatch):
+    """Same inputs through both kernel families: the differences are rounding only (the gas optics are the same
+    arithmetic; the longwave level source is formed by the other warp)."""
+    st = R.synthetic.make_atmosphere(512, 64, cld_frac=None, cos_zenith=None)
+    kw = dict(method="all_sky", aerosols=True, seed=31)
+    monkeypatch.delenv("RRTMGP_B200_KERNEL", raising=False)
+    a = run_engine(real_pack, st, np.float32, **kw)
+    monkeypatch.setenv("RRTMGP_B200_KERNEL", "ws")
+    b = run_engine(real_pack, st, np.float32, **kw)
+    for k in ("lw_up", "lw_dn"):
+        assert maxdiff(a[k], b[k]) <= F32_LW, k
+    for k in ("sw_up", "sw_dn", "sw_dir"):
+        assert maxdiff(a[k], b[k]) <= 1e-2, k
+    np.testing.assert_array_equal(a["cld_cover_sw"], b["cld_cover_sw"])
+    np.testing.assert_array_equal(a["aod_sw_ext"], b["aod_sw_ext"])
