@@ -60,15 +60,23 @@ __device__ __forceinline__ float pdiv(float a, float b) { return __fdiv_rn(a, b)
 __device__ __forceinline__ double pdiv(double a, double b) { return a / b; }
 // hot-loop forms
 __device__ __forceinline__ double hdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ double hrcp(double x) { return 1.0 / x; }
 __device__ __forceinline__ double hsqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ double hexp(double x) { return exp(x); }
 __device__ __forceinline__ double h_one_minus_exp_neg(double x, double) { return -expm1(-x); }
 #if RB_EXACT_MATH
+__device__ __forceinline__ float hrcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ float hdiv(float a, float b) { return a / b; }
 __device__ __forceinline__ float hsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ float hexp(float x) { return expf(x); }
 __device__ __forceinline__ float h_one_minus_exp_neg(float x, float) { return -expm1f(-x); }
 #else
+// reciprocal as ONE MUFU.RCP (div.approx of 1 by x costs an extra canonicalising FADD.FTZ)
+__device__ __forceinline__ float hrcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float hdiv(float a, float b) {
     float r;
     asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -200,7 +208,7 @@ __device__ __forceinline__ LwCoef lw_2stream_coeffs_nosrc(float tau, float ssa, 
     const float om1 = h_one_minus_exp_neg(tk, e1);
     const float one_p_e1 = 1.f + e1;
     const float one_minus_e2kt = om1 * one_p_e1;
-    const float RT_term = hdiv(1.f, k * fmaf(e1, e1, 1.f) + g1 * one_minus_e2kt);
+    const float RT_term = hrcp(k * fmaf(e1, e1, 1.f) + g1 * one_minus_e2kt);
     LwCoef c;
     c.Rdif = RT_term * g2 * one_minus_e2kt;
     c.Tdif = RT_term * 2.f * k * e1;
@@ -229,7 +237,7 @@ __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, 
     FT e2 = e * e;
     FT om1 = h_one_minus_exp_neg(tk, e);
     FT one_minus_e2kt = om1 * (FT(1) + e);
-    FT RT_term = hdiv(FT(1), k * (FT(1) + e2) + g1 * one_minus_e2kt);
+    FT RT_term = hrcp(k * (FT(1) + e2) + g1 * one_minus_e2kt);
     Rdif = RT_term * g2 * one_minus_e2kt;
     Tdif = RT_term * FT(2) * k * e;
     FT T0 = hexp(-tau * inv_mu0);                       // inv_mu0 = 1 / max(mu0, eps) (Numerics.jl:63)

@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
     const int nlay = P.nlay, nlev = nlay + 1;
     const FT* major = LWG ? L.kmaj_pf : L.kmajor;
     const float4* minor4 = reinterpret_cast<const float4*>(L.kminor4[0]);
-    const int RW = P.rec_words;
+    constexpr int RW = 20 + 4 * NG;                                   // words per band record (plan_smem_fast)
+    constexpr int RR = (((2 * RW) >> 2) & 1) ? 2 * RW : 2 * RW + 4;   // words per record row: 4 * odd
 
     // Columns are handed out by an atomic counter, in order, one at a time: night columns (SW) and cloud-free
     // columns cost a fraction of the others, and a static assignment leaves the time of a launch to the unluckiest
@@ -299,15 +300,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
 
             const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
             const FT* rec_lane = W.rec + bl * RW;          // this lane's band within a record row pair
-            const FT* major_lane = major + (LWG ? 2 : 1) * gpt;   // tables offset by this lane's g-point
-            const float4* minor_lane = minor4 + gpt;
+            // per-lane table bases (offset by this lane's g-point) as opaque 64-bit values: every gather base is then one
+            // IMAD.WIDE instead of a uniform base + lane offset re-added and sign-extended per address (profiles/r1r: 9
+            // integer instructions for the two minor-table bases)
+            auto opaque = [](const void* p) { unsigned long long v = (unsigned long long)p; asm("" : "+l"(v)); return v; };
+            const unsigned long long major_lane = opaque(major + (LWG ? 2 : 1) * gpt);
+            const unsigned long long minor_lane = opaque(minor4 + gpt);
             const unsigned mask0 = W.mask[0], mask1 = W.mask[1], mask2 = W.mask[NOWN - 1];   // (mask2 used when NOWN = 3)
+            auto mask_word = [&](int k) -> unsigned { return k < 32 ? mask0 : ((NOWN > 2 && k >= 64) ? mask2 : mask1); };
 
-            // ---- issue every load of cell (layer k, this g-point): compile-time strides, 64/128-bit gathers ----
-            auto gather = [&](int k, FastCell<LWG, NG>& G) {
-                const FT* r = rec_lane + (k & 31) * P.rec_row;
-                bool cb = false;
-                if (HAS_CLD) cb = ((k < 32 ? mask0 : ((NOWN > 2 && k >= 64) ? mask2 : mask1)) >> (k & 31)) & 1u;
+            // ---- issue every load of the cell whose band-record row is `r` (`cb`: cloudy in this g-point's McICA
+            //      sample): compile-time strides, 64/128-bit gathers ----
+            auto gather_r = [&](const FT* r, bool cb, FastCell<LWG, NG>& G) {
                 G.s = *reinterpret_cast<const float4*>(r + 8);
                 G.x = *reinterpret_cast<const float4*>(r + 12 + 4 * NG + (cb ? 4 : 0));
                 G.v0 = *reinterpret_cast<const float4*>(r);
@@ -322,16 +326,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     G.c2[0] = __ldg(pa); G.c2[1] = __ldg(pa + KE); G.c2[2] = __ldg(pa + KP); G.c2[3] = __ldg(pa + KP + KE);
                     G.c2[4] = __ldg(pb); G.c2[5] = __ldg(pb + KE); G.c2[6] = __ldg(pb + KP); G.c2[7] = __ldg(pb + KP + KE);
                 } else {
-                    const FT* pa = major_lane + ia;
-                    const FT* pb = major_lane + ib;
+                    const FT* pa = reinterpret_cast<const FT*>(major_lane) + ia;
+                    const FT* pb = reinterpret_cast<const FT*>(major_lane) + ib;
                     G.c1[0] = __ldg(pa); G.c1[1] = __ldg(pa + KE); G.c1[2] = __ldg(pa + KP); G.c1[3] = __ldg(pa + KP + KE);
                     G.c1[4] = __ldg(pb); G.c1[5] = __ldg(pb + KE); G.c1[6] = __ldg(pb + KP); G.c1[7] = __ldg(pb + KP + KE);
                 }
+                const float4* qa = reinterpret_cast<const float4*>(minor_lane) + ma;
+                const float4* qb = reinterpret_cast<const float4*>(minor_lane) + mb;
 #pragma unroll
                 for (int gi = 0; gi < NG; ++gi) {
-                    G.m[4 * gi + 0] = __ldg(minor_lane + ma + gi * MS); G.m[4 * gi + 1] = __ldg(minor_lane + ma + gi * MS + ME);
-                    G.m[4 * gi + 2] = __ldg(minor_lane + mb + gi * MS); G.m[4 * gi + 3] = __ldg(minor_lane + mb + gi * MS + ME);
+                    G.m[4 * gi + 0] = __ldg(qa + gi * MS); G.m[4 * gi + 1] = __ldg(qa + gi * MS + ME);
+                    G.m[4 * gi + 2] = __ldg(qb + gi * MS); G.m[4 * gi + 3] = __ldg(qb + gi * MS + ME);
                 }
+            };
+            auto gather = [&](int k, FastCell<LWG, NG>& G) {
+                bool cb = false;
+                if (HAS_CLD) cb = (mask_word(k) >> (k & 31)) & 1u;
+                gather_r(rec_lane + (k & 31) * RR, cb, G);
             };
             // ---- gas + cloud + aerosol optics of the gathered cell (gas_optics.jl:176-320, optics_utils.jl:85-181) ----
             auto finish = [&](const FastCell<LWG, NG>& G, FT& tau, FT& ssa, FT& g, FT& pfrac) {
@@ -445,15 +456,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 for (int k0 = 0; k0 < nlay; k0 += 16) {                 // tiles of <= 16 interfaces k
                     const int ks = k0 > 0 ? k0 : 1, ke = k0 + 16 < nlay ? k0 + 16 : nlay;
                     if (k0 > 0 && (k0 & 31) == 0) build_records(k0 >> 5);   // next 32 layers' records
+                    // record row, McICA bit, Planck value and staging row of layer k advance by increments
+                    const FT* rk = rec_lane + (ks & 31) * RR;
+                    unsigned mw = HAS_CLD ? mask_word(ks) >> (ks & 31) : 0u;
+                    const FT* pk = pbk + ks;
+                    FT* sk = stage + lane;
                     for (int k = ks; k < ke; ++k) {                       // single basic block
-                        gather(k, G);
+                        gather_r(rk, mw & 1u, G);
                         const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
-                        const FT denom = hdiv(1.f, 1.f - C.Rdif * albedo);
-                        const FT bk = pbk[k];
+                        const FT denom = hrcp(1.f - C.Rdif * albedo);
+                        const FT bk = *pk;
                         const FT inc_k = bk * pf;
                         finish(G, tau, ssa, g, pf);
                         const FT lev_top = hsqrt(inc_k * (bk * pf));
-                        stage[(k - ks) * kStageStride + lane] = close_layer(k - 1, C, denom, lev_top);
+                        *sk = close_layer(k - 1, C, denom, lev_top);
+                        rk += RR; mw >>= 1; ++pk; sk += kStageStride;
                     }
                     __syncwarp();
                     {                                                     // sum_g src of levels ks-1 .. ke-2
@@ -466,7 +483,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 }
                 {   // top layer: its upper source is its own increment (compute_optical_props.jl:193-195)
                     const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
-                    const FT denom = hdiv(1.f, 1.f - C.Rdif * albedo);
+                    const FT denom = hrcp(1.f - C.Rdif * albedo);
                     const FT s_top = close_layer(nlay - 1, C, denom, pbk[nlay] * pf);
                     FT hs;
                     const FT ssum = warp_sum2(s_top, hs);
@@ -679,7 +696,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     FT Rdir, Tdir, Rdif, Tdif;
                     sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
                     const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
-                    const FT denom = hdiv(1.f, 1.f - Rdif * beta);
+                    const FT denom = hrcp(1.f - Rdif * beta);
                     // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
                     tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
                     st_alpha(k, beta);
@@ -695,11 +712,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 for (int jc = (nlay - 2) & ~7; jc >= 0; jc -= 8) {     // 8 layers x (d_{k+1}, dir_k) per tile, k = j + 1
                     if ((jc & 31) == 24 && jc + 8 < nlay) build_records(jc >> 5);   // next 32 layers down
                     const int jtop = jc + 7 < nlay - 2 ? jc + 7 : nlay - 2;
+                    const FT* rk = rec_lane + (jtop & 31) * RR;
+                    unsigned mw = HAS_CLD ? mask_word(jtop) << (31 - (jtop & 31)) : 0u;   // bit 31 = layer j
+                    FT* sk = stage + ((jtop - jc) * 2) * kStageStride + lane;
                     for (int j = jtop; j >= jc; --j) {                  // single basic block
-                        gather(j, G);
-                        stage[((j - jc) * 2 + 0) * kStageStride + lane] = march(j + 1);
-                        stage[((j - jc) * 2 + 1) * kStageStride + lane] = dir;
+                        gather_r(rk, (mw >> 31) & 1u, G);
+                        sk[0] = march(j + 1);
+                        sk[kStageStride] = dir;
                         finish(G, tau, ssa, g, pf);
+                        rk -= RR; mw <<= 1; sk -= 2 * kStageStride;
                     }
                     __syncwarp();
                     {
