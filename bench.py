@@ -6,8 +6,9 @@
 One process per GPU (torchrun for N > 1; RANK / LOCAL_RANK / WORLD_SIZE from the env).  A "step" is one
 full `update_fluxes!` (prepare_atmosphere! + LW two-stream + SW two-stream + net flux, clouds with McICA,
 15-species aerosols) over one batch of synthetic columns (seeded generator).  Columns shard
-across ranks (weak scaling: `--ncol` columns PER GPU); for N > 1 the step ends with the NCCL all-gather of
-the eight (nlev, ncol) flux views (north star).
+across ranks (weak scaling: `--ncol` columns PER GPU); for N > 1 the step is `update_fluxes_gathered` of the C ABI:
+the all-gather of the eight (nlev, ncol) flux views (north star) pushed over NVLink by the copy
+engines while the shortwave kernel still runs, framed by two one-element NCCL all-reduces.
 
 Rank 0 prints ONE JSON line.  `value` = whole-job columns/s with inputs resident in HBM; `e2e` = the same
 step driven from pinned HOST buffers (H2D of every input + D2H of every flux inside the timed region);
@@ -44,7 +45,8 @@ def config_of(ncol, nlay, world):
     """The `config` object of both arms (engine and `--impl reference`): same keys, same workload string."""
     in_bytes = ncol * ((nlay * 4 + nlay * 2 + nlay * 5 + 2 * nlay * 15) * 4 + 400)
     return {"workload": workload_name(ncol, nlay), "global_columns": world * ncol,
-            "parallelism": f"column shards x{world}" + (", NCCL all-gather of 8 flux views" if world > 1 else ""),
+            "parallelism": f"column shards x{world}" + (", all-gather of 8 flux views (copy-engine pushes over NVLink + NCCL fences, "
+                                                        "rrtmgp_b200_update_fluxes_gathered)" if world > 1 else ""),
             "l2_policy": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"}
 
 
@@ -195,6 +197,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
@@ -225,18 +228,20 @@ def main():
     s.set_state(st)
     R.compute_relative_humidity(s)
 
-    flux_keys = ("lw_flux_up", "lw_flux_dn", "lw_flux_net", "sw_flux_up", "sw_flux_dn", "sw_flux_net",
-                 "sw_flux_dn_dir", "net_flux")
-    gathered = None
-    if world > 1:   # (nlev, ncol) views are contiguous per shard: one all-gather per array, grouped
-        gathered = {k: torch.empty(world * ncol, nlev, dtype=torch.float32, device=dev) for k in flux_keys}
+    def join(solver):
+        """Every rank joins the engine's own communicator (NCCL id created by rank 0, shipped through torch.distributed)."""
+        box = [R.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        R.comm_init(solver, box[0], rank, world)
+
+    if world > 1:
+        join(s)
 
     def step(seed):
-        R.update_fluxes(s, seed)
         if world > 1:
-            works = [dist.all_gather_into_tensor(gathered[k], s.buffers[k], async_op=True) for k in flux_keys]
-            for w in works:
-                w.wait()
+            R.update_fluxes_gathered(s, seed)   # compute + all-gather of the eight (nlev, ncol) views, overlapped
+        else:
+            R.update_fluxes(s, seed)
 
     def barrier():
         if world > 1:
@@ -332,25 +337,50 @@ def main():
 
     # --- e2e: the state lives in pinned HOST memory; every step copies every per-column input H2D, runs
     # update_fluxes! and copies every flux / diagnostic D2H (HostPipeline: column chunks on 3 streams) ---
-    e2e = None
+    e2e, pipe = None, None
     if not args.no_e2e:
         pipe = R.HostPipeline(s, n_chunks=args.e2e_chunks)
         pipe.load_host_inputs(st)
         pipe.host_in["layerdata"].copy_(s.buffers["layerdata"].cpu())   # rel_hum computed above
+        def e2e_step(seed):
+            pipe.update_fluxes(seed)            # H2D of every input, update_fluxes!, D2H of every flux (column chunks)
+            if world > 1:
+                R.all_gather_fluxes(s)          # + the gather of the eight views (grouped ncclAllGather)
+                torch.cuda.synchronize()
         for i in range(2):
-            pipe.update_fluxes(i)
+            e2e_step(i)
         barrier()
         n_e2e = max(2, min(args.steps, 5))
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            pipe.update_fluxes(300 + i)
+            e2e_step(300 + i)
         torch.cuda.synchronize()
         dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        # the host-side ceiling of this leg: all ranks copy their inputs H2D at the same time, nothing else running
+        barrier()
+        t0 = time.perf_counter()
+        for k in pipe.in_keys:
+            s.buffers[k].copy_(pipe.host_in[k], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(h2d, op=dist.ReduceOp.MAX)
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            affinity = f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)"
+        except Exception:
+            affinity = None
         e2e = {"value": world * ncol / float(dt.item()), "unit": "columns/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": float(dt.item()) * 1e3,
-               "how": f"HostPipeline: {len(pipe.chunks)} column chunks on {len(pipe.streams)} CUDA streams, pinned host buffers"}
+               "includes_gather": world > 1,
+               "h2d_only_ms": float(h2d.item()) * 1e3,
+               "h2d_only_gbs_per_rank": pipe.h2d_bytes / float(h2d.item()) / 1e9,
+               "h2d_only_gbs_all_ranks": world * pipe.h2d_bytes / float(h2d.item()) / 1e9,
+               "host_cpu_affinity_rank0": affinity,
+               "how": f"HostPipeline: {len(pipe.chunks)} column chunks on {len(pipe.streams)} CUDA streams, pinned host buffers"
+                      + ("; then the grouped ncclAllGather of the 8 views" if world > 1 else "")}
 
     # --- SURVEY §8d variants of the same workload, reported beside the headline (device-resident, rank 0 of a
     # 1-GPU run only): day/night mix cos_zenith ~ U(-0.2, 1) (about 17 % night columns skip the SW solve) and
@@ -366,6 +396,40 @@ def main():
             ms_v = time_call(lambda i: R.update_fluxes(s, 300 + i), 3)
             variants[name] = {"value": ncol / (ms_v * 1e-3), "unit": "columns/s", "ms_per_step": ms_v}
             s.buffers["cos_zenith"].copy_(base_cz); s.buffers["cld_frac"].copy_(base_cf)
+
+    # --- BASELINE config 5: weak-scaling sweep ncol/GPU = 1e4 .. 1e6 (device-timed, inputs resident, gather included
+    # for N > 1); the 1e5-column synthetic state is tiled on the device for the larger points ---
+    sweep = None
+    if not args.no_sweep:
+        sweep = []
+        del pipe
+        base = {k: v for k, v in s.buffers.items() if v is not None and v.dim() >= 1 and v.shape[0] == ncol}
+        for n_sw in (10_000, 30_000, 100_000, 300_000, 1_000_000):
+            if n_sw == ncol:
+                sweep.append({"ncol_per_gpu": n_sw, "value": value, "unit": "columns/s", "ms_per_step": ms})
+                continue
+            gp2 = R.RRTMGPGridParams(FT=np.float32, domain_nlay=nlay, ncol=n_sw, device=local_rank)
+            s2 = R.RRTMGPSolver(gp2, rm, R.default_parameters(**PARAMS), pack, col_offset=rank * n_sw)
+            for k, v in base.items():
+                dst = s2.buffers[k]
+                for a in range(0, n_sw, ncol):
+                    m = min(ncol, n_sw - a)
+                    dst[a:a + m].copy_(v[:m])
+            s2.buffers["vmr"].copy_(s.buffers["vmr"])
+            if world > 1:
+                join(s2)
+            fn = (lambda i: R.update_fluxes_gathered(s2, 400 + i)) if world > 1 else (lambda i: R.update_fluxes(s2, 400 + i))
+            fn(0)
+            barrier()
+            ms_s = torch.tensor([time_call(fn, 3)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+            sweep.append({"ncol_per_gpu": n_sw, "value": world * n_sw / (float(ms_s.item()) * 1e-3), "unit": "columns/s",
+                          "ms_per_step": float(ms_s.item())})
+            if world > 1:
+                R.comm_destroy(s2)
+            del s2
+            torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -389,7 +453,7 @@ def main():
                 "config": config_of(ncol, nlay, world),
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_fp32": roofline_fp32, "roofline_issue": roofline_issue, "cpu_baseline": cpu_baseline,
-                "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants}
+                "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants, "sweep": sweep}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -214,6 +214,35 @@ typedef enum {
 } rrtmgp_b200_invalid_input;
 int rrtmgp_b200_validate_inputs(rrtmgp_b200_handle_t* h, uint32_t* failed, void* stream);
 
+/* ---- multi-GPU: column shards across the ranks of one box, one process per GPU ----
+ * The reference has no multi-GPU path (docs/src/howto/gpu.md:69-84: one device per process, the host model
+ * decomposes the columns); what a sharded host needs beyond its own shard is the concatenation of the presented
+ * (nlev, ncol) flux views (getters.jl:320-470), i.e. one all-gather per view.  Because `ncol` is the slowest axis
+ * of every view, rank r's result is rows [r ncol, (r + 1) ncol) of the gathered array.
+ *
+ *   comm_unique_id   rank 0 creates the NCCL id; the host ships its 128 bytes to every rank (MPI_Bcast, a file, ...).
+ *   comm_init        joins the communicator (libnccl.so.2 is dlopen'ed: the library has no link-time dependency),
+ *                    allocates the gathered arrays ([nranks ncol][nlev] each, 8 of them: rrtmgp_b200_gathered_t),
+ *                    and opens every peer's copy through CUDA IPC so results can be pushed over NVLink by the copy
+ *                    engines.  Every rank must use the same ncol, nlay and dtype.
+ *   update_fluxes_gathered   update_fluxes! + the gather, overlapped: the three longwave views travel while the
+ *                    shortwave kernel runs, the shortwave / net views per column chunk as it finishes; copies are
+ *                    cudaMemcpyAsync on a side stream (DMA engines -- the persistent kernels leave no SM for a
+ *                    collective kernel), framed by two one-element NCCL all-reduces (nobody still reads the previous
+ *                    step's arrays / everybody's pushes have landed).  On return (stream order) every rank holds all
+ *                    columns.
+ *   all_gather_fluxes   the plain alternative: one grouped ncclAllGather of the eight views as they are now. */
+typedef struct {
+    void *lw_flux_up, *lw_flux_dn, *lw_flux_net, *sw_flux_up, *sw_flux_dn, *sw_flux_net, *sw_flux_dn_dir, *net_flux;
+} rrtmgp_b200_gathered_t;
+#define RRTMGP_B200_UNIQUE_ID_BYTES 128
+int rrtmgp_b200_comm_unique_id(void* id_out, size_t nbytes);
+int rrtmgp_b200_comm_init(rrtmgp_b200_handle_t* h, const void* unique_id, int32_t rank, int32_t nranks);
+int rrtmgp_b200_gathered_buffers(const rrtmgp_b200_handle_t* h, rrtmgp_b200_gathered_t* out);
+int rrtmgp_b200_update_fluxes_gathered(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream);
+int rrtmgp_b200_all_gather_fluxes(rrtmgp_b200_handle_t* h, void* stream);
+int rrtmgp_b200_comm_destroy(rrtmgp_b200_handle_t* h);
+
 /* Measurement aid (no reference counterpart): FP32 CUDA-core peak of `device` from a stream of
  * independent scalar FFMA and of packed FFMA2, in TFLOP/s -- the denominator bench.py reports `roofline_fp32` against.
  * Synchronous; a few milliseconds. */

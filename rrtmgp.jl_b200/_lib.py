@@ -47,6 +47,14 @@ class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BUFFER_FIELDS]
 
 
+GATHERED_FIELDS = ("lw_flux_up", "lw_flux_dn", "lw_flux_net", "sw_flux_up", "sw_flux_dn", "sw_flux_net", "sw_flux_dn_dir", "net_flux")
+UNIQUE_ID_BYTES = 128
+
+
+class Gathered(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in GATHERED_FIELDS]
+
+
 class LutInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_gpt_lw", "n_bnd_lw", "n_gpt_sw", "n_bnd_sw", "ngas", "iband_550nm")] + [
         (n, C.c_double) for n in ("p_ref_min", "t_ref_min", "t_ref_max", "solar_src_tot")]
@@ -63,6 +71,8 @@ EXPORTS = ("rrtmgp_b200_create", "rrtmgp_b200_destroy", "rrtmgp_b200_load_luts",
            "rrtmgp_b200_update_fluxes_range",
            "rrtmgp_b200_set_level_interpolation", "rrtmgp_b200_heating_rate",
            "rrtmgp_b200_compute_relative_humidity", "rrtmgp_b200_validate_inputs", "rrtmgp_b200_measure_fp32_peak",
+           "rrtmgp_b200_comm_unique_id", "rrtmgp_b200_comm_init", "rrtmgp_b200_gathered_buffers",
+           "rrtmgp_b200_update_fluxes_gathered", "rrtmgp_b200_all_gather_fluxes", "rrtmgp_b200_comm_destroy",
            "rrtmgp_b200_last_launch_count",
            "rrtmgp_b200_last_cuda_error", "rrtmgp_b200_strerror", "rrtmgp_b200_abi_version")
 
@@ -102,6 +112,12 @@ def lib():
         L.rrtmgp_b200_compute_relative_humidity.argtypes = [H, C.c_void_p]
         L.rrtmgp_b200_set_level_interpolation.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.rrtmgp_b200_heating_rate.argtypes = [H, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.rrtmgp_b200_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+        L.rrtmgp_b200_comm_init.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32]
+        L.rrtmgp_b200_gathered_buffers.argtypes = [H, C.POINTER(Gathered)]
+        L.rrtmgp_b200_update_fluxes_gathered.argtypes = [H, C.c_uint64, C.c_int, C.c_void_p]
+        L.rrtmgp_b200_all_gather_fluxes.argtypes = [H, C.c_void_p]
+        L.rrtmgp_b200_comm_destroy.argtypes = [H]
         L.rrtmgp_b200_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rrtmgp_b200_last_launch_count.argtypes = [H]
         L.rrtmgp_b200_last_cuda_error.argtypes = [H]

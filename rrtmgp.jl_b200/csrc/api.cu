@@ -2,6 +2,8 @@
 // orchestration of src/api/update_fluxes.jl on a CUDA stream.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -12,7 +14,37 @@
 
 using namespace rb;
 
+// ---- multi-GPU state (rrtmgp_b200_comm_*): NCCL through dlopen (types restated from nccl.h 2.27: the library has no
+// link-time dependency on it), the gathered arrays and every peer's copy of them (CUDA IPC) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { kNcclChar = 0, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kMaxRanks = 16, kGatheredViews = 8;
+struct CommState {
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr}, ev_copied = nullptr;
+    unsigned char* gathered = nullptr;       // this rank's 8 arrays, [view][nranks * ncol][nlev]
+    size_t view_bytes = 0;                   // bytes of one gathered view
+    unsigned char* peer[kMaxRanks] = {};     // every rank's `gathered` as mapped here (peer[rank] == gathered)
+    float* token = nullptr;                  // 2 floats for the framing all-reduces
+};
+
 struct rrtmgp_b200_handle {
+    CommState* comm = nullptr;
     rrtmgp_b200_config_t cfg;
     rrtmgp_b200_buffers_t buf;
     bool bound = false;
@@ -512,6 +544,7 @@ int rrtmgp_b200_create(const rrtmgp_b200_config_t* cfg, rrtmgp_b200_handle_t** o
 
 void rrtmgp_b200_destroy(rrtmgp_b200_handle_t* h) {
     if (!h) return;
+    rrtmgp_b200_comm_destroy(h);
     DeviceGuard g(h->cfg.device);
     free_lut_store(h->luts);
     if (h->work_counters) cudaFree(h->work_counters);
@@ -728,6 +761,215 @@ int rrtmgp_b200_validate_inputs(rrtmgp_b200_handle_t* h, uint32_t* failed, void*
     if (st) return st;
     DeviceGuard g(h->cfg.device);
     return h->cfg.dtype == 1 ? validate_t<double>(h, failed, (cudaStream_t)stream) : validate_t<float>(h, failed, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// multi-GPU (include/rrtmgp_b200.h "multi-GPU")
+// ------------------------------------------------------------------------------------------------------------------
+static bool load_nccl(NcclApi& n) {
+    if (n.lib) return true;
+    // libnccl.so.2 is already mapped when the host uses torch.distributed / NCCL.jl; otherwise the loader path decides
+    n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.lib) n.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.lib) return false;
+#define RB_NCCL_SYM(field, name) n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.lib, name)); if (!n.field) return false;
+    RB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") RB_NCCL_SYM(CommInitRank, "ncclCommInitRank") RB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    RB_NCCL_SYM(AllGather, "ncclAllGather") RB_NCCL_SYM(AllReduce, "ncclAllReduce") RB_NCCL_SYM(GroupStart, "ncclGroupStart")
+    RB_NCCL_SYM(GroupEnd, "ncclGroupEnd") RB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef RB_NCCL_SYM
+    return true;
+}
+
+static int fail_nccl(rrtmgp_b200_handle* h, const NcclApi& n, int rc) {
+    std::snprintf(h->cuda_err, sizeof(h->cuda_err), "NCCL: %s", n.GetErrorString ? n.GetErrorString(rc) : "error");
+    return RRTMGP_B200_ERR_CUDA;
+}
+
+// the eight local flux views in the order of rrtmgp_b200_gathered_t
+static void local_views(const rrtmgp_b200_handle* h, void* v[kGatheredViews]) {
+    const rrtmgp_b200_buffers_t& B = h->buf;
+    void* t[kGatheredViews] = {B.lw_flux_up, B.lw_flux_dn, B.lw_flux_net, B.sw_flux_up, B.sw_flux_dn, B.sw_flux_net, B.sw_flux_dn_dir, B.net_flux};
+    for (int i = 0; i < kGatheredViews; ++i) v[i] = t[i];
+}
+
+int rrtmgp_b200_comm_unique_id(void* id_out, size_t nbytes) {
+    if (!id_out || nbytes < RRTMGP_B200_UNIQUE_ID_BYTES) return RRTMGP_B200_ERR_INVALID_ARG;
+    NcclApi n;
+    if (!load_nccl(n)) return RRTMGP_B200_ERR_UNSUPPORTED;
+    ncclUniqueId id;
+    if (n.GetUniqueId(&id) != 0) return RRTMGP_B200_ERR_CUDA;
+    std::memcpy(id_out, id.internal, sizeof(id.internal));
+    return RRTMGP_B200_OK;
+}
+
+int rrtmgp_b200_comm_destroy(rrtmgp_b200_handle_t* h) {
+    if (!h) return RRTMGP_B200_ERR_INVALID_ARG;
+    CommState* c = h->comm;
+    if (!c) return RRTMGP_B200_OK;
+    DeviceGuard g(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->nranks; ++p)
+        if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+    if (c->comm) c->nccl.CommDestroy(c->comm);
+    if (c->gathered) cudaFree(c->gathered);
+    if (c->token) cudaFree(c->token);
+    for (auto& e : c->ev_kernel) if (e) cudaEventDestroy(e);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+    h->comm = nullptr;
+    return RRTMGP_B200_OK;
+}
+
+int rrtmgp_b200_comm_init(rrtmgp_b200_handle_t* h, const void* unique_id, int32_t rank, int32_t nranks) {
+    if (!h || !unique_id || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (h->comm) return RRTMGP_B200_ERR_INVALID_ARG;   // one communicator per handle
+    DeviceGuard g(h->cfg.device);
+    CommState* c = new (std::nothrow) CommState();
+    if (!c) return RRTMGP_B200_ERR_INVALID_ARG;
+    h->comm = c;
+    c->rank = rank; c->nranks = nranks;
+    auto bail = [&](int code) { rrtmgp_b200_comm_destroy(h); return code; };
+    if (!load_nccl(c->nccl)) { std::snprintf(h->cuda_err, sizeof(h->cuda_err), "libnccl.so.2 not found"); return bail(RRTMGP_B200_ERR_UNSUPPORTED); }
+    ncclUniqueId id;
+    std::memcpy(id.internal, unique_id, sizeof(id.internal));
+    int rc = c->nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (rc != 0) { fail_nccl(h, c->nccl, rc); return bail(RRTMGP_B200_ERR_CUDA); }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (auto& ev : c->ev_kernel) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming);
+    const size_t esz = h->cfg.dtype == 1 ? 8 : 4;
+    c->view_bytes = (size_t)nranks * h->cfg.ncol * (h->cfg.nlay + 1) * esz;
+    // an allocation of its own (cudaMalloc, not a pool): CUDA IPC exports whole allocations
+    if (e == cudaSuccess) e = cudaMalloc(&c->gathered, kGatheredViews * c->view_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->gathered, 0, kGatheredViews * c->view_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->token, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->token, 0, 2 * sizeof(float));
+    if (e != cudaSuccess) { fail_cuda(h, e); return bail(RRTMGP_B200_ERR_CUDA); }
+    // exchange (IPC handle, ncol, nlay, dtype) of every rank through the communicator itself
+    struct Card { cudaIpcMemHandle_t handle; int32_t ncol, nlay, dtype, pad; };
+    static_assert(sizeof(Card) % 8 == 0, "card is exchanged as bytes");
+    Card mine{};
+    e = cudaIpcGetMemHandle(&mine.handle, c->gathered);
+    mine.ncol = h->cfg.ncol; mine.nlay = h->cfg.nlay; mine.dtype = h->cfg.dtype;
+    Card* d_cards = nullptr;
+    Card cards[kMaxRanks];
+    if (e == cudaSuccess) e = cudaMalloc(&d_cards, nranks * sizeof(Card));
+    if (e == cudaSuccess) e = cudaMemcpy(d_cards + rank, &mine, sizeof(Card), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { if (d_cards) cudaFree(d_cards); fail_cuda(h, e); return bail(RRTMGP_B200_ERR_CUDA); }
+    rc = c->nccl.AllGather(d_cards + rank, d_cards, sizeof(Card), kNcclChar, c->comm, c->copy_stream);
+    if (rc == 0) e = cudaStreamSynchronize(c->copy_stream);
+    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(cards, d_cards, nranks * sizeof(Card), cudaMemcpyDeviceToHost);
+    cudaFree(d_cards);
+    if (rc != 0) { fail_nccl(h, c->nccl, rc); return bail(RRTMGP_B200_ERR_CUDA); }
+    if (e != cudaSuccess) { fail_cuda(h, e); return bail(RRTMGP_B200_ERR_CUDA); }
+    for (int p = 0; p < nranks; ++p) {
+        if (cards[p].ncol != mine.ncol || cards[p].nlay != mine.nlay || cards[p].dtype != mine.dtype) {
+            std::snprintf(h->cuda_err, sizeof(h->cuda_err), "rank %d has ncol/nlay/dtype %d/%d/%d, this rank %d/%d/%d", p, cards[p].ncol,
+                          cards[p].nlay, cards[p].dtype, mine.ncol, mine.nlay, mine.dtype);
+            return bail(RRTMGP_B200_ERR_INVALID_ARG);
+        }
+        if (p == rank) { c->peer[p] = c->gathered; continue; }
+        void* mapped = nullptr;
+        e = cudaIpcOpenMemHandle(&mapped, cards[p].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { fail_cuda(h, e); return bail(RRTMGP_B200_ERR_CUDA); }
+        c->peer[p] = (unsigned char*)mapped;
+    }
+    return RRTMGP_B200_OK;
+}
+
+int rrtmgp_b200_gathered_buffers(const rrtmgp_b200_handle_t* h, rrtmgp_b200_gathered_t* out) {
+    if (!h || !out) return RRTMGP_B200_ERR_INVALID_ARG;
+    if (!h->comm || !h->comm->gathered) return RRTMGP_B200_ERR_NOT_READY;
+    void** o = reinterpret_cast<void**>(out);
+    for (int v = 0; v < kGatheredViews; ++v) o[v] = h->comm->gathered + v * h->comm->view_bytes;
+    return RRTMGP_B200_OK;
+}
+
+// one-element all-reduce on `s`: a rank passes it only when every rank has reached it (stream order)
+static int comm_fence(rrtmgp_b200_handle* h, int which, cudaStream_t s) {
+    CommState* c = h->comm;
+    int rc = c->nccl.AllReduce(c->token + which, c->token + which, 1, kNcclFloat32, kNcclSum, c->comm, s);
+    return rc == 0 ? RRTMGP_B200_OK : fail_nccl(h, c->nccl, rc);
+}
+
+// push rows [c0, c0 + count) of the local views [first, last) into every rank's gathered arrays (copy engines)
+static cudaError_t push_views(rrtmgp_b200_handle* h, int first, int last, long long c0, int count) {
+    CommState* c = h->comm;
+    const size_t esz = h->cfg.dtype == 1 ? 8 : 4, row = (size_t)(h->cfg.nlay + 1) * esz;
+    void* v[kGatheredViews];
+    local_views(h, v);
+    for (int p = 0; p < c->nranks; ++p) {
+        const int peer = (c->rank + p) % c->nranks;      // own copy first, then a different first peer per rank
+        for (int i = first; i < last; ++i) {
+            if (!v[i]) continue;
+            unsigned char* dst = c->peer[peer] + i * c->view_bytes + ((size_t)c->rank * h->cfg.ncol + c0) * row;
+            const unsigned char* src = (const unsigned char*)v[i] + (size_t)c0 * row;
+            cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)count * row, cudaMemcpyDeviceToDevice, c->copy_stream);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
+}
+
+int rrtmgp_b200_update_fluxes_gathered(rrtmgp_b200_handle_t* h, uint64_t seed, int have_seed, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    if (!h->comm) return RRTMGP_B200_ERR_NOT_READY;
+    if (!h->buf.net_flux) return RRTMGP_B200_ERR_INVALID_ARG;
+    DeviceGuard g(h->cfg.device);
+    CommState* c = h->comm;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool f64 = h->cfg.dtype == 1;
+    const unsigned long long sd = effective_seed(h, seed, have_seed);
+    const int ncol = h->cfg.ncol;
+    h->last_launches = 0;
+    // nobody may still be reading the arrays of the previous step when the first push lands
+    if ((st = comm_fence(h, 0, s))) return st;
+    st = f64 ? prepare_t<double>(h, 0, ncol, s) : prepare_t<float>(h, 0, ncol, s);
+    if (!st) st = f64 ? solve_lw_t<double>(h, sd, 0, ncol, s) : solve_lw_t<float>(h, sd, 0, ncol, s);
+    if (st) return st;
+    cudaError_t e = cudaEventRecord(c->ev_kernel[0], s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_kernel[0], 0);
+    if (e == cudaSuccess) e = push_views(h, 0, 3, 0, ncol);                 // longwave views travel under the shortwave kernel
+    if (e != cudaSuccess) return fail_cuda(h, e);
+    // shortwave (+ net) in column chunks of whole waves of the persistent kernel; a chunk travels while the next one runs
+    const int wave = 12 * (h->sm_count > 0 ? h->sm_count : 148);
+    int nchunk = (h->cfg.spectral_fluxes || ncol < 4 * wave) ? 1 : 3;
+    long long c0 = 0;
+    for (int i = 0; i < nchunk; ++i) {
+        long long c1 = i + 1 == nchunk ? ncol : (long long)((ncol * (long long)(i + 1) / nchunk) / wave) * wave;
+        if (c1 <= c0) continue;
+        st = f64 ? solve_sw_t<double>(h, sd, true, c0, (int)(c1 - c0), s) : solve_sw_t<float>(h, sd, true, c0, (int)(c1 - c0), s);
+        if (st) return st;
+        e = cudaEventRecord(c->ev_kernel[1 + i], s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_kernel[1 + i], 0);
+        if (e == cudaSuccess) e = push_views(h, 3, kGatheredViews, c0, (int)(c1 - c0));
+        if (e != cudaSuccess) return fail_cuda(h, e);
+        c0 = c1;
+    }
+    e = cudaEventRecord(c->ev_copied, c->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_copied, 0);
+    if (e != cudaSuccess) return fail_cuda(h, e);
+    return comm_fence(h, 1, s);                                             // everybody's pushes have landed
+}
+
+int rrtmgp_b200_all_gather_fluxes(rrtmgp_b200_handle_t* h, void* stream) {
+    int st = ready(h);
+    if (st) return st;
+    if (!h->comm) return RRTMGP_B200_ERR_NOT_READY;
+    DeviceGuard g(h->cfg.device);
+    CommState* c = h->comm;
+    void* v[kGatheredViews];
+    local_views(h, v);
+    const size_t n = (size_t)h->cfg.ncol * (h->cfg.nlay + 1);
+    int rc = c->nccl.GroupStart();
+    for (int i = 0; i < kGatheredViews && rc == 0; ++i)
+        if (v[i]) rc = c->nccl.AllGather(v[i], c->gathered + i * c->view_bytes, n, h->cfg.dtype == 1 ? kNcclFloat64 : kNcclFloat32, c->comm,
+                                         (cudaStream_t)stream);
+    const int rc2 = c->nccl.GroupEnd();
+    if (rc != 0 || rc2 != 0) return fail_nccl(h, c->nccl, rc != 0 ? rc : rc2);
+    return RRTMGP_B200_OK;
 }
 
 int rrtmgp_b200_last_launch_count(const rrtmgp_b200_handle_t* h) { return h ? h->last_launches : 0; }

@@ -299,6 +299,53 @@ def update_fluxes_range(s: RRTMGPSolver, seedval: int, col_begin: int, col_count
                                                 col_count, st), s._h)
 
 
+# -- multi-GPU: column shards, one process per GPU (include/rrtmgp_b200.h "multi-GPU"; sharding.py) ---------------
+class _DevicePtr:
+    """A device allocation owned by librrtmgp_b200.so, exposed to torch through `__cuda_array_interface__`."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def comm_unique_id() -> bytes:
+    """The NCCL id rank 0 creates and ships to every rank (`rrtmgp_b200_comm_unique_id`)."""
+    buf = (C.c_char * _lib.UNIQUE_ID_BYTES)()
+    check(lib().rrtmgp_b200_comm_unique_id(buf, _lib.UNIQUE_ID_BYTES))
+    return bytes(buf)
+
+
+def comm_init(s: RRTMGPSolver, unique_id: bytes, rank: int, nranks: int) -> Dict[str, torch.Tensor]:
+    """Joins the communicator and returns the gathered `(nlev, nranks * ncol)` flux views of this rank
+    (`[nranks * ncol, nlev]` tensors over memory the library owns; also kept as `s.gathered`)."""
+    if len(unique_id) != _lib.UNIQUE_ID_BYTES:
+        raise ValueError(f"unique_id must be {_lib.UNIQUE_ID_BYTES} bytes")
+    check(lib().rrtmgp_b200_comm_init(s._h, unique_id, rank, nranks), s._h)
+    g = _lib.Gathered()
+    check(lib().rrtmgp_b200_gathered_buffers(s._h, C.byref(g)), s._h)
+    shape = (nranks * s.grid_params.ncol, s.grid_params.nlay + 1)
+    typestr = "<f8" if s.dtype == np.float64 else "<f4"
+    s.gathered = {k: torch.as_tensor(_DevicePtr(getattr(g, k), shape, typestr), device=s.device) for k in _lib.GATHERED_FIELDS}
+    s.comm_rank, s.comm_nranks = rank, nranks
+    return s.gathered
+
+
+def update_fluxes_gathered(s: RRTMGPSolver, seedval=None) -> None:
+    """`update_fluxes!` on this rank's columns + the all-gather of the eight flux views into `s.gathered`, overlapped
+    (longwave views travel under the shortwave kernel; copy engines over NVLink)."""
+    seed, have = _seed_args(s, seedval)
+    check(lib().rrtmgp_b200_update_fluxes_gathered(s._h, seed, have, s._stream()), s._h)
+
+
+def all_gather_fluxes(s: RRTMGPSolver) -> None:
+    """One grouped ncclAllGather of the eight local flux views into `s.gathered` (no compute)."""
+    check(lib().rrtmgp_b200_all_gather_fluxes(s._h, s._stream()), s._h)
+
+
+def comm_destroy(s: RRTMGPSolver) -> None:
+    s.gathered = None
+    check(lib().rrtmgp_b200_comm_destroy(s._h), s._h)
+
+
 INPUT_KEYS = ("layerdata", "p_lev", "t_lev", "t_sfc", "vmr_h2o", "vmr_o3", "cld_r_eff_liq", "cld_r_eff_ice",
               "cld_path_liq", "cld_path_ice", "cld_frac", "aero_mass", "aero_size", "sfc_emis", "cos_zenith", "toa_flux",
               "sfc_alb_direct", "sfc_alb_diffuse", "lat", "metric_scaling")

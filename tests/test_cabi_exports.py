@@ -102,3 +102,19 @@ def test_aerosol_and_gas_naming_helpers():
     names = R.gas_names_sw()
     assert len(names) == 21 and set(R.synthetic.GAS_NAMES) | {"h2o_self", "h2o_frgn"} == set(names)
     assert R.requires_z("BestFit") and R.requires_z("HydrostaticBottom") and not R.requires_z("UniformP")
+
+
+def test_comm_entry_points_validate_arguments(lib):
+    """The multi-GPU entry points (include/rrtmgp_b200.h "multi-GPU") answer with status codes without a GPU: a
+    short id buffer, NULL handles."""
+    small = (C.c_char * 16)()
+    assert lib.rrtmgp_b200_comm_unique_id(small, 16) == _lib.ERR_INVALID_ARG
+    assert lib.rrtmgp_b200_comm_unique_id(None, 128) == _lib.ERR_INVALID_ARG
+    uid = (C.c_char * 128)()
+    assert lib.rrtmgp_b200_comm_init(None, uid, 0, 1) == _lib.ERR_INVALID_ARG
+    g = _lib.Gathered()
+    assert lib.rrtmgp_b200_gathered_buffers(None, C.byref(g)) == _lib.ERR_INVALID_ARG
+    assert lib.rrtmgp_b200_comm_destroy(None) == _lib.ERR_INVALID_ARG
+    assert lib.rrtmgp_b200_update_fluxes_gathered(None, 0, 1, None) == _lib.ERR_INVALID_ARG
+    assert lib.rrtmgp_b200_all_gather_fluxes(None, None) == _lib.ERR_INVALID_ARG
+    assert C.sizeof(_lib.Gathered) == 8 * C.sizeof(C.c_void_p) and _lib.UNIQUE_ID_BYTES == 128

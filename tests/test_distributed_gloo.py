@@ -61,3 +61,37 @@ def test_two_rank_gather_equals_single_process(tmp_path):
     ref = Oracle(pack, np.float64).update_fluxes(st, seed=77, nthreads=1)
     for k in FLUX_KEYS:
         np.testing.assert_array_equal(got[k], ref[_KEYMAP[k]])
+
+
+def _id_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        from rrtmgp_b200 import _lib
+        box = [None]
+        if rank == 0:
+            buf = (C.c_char * _lib.UNIQUE_ID_BYTES)()
+            st = _lib.lib().rrtmgp_b200_comm_unique_id(buf, _lib.UNIQUE_ID_BYTES)
+            box = [(st, bytes(buf))]
+        dist.broadcast_object_list(box, src=0)      # how bench.py ships the id to every rank
+        with open(os.path.join(out_dir, f"id{rank}.bin"), "wb") as f:
+            f.write(bytes([box[0][0]]) + box[0][1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_comm_unique_id_reaches_every_rank(tmp_path):
+    """`rrtmgp_b200_comm_unique_id` (rank 0) -> broadcast -> every rank holds the same 128 bytes to hand to
+    `rrtmgp_b200_comm_init`; the gathered layout is rank r -> rows [r ncol, (r + 1) ncol) (shard_range with equal
+    shards).  NCCL itself needs GPUs; without libnccl the entry point answers UNSUPPORTED."""
+    from rrtmgp_b200 import _lib
+    world = 2
+    mp.spawn(_id_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (open(tmp_path / f"id{r}.bin", "rb").read() for r in range(world))
+    assert a == b and len(a) == 1 + _lib.UNIQUE_ID_BYTES
+    assert a[0] in (_lib.OK, _lib.ERR_UNSUPPORTED)
+    if a[0] == _lib.OK:
+        assert any(a[1:])                            # a real id, not zeros
+    for r in range(4):
+        assert shard_range(4 * 1000, r, 4) == (r * 1000, (r + 1) * 1000)

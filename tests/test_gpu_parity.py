@@ -827,3 +827,35 @@ def test_warp_specialised_kernels_match_single_role_kernels_f32(real_pack, monke
         assert maxdiff(a[k], b[k]) <= 1e-2, k
     np.testing.assert_array_equal(a["cld_cover_sw"], b["cld_cover_sw"])
     np.testing.assert_array_equal(a["aod_sw_ext"], b["aod_sw_ext"])
+
+
+def test_comm_single_rank_gathered_equals_local(real_pack):
+    """The multi-GPU entry points on one rank (NCCL refuses two ranks on one device, so N > 1 runs under
+    `bench.py --gpus N`): `update_fluxes_gathered` = `update_fluxes` bit for bit, the gathered views equal the local
+    ones after the overlapped pushes and after the plain `all_gather_fluxes`, chunked shortwave included."""
+    import torch
+    from helpers import make_solver
+    from rrtmgp_b200.sharding import FLUX_KEYS as GATHERED_KEYS
+    ncol = 12 * 148 * 5 + 77                      # more than four waves: the shortwave runs in three column chunks
+    st = R.synthetic.make_atmosphere(ncol, 64, cld_frac=None, cos_zenith=None)
+    a = make_solver(real_pack, st, np.float32, method="all_sky", aerosols=True)
+    b = make_solver(real_pack, st, np.float32, method="all_sky", aerosols=True)
+    R.update_fluxes(a, 5)
+    g = R.comm_init(b, R.comm_unique_id(), 0, 1)
+    R.update_fluxes_gathered(b, 5)
+    torch.cuda.synchronize()
+    for k in GATHERED_KEYS:
+        assert g[k].shape == (ncol, 65)
+        assert torch.equal(a.buffers[k], b.buffers[k]), k
+        assert torch.equal(g[k], b.buffers[k]), k
+    for t in g.values():
+        t.zero_()
+    R.all_gather_fluxes(b)
+    torch.cuda.synchronize()
+    for k in GATHERED_KEYS:
+        assert torch.equal(g[k], b.buffers[k]), k
+    with pytest.raises(R.RRTMGPB200Error):
+        R.comm_init(b, R.comm_unique_id(), 0, 1)   # one communicator per handle
+    R.comm_destroy(b)
+    with pytest.raises(R.RRTMGPB200Error):
+        R.update_fluxes_gathered(b, 5)             # not ready without a communicator
