@@ -268,6 +268,20 @@ def main():
     ms = float(t.item())
     value = world * ncol / (ms * 1e-3)
 
+    # --- N > 1: every rank must hold every rank's columns (checksum of each rank's rows against that rank's own) ---
+    gather_check = None
+    if world > 1:
+        from rrtmgp_b200.sharding import FLUX_KEYS as GK
+        torch.cuda.synchronize()
+        mine = torch.stack([s.buffers[k].double().sum() for k in GK])
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        ok = all(torch.allclose(torch.stack([s.gathered[k][r * ncol:(r + 1) * ncol].double().sum() for k in GK]), sums[r],
+                                rtol=1e-12, atol=0) for r in range(world))
+        okt = torch.tensor([1.0 if ok and float(mine.abs().sum()) > 0 else 0.0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_check = "ok: every rank holds every rank's rows (8 views, checksums)" if okt.item() == 1.0 else "MISMATCH"
+
     # --- dominant kernel: per-kernel CUDA-event timing on the launching stream ---
     def time_call(fn, n):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -453,7 +467,7 @@ def main():
                 "config": config_of(ncol, nlay, world),
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_fp32": roofline_fp32, "roofline_issue": roofline_issue, "cpu_baseline": cpu_baseline,
-                "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants, "sweep": sweep}
+                "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants, "sweep": sweep, "gather_check": gather_check}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -160,6 +160,39 @@ function heating_rate(e::B200Engine, s::RRTMGPSolver)
     return hr
 end
 
+# ---- multi-GPU: column shards, one process (MPI rank) per GPU (include/rrtmgp_b200.h "multi-GPU") ----
+# The reference has no multi-GPU path (docs/src/howto/gpu.md:69-84).  Rank 0 creates the NCCL id, the host ships its
+# 128 bytes to every rank (e.g. `MPI.Bcast!`), every rank calls `comm_init!`; afterwards `update_fluxes_gathered!`
+# leaves the (nlev, nranks * ncol) concatenation of the eight flux views on EVERY rank, the transfers overlapped
+# with the shortwave kernel (copy engines over NVLink).  The gathered arrays are owned by the library and wrapped,
+# not copied.
+comm_unique_id() = (id = Vector{UInt8}(undef, 128); check(ccall((:rrtmgp_b200_comm_unique_id, LIB), Cint, (Ptr{UInt8}, Csize_t), id, 128)); id)
+
+const GATHERED_NAMES = (:lw_flux_up, :lw_flux_dn, :lw_flux_net, :sw_flux_up, :sw_flux_dn, :sw_flux_net, :sw_flux_dn_dir, :net_flux)
+
+function comm_init!(e::B200Engine, s::RRTMGPSolver, unique_id::Vector{UInt8}, rank::Integer, nranks::Integer)
+    length(unique_id) == 128 || error("unique_id must be 128 bytes")
+    check(ccall((:rrtmgp_b200_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), e.handle, unique_id, rank, nranks))
+    ptrs = Ref(ntuple(_ -> CuPtr{Cvoid}(0), 8))
+    check(ccall((:rrtmgp_b200_gathered_buffers, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, ptrs))
+    FT = eltype(s.grid_params)
+    dims = (s.grid_params.nlay + 1, nranks * s.grid_params.ncol)            # (nlev, nranks * ncol), column-major
+    return NamedTuple{GATHERED_NAMES}(ntuple(i -> unsafe_wrap(CuArray, reinterpret(CuPtr{FT}, ptrs[][i]), dims), 8))
+end
+
+function update_fluxes_gathered!(e::B200Engine, seedval = nothing)
+    check(ccall((:rrtmgp_b200_update_fluxes_gathered, LIB), Cint, (Ptr{Cvoid}, UInt64, Cint, Ptr{Cvoid}), e.handle,
+                isnothing(seedval) ? UInt64(0) : UInt64(seedval), isnothing(seedval) ? 0 : 1, CUDA.stream().handle))
+    return nothing
+end
+all_gather_fluxes!(e::B200Engine) =
+    (check(ccall((:rrtmgp_b200_all_gather_fluxes, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, CUDA.stream().handle)); nothing)
+comm_destroy!(e::B200Engine) = (check(ccall((:rrtmgp_b200_comm_destroy, LIB), Cint, (Ptr{Cvoid},), e.handle)); nothing)
+
+# relative humidity as the engine's kernel (a host duty in the reference, grid_adaptation.jl:267-270)
+compute_relative_humidity!(e::B200Engine) =
+    (check(ccall((:rrtmgp_b200_compute_relative_humidity, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, CUDA.stream().handle)); nothing)
+
 # name -> Array pairs of a loaded `LookupBundle` (src/api/lookup_bundle.jl:29-46), i.e. exactly what
 # `lookup_tables(grid_params, method)` built from the rrtmgp-data artifact, in the entry names
 # `rrtmgp_b200_load_luts` reads.  `rrtmgp.jl_b200/tables.py` produces the same entries from the NetCDF files
