@@ -243,10 +243,18 @@ struct Warp {
     // staged copy, so the dependent chains of phase 1 (key species -> gas -> vmr) never wait on global memory.
     __device__ __forceinline__ FT vmr_of(int ig, int k, int j) const {
         if (FUSED) {
-            if (ig == 1 && L.idx_h2o == 1) return own_h2o[j];
-            if (ig == 3) return own_g3[j];
+            if (ig == 1 && L.idx_h2o == 1) return pick(own_h2o, j);
+            if (ig == 3) return pick(own_g3, j);
         }
         return get_vmr(P, ig, k, col, FUSED ? svmr : nullptr);
+    }
+    // own_x[j] for a warp-uniform RUNTIME j as selects (a dynamically indexed register array would go to local
+    // memory); with a compile-time j (generic kernel: unrolled loop) it folds to the element
+    template <class T> __device__ __forceinline__ T pick(const T (&a)[NOWN], int j) const {
+        T r = a[0];
+        if (NOWN > 1 && j == 1) r = a[1];
+        if (NOWN > 2 && j == 2) r = a[2];
+        return r;
     }
 
     // ---------------- phase 0 (gas_optics.jl:87-115,188 and the hoisted per-layer searches) ----------------
@@ -360,15 +368,26 @@ struct Warp {
         const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
         const int n_eta = L.n_eta;
         aod_e = aod_s = FT(0);
+        // Fast kernels (half >= 0): ONE copy of the body with j = half selected at run time -- unrolled over j the
+        // body existed NOWN times (~15 KB each), and phase 1 + the main loop no longer fit the instruction cache
+        // (profiles/r1r: no_inst 10-12 %).  Generic kernel (half < 0): all layers, unrolled.
 #pragma unroll
-        for (int j = 0; j < NOWN; ++j) {
+        for (int jj = 0; jj < (FUSED ? 1 : NOWN); ++jj) {
+            const int j = FUSED ? half : jj;
             const int k = lane + 32 * j;
-            if (k >= nlay || (half >= 0 && j != half)) continue;
+            if (k >= nlay) continue;
             const int kr = half >= 0 ? lane : k;   // record row
             const int cj = colj[k];
             const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
-            const FT col_dry = own_cdry[j];
-            const FT vmr_h2o = own_h2o[j];
+            const FT col_dry = pick(own_cdry, j);
+            const FT vmr_h2o = pick(own_h2o, j);
+            const FT dens_j = pick(own_dens, j);
+            const int cld_j = pick(own_cld, j);
+            const FT cld_fl_j = pick(own_cld_fl, j), cld_fi_j = pick(own_cld_fi, j);
+            const AeroLayer aero_j = pick(own_aero, j);
+            const FT rh_f_j = pick(own_rh_f, j);
+            const int pl_loc_j = pick(own_pl_loc, j), py_loc_j = pick(own_py_loc, j);
+            const FT pl_f_j = pick(own_pl_f, j), py_f_j = pick(own_py_f, j);
             const FT dry_fact = hdiv(FT(1), FT(1) + vmr_h2o);
             for (int b = 0; b < nb; ++b) {
                 const int ib = b_first + b;
@@ -412,7 +431,7 @@ struct Warp {
                     if (vmr_i > FT(0)) {
                         scaling = vmr_i * col_dry;
                         if (gd.z == 1) {
-                            scaling *= own_dens[j];
+                            scaling *= dens_j;
                             if (gd.y > 0) {
                                 if (gd.w == 1) scaling *= (FT(1) - vmr_of(gd.y, k, j) * dry_fact);
                                 else scaling *= vmr_of(gd.y, k, j) * dry_fact;
@@ -427,14 +446,14 @@ struct Warp {
                 FT tc = FT(0), sc = FT(0), gc = FT(0);
                 // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
                 if (use_cloud) {
-                    if ((own_cld[j] >> 16) & 1) {
+                    if ((cld_j >> 16) & 1) {
                         const CldLut<FT>& C = P.cld;
                         size_t kk = (size_t)col * nlay + k;
                         const FT* liq = tb(C.liqdata) + (size_t)3 * C.nsize_liq * ib;
                         const FT* ice = tb(C.icedata) + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
                         FT tl, tls, tlsg, ti, tis, tisg;
-                        cld_eval<FUSED>(C.nsize_liq, liq, own_cld[j] & 0xff, own_cld_fl[j], __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
-                        cld_eval<FUSED>(C.nsize_ice, ice, (own_cld[j] >> 8) & 0xff, own_cld_fi[j], __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
+                        cld_eval<FUSED>(C.nsize_liq, liq, cld_j & 0xff, cld_fl_j, __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
+                        cld_eval<FUSED>(C.nsize_ice, ice, (cld_j >> 8) & 0xff, cld_fi_j, __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
                         if (NOSCAT) {
                             tc = (tl - tls) + (ti - tis);
                         } else {
@@ -452,7 +471,7 @@ struct Warp {
                     if ((cj >> 17) & 1) {
                         size_t kk = ((size_t)col * nlay + k) * 15;
                         FT tsa, tsga;
-                        lookup_aerosol<FUSED>(P.aero, tb(P.aero.dust), ib, P.io.aero_mass + kk, own_aero[j], own_rh_f[j], ta, tsa, tsga);
+                        lookup_aerosol<FUSED>(P.aero, tb(P.aero.dust), ib, P.io.aero_mass + kk, aero_j, rh_f_j, ta, tsa, tsga);
                         if (!LW && ib + 1 == P.aero.iband_550nm) { aod_e += ta; aod_s += tsa; }   // :96-116
                         if (NOSCAT) {
                             ta = ta - tsa;
@@ -498,12 +517,12 @@ struct Warp {
                     // the fast kernels keep just the nlev + 1 values they use
                     // (fast no-scattering kernel: B(t_lev) [nlev], B(t_sfc), then B(t_lay) [nlay])
                     FT* pb = plk + (size_t)b * plk_stride();
-                    pb[k + 1] = interp1d_eq_eval<FUSED>(own_pl_loc[j], own_pl_f[j], totplnk, L.n_t_plnk);
+                    pb[k + 1] = interp1d_eq_eval<FUSED>(pl_loc_j, pl_f_j, totplnk, L.n_t_plnk);
                     if (k == 0) {
                         pb[0] = interp1d_eq_eval<FUSED>(p0_loc, p0_f, totplnk, L.n_t_plnk);
                         pb[FUSED ? nlev : nlev + nlay] = interp1d_eq_eval<FUSED>(psfc_loc, psfc_f, totplnk, L.n_t_plnk);
                     }
-                    if (NOSCAT) pb[(FUSED ? nlev + 1 : nlev) + k] = interp1d_eq_eval<FUSED>(own_py_loc[j], own_py_f[j], totplnk, L.n_t_plnk);
+                    if (NOSCAT) pb[(FUSED ? nlev + 1 : nlev) + k] = interp1d_eq_eval<FUSED>(py_loc_j, py_f_j, totplnk, L.n_t_plnk);
                 }
             }
         }

@@ -288,14 +288,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 }
                 __syncwarp();
             };
-            if (!day) {   // night: AOD and masks only (shortwave_2stream.jl:66-102)
+            if (!day) {   // night: AOD and masks only (shortwave_2stream.jl:66-102); the band records of the 550 nm
+                          // block are still built, by the ONE call site of the shortwave sweep below (phase 1 is ~15 KB of
+                          // code per inlined copy, and the hot code of a block should fit the 32 KB instruction cache)
                 if (spectral) flush_bands(true);
-                if (aod_here) {
-                    for (int part = 0; part * 32 < nlay; ++part) build_records(part);
-                    aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
-                    if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
-                }
-                continue;
+                if (!aod_here) continue;
             }
 
             const int gpt = W.gpt, ibnd = W.ibnd, bl = W.bl;
@@ -432,13 +429,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 const FT* pbk = W.plk + bl * (nlev + 1);
                 const FT emis = __ldg(P.io.sfc_emis + (size_t)col * L.n_bnd + ibnd);
                 const FT inc = P.io.inc_flux_lw ? __ldg(P.io.inc_flux_lw + (size_t)gpt * P.ncol_total + col) : 0.f;
-                build_records(0);
-                FT tau, ssa, g, pf;
-                gather(0, G);
-                finish(G, tau, ssa, g, pf);
-                FT lev_bot = pbk[0] * pf;
-                FT albedo = 1.f - emis;
-                FT src = Num<FT>::pi() * emis * (pbk[nlev] * pf);
+                FT tau = 0.f, ssa = 0.f, g = 0.f, pf = 0.f;
+                FT lev_bot = 0.f, albedo = 1.f - emis, src = 0.f;
                 // finishes layer kl = k - 1 given the Planck source at its top
                 auto close_layer = [&](int kl, const LwCoef& C, FT denom, FT lev_top) {
                     const FT dB = lev_bot - lev_top;
@@ -455,7 +447,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 };
                 for (int k0 = 0; k0 < nlay; k0 += 16) {                 // tiles of <= 16 interfaces k
                     const int ks = k0 > 0 ? k0 : 1, ke = k0 + 16 < nlay ? k0 + 16 : nlay;
-                    if (k0 > 0 && (k0 & 31) == 0) build_records(k0 >> 5);   // next 32 layers' records
+                    if ((k0 & 31) == 0) build_records(k0 >> 5);             // this and the next 31 layers' records (one call site)
+                    if (k0 == 0) {                                           // layer 0 and the surface
+                        gather(0, G);
+                        finish(G, tau, ssa, g, pf);
+                        lev_bot = pbk[0] * pf;
+                        src = Num<FT>::pi() * emis * (pbk[nlev] * pf);
+                    }
                     // record row, McICA bit, Planck value and staging row of layer k advance by increments
                     const FT* rk = rec_lane + (ks & 31) * RR;
                     unsigned mw = HAS_CLD ? mask_word(ks) >> (ks & 31) : 0u;
@@ -681,16 +679,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 const FT neg_inv_mu0_l2e = -inv_mu0 * 1.4426950408889634f;
                 FT tau_cum = 0.f, dir = dir_top;
                 FT beta = 0.f, d = 0.f;   // reflectance / downward diffuse source of everything above the level
-                {
+                if (day) {
                     FT hs;
                     FT sum = warp_sum2(dir_top, hs);   // TOA: diffuse incident flux is zero (shortwave_2stream.jl:331)
                     if (lane == 0) { accs[DIR * kAccStride + nlay] += sum; accs[DN * kAccStride + nlay] += sum; }
                     if (spectral && (lane & 15) == 0) band_add(DN, nlay, hs);
                 }
-                build_records((nlay - 1) >> 5);
-                FT tau, ssa, g, pf;
-                gather(nlay - 1, G);
-                finish(G, tau, ssa, g, pf);
+                FT tau = 0.f, ssa = 0.f, g = 0.f, pf = 0.f;
                 // layer k: coefficients, TMEM store, marching update; returns d_{k+1} (before the update)
                 auto march = [&](int k) -> FT {
                     FT Rdir, Tdir, Rdif, Tdif;
@@ -709,8 +704,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     dir = dir_top * ex;                               // direct flux at level k
                     return d_above;
                 };
-                for (int jc = (nlay - 2) & ~7; jc >= 0; jc -= 8) {     // 8 layers x (d_{k+1}, dir_k) per tile, k = j + 1
-                    if ((jc & 31) == 24 && jc + 8 < nlay) build_records(jc >> 5);   // next 32 layers down
+                int part_built = -1;
+                // 8 layers x (d_{k+1}, dir_k) per tile, k = j + 1; the first pass only gathers the top layer
+                for (int jc = ((nlay - 2) & ~7) + 8; jc >= 0; jc -= 8) {
+                    const bool top_only = jc > nlay - 2;
+                    const int part = top_only ? (nlay - 1) >> 5 : jc >> 5;
+                    if (part != part_built) { build_records(part); part_built = part; }   // the one call site
+                    if (!day) continue;                                  // night: records (AOD) only
+                    if (top_only) {
+                        gather(nlay - 1, G);
+                        finish(G, tau, ssa, g, pf);
+                        continue;
+                    }
                     const int jtop = jc + 7 < nlay - 2 ? jc + 7 : nlay - 2;
                     const FT* rk = rec_lane + (jtop & 31) * RR;
                     unsigned mw = HAS_CLD ? mask_word(jtop) << (31 - (jtop & 31)) : 0u;   // bit 31 = layer j
@@ -737,6 +742,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                         if (spectral && okb && !(lane & 1)) band_add(DN, kk + 1, hs);
                     }
                     __syncwarp();
+                }
+                if (!day) {   // night: the 550 nm optical depths are all this block produces
+                    aod_e = warp_sum(aod_e); aod_s = warp_sum(aod_s);
+                    if (lane == 0) { P.io.aod_ext[col] = aod_e; P.io.aod_sca[col] = aod_s; }
+                    continue;
                 }
                 {   // lowest layer
                     FT hd1, hdir0;
