@@ -219,22 +219,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
         {
             const long long nc = col_next;
             if (nc < P.ncol) {
-                auto prefetch_row = [&](const FT* base, int n) {
+                // one rolled loop over (row pointer, bytes) pairs: inlined per array this was 13 KB of code run once per
+                // column, which evicted the hot loops from the instruction cache
+                const char* rows[12];
+                int bytes[12];
+                int nrow = 0;
+                auto add_row = [&](const FT* base, int n) {
                     if (base == nullptr) return;
-                    const char* b = reinterpret_cast<const char*>(base + (size_t)nc * n);
-                    const int bytes = n * (int)sizeof(FT);
-                    for (int o = lane * 128; o < bytes + 127; o += 32 * 128)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (o < bytes ? o : bytes - 1)));
+                    rows[nrow] = reinterpret_cast<const char*>(base + (size_t)nc * n);
+                    bytes[nrow++] = n * (int)sizeof(FT);
                 };
-                prefetch_row(P.io.layerdata, 4 * nlay);
-                prefetch_row(P.io.t_lev, nlev);
-                if (P.vmr_kind == 0) { prefetch_row(P.io.vmr_h2o, nlay); prefetch_row(P.io.vmr_o3, nlay); }
-                else prefetch_row(P.io.vmr, nlay * P.ngas);
+                add_row(P.io.layerdata, 4 * nlay);
+                add_row(P.io.t_lev, nlev);
+                if (P.vmr_kind == 0) { add_row(P.io.vmr_h2o, nlay); add_row(P.io.vmr_o3, nlay); }
+                else add_row(P.io.vmr, nlay * P.ngas);
                 if (HAS_CLD) {
-                    prefetch_row(P.io.cld_frac, nlay); prefetch_row(P.io.cld_path_liq, nlay); prefetch_row(P.io.cld_path_ice, nlay);
-                    prefetch_row(P.io.cld_r_eff_liq, nlay); prefetch_row(P.io.cld_r_eff_ice, nlay);
+                    add_row(P.io.cld_frac, nlay); add_row(P.io.cld_path_liq, nlay); add_row(P.io.cld_path_ice, nlay);
+                    add_row(P.io.cld_r_eff_liq, nlay); add_row(P.io.cld_r_eff_ice, nlay);
                 }
-                if (HAS_AER) { prefetch_row(P.io.aero_mass, 15 * nlay); prefetch_row(P.io.aero_size, 15 * nlay); }
+                if (HAS_AER) { add_row(P.io.aero_mass, 15 * nlay); add_row(P.io.aero_size, 15 * nlay); }
+#pragma unroll 1
+                for (int a = 0; a < nrow; ++a) {
+                    const char* b = rows[a];
+                    const int nb = bytes[a];
+#pragma unroll 1
+                    for (int o = lane * 128; o < nb + 127; o += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (o < nb ? o : nb - 1)));
+                }
             }
         }
         W.phase0();
