@@ -389,13 +389,26 @@ struct Warp {
             const int pl_loc_j = pick(own_pl_loc, j), py_loc_j = pick(own_py_loc, j);
             const FT pl_f_j = pick(own_pl_f, j), py_f_j = pick(own_py_f, j);
             const FT dry_fact = hdiv(FT(1), FT(1) + vmr_h2o);
+            // vmr of gas ig, branch-free for the fast kernels with VmrGM storage (the gas index depends on (tropo, band), so
+            // lanes disagree and the if-chain of vmr_of diverged: 6 % of the longwave kernel's time in profiles/r2h)
+            const bool gm_fast = FUSED && P.vmr_kind == 0 && svmr != nullptr && L.idx_h2o == 1 && P.ngas >= 3;   // warp-uniform
+            const FT g3_j = pick(own_g3, j);
+            auto vmrq = [&](int ig) -> FT {
+                if (gm_fast) {
+                    FT v = svmr[ig > 0 ? ig - 1 : 0];
+                    v = ig == 1 ? vmr_h2o : v;
+                    v = ig == 3 ? g3_j : v;
+                    return ig == 0 ? FT(1) : v;
+                }
+                return vmr_of(ig, k, j);
+            };
             for (int b = 0; b < nb; ++b) {
                 const int ib = b_first + b;
                 FT* r = rec + (size_t)kr * P.rec_row + b * RW;
                 // gas_optics.jl:129-170
                 const int* ksp = tb(L.key_species) + 2 * ((tropo - 1) + 2 * ib);
                 const int ig1 = ldt<FUSED>(ksp), ig2 = ldt<FUSED>(ksp + 1);
-                const FT vmr1 = vmr_of(ig1, k, j), vmr2 = vmr_of(ig2, k, j);
+                const FT vmr1 = vmrq(ig1), vmr2 = vmrq(ig2);
                 int je[2];
                 FT fe[2], smix[2];
                 // fast kernels (FUSED): record = 8 corner weights | s1, s2, major-table offsets of the two T nodes |
@@ -420,26 +433,27 @@ struct Warp {
                 // (gas_optics.jl:430-444: (vmr_h2o + 1) * col_dry).
                 const int soff = (FUSED && !LW) ? 1 : 0;
                 const int nslots = FUSED ? 4 * L.n_minor_groups : L.nminor_max;
-                if (FUSED && !LW) r[sc0] = (vmr_h2o + FT(1)) * col_dry;
                 const int* bst = tb(L.minor_bnd_st[tropo - 1]);
                 const int4* gdt = reinterpret_cast<const int4*>(tb(L.minor_gasdata[tropo - 1]));
                 const int m0 = ldt<FUSED>(bst + ib), nmin = ldt<FUSED>(bst + ib + 1) - m0;
-                for (int i = 0; i < nmin; ++i) {
+                auto minor_scaling = [&](int i) -> FT {      // gas_optics.jl:344-412, absorber i of this (band, tropo)
                     const int4 gd = ldt<FUSED>(gdt + (m0 + i));
-                    FT vmr_i = vmr_of(gd.x, k, j);
+                    const FT vmr_i = vmrq(gd.x);
                     FT scaling = FT(0);
                     if (vmr_i > FT(0)) {
                         scaling = vmr_i * col_dry;
                         if (gd.z == 1) {
                             scaling *= dens_j;
                             if (gd.y > 0) {
-                                if (gd.w == 1) scaling *= (FT(1) - vmr_of(gd.y, k, j) * dry_fact);
-                                else scaling *= vmr_of(gd.y, k, j) * dry_fact;
+                                if (gd.w == 1) scaling *= (FT(1) - vmrq(gd.y) * dry_fact);
+                                else scaling *= vmrq(gd.y) * dry_fact;
                             }
                         }
                     }
-                    r[sc0 + soff + i] = scaling;
-                }
+                    return scaling;
+                };
+                if (FUSED && !LW) r[sc0] = (vmr_h2o + FT(1)) * col_dry;
+                for (int i = 0; i < nmin; ++i) r[sc0 + soff + i] = minor_scaling(i);
                 if (FUSED)
                     for (int i = soff + nmin; i < nslots; ++i) r[sc0 + i] = FT(0);
                 FT* rc = r + sc0 + nslots;   // cloud (3) then aerosol (3)  [FUSED: aerosol-only / cloud+aerosol products]
