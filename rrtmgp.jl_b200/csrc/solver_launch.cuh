@@ -64,10 +64,10 @@ static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin
     F.off_blob = tail;
     int room = max_smem_optin - 64 - tail;   // 64: static shared memory of the kernel
     // Shared memory is carved out of the L1 cache, which serves the k-distribution gathers: staging the most-read
-    // ~24 KB of the block (key species, reference vmr, minor-absorber lists, the first Planck / aerosol tables) and
+    // ~20 KB of the block (key species, reference vmr, minor-absorber lists, the Planck table; not the aerosol and cloud tables) and
     // leaving the rest of the space to L1 measured best on B200 at ncol = 1e5 (LW 17.9 ms against 18.4 with
     // everything staged and 18.7 with nothing; SW 16.8 / 17.0 / 17.1).  RRTMGP_B200_STAGE_BYTES overrides the cap.
-    room = std::min(room, 24576);
+    room = std::min(room, 20480);
     if (const char* e = std::getenv("RRTMGP_B200_STAGE_BYTES")) room = std::min(max_smem_optin - 64 - tail, std::atoi(e));
     F.staged_bytes = 0;
     for (int i = 0; i < P.lut.n_blob_cut; ++i)
