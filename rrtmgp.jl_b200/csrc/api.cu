@@ -31,6 +31,7 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
 };
 constexpr int kMaxRanks = 16, kGatheredViews = 8;
+constexpr int kSplitMaxCols = 16 * 12 * 160;   // above 16 columns per warp (12 warps on up to 160 SMs) nothing is split
 struct CommState {
     NcclApi nccl;
     ncclComm_t comm = nullptr;
@@ -58,6 +59,10 @@ struct rrtmgp_b200_handle {
     // may overlap on several streams, rrtmgp_b200_update_fluxes_range)
     unsigned int* work_counters = nullptr;
     mutable unsigned work_seq = 0;
+    // small shards (solver_fast.cuh): partial sums and arrival counters of the split columns, indexed by the handle's
+    // column; allocated at create for handles of fewer than kSplitMaxCols Float32 columns
+    float* split_scratch = nullptr;
+    unsigned int* split_flags = nullptr;
     // interpolate_levels! configuration (rrtmgp_b200_set_level_interpolation)
     int interpolation = RRTMGP_B200_NO_INTERPOLATION, bottom_extrapolation = RRTMGP_B200_SAME_AS_INTERPOLATION;
     const void* center_z = nullptr;
@@ -316,6 +321,16 @@ void base_params(const rrtmgp_b200_handle* h, SolveParams<FT>& P, bool sw, bool 
     P.col_offset = c.col_offset + c0;
     P.seed = seed;
     P.work_counter = h->work_counters ? h->work_counters + (h->work_seq++ % 255u) : nullptr;   // slot 255: validate_inputs
+    // small shards: the number of work items per column follows from the HANDLE's column count, so every launch of a
+    // handle (full range or column ranges, which touch disjoint columns of the scratch) sums in the same order
+    {
+        const int warps = (c.nlay > 64 ? 8 : 12) * (h->sm_count > 0 ? h->sm_count : 148);
+        const long long per_warp = (long long)c.ncol / warps;
+        P.split = h->split_scratch == nullptr ? 1 : (per_warp >= 16 ? 1 : (per_warp >= 8 ? 2 : 4));
+        const size_t scr = 3 * (size_t)((c.nlay > 64 ? 96 : 64) + 4) + 4;      // solver_fast.cuh: kScr of the geometry in use
+        P.split_scratch = h->split_scratch ? h->split_scratch + (size_t)c0 * P.split * scr : nullptr;
+        P.split_flags = h->split_flags ? h->split_flags + c0 : nullptr;
+    }
     gauss_angles<FT>(P.n_mu, P.Ds, P.wts);
 }
 
@@ -537,6 +552,18 @@ int rrtmgp_b200_create(const rrtmgp_b200_config_t* cfg, rrtmgp_b200_handle_t** o
     {
         DeviceGuard g(cfg->device);
         if (cudaMalloc(&h->work_counters, 256 * sizeof(unsigned int)) != cudaSuccess) { delete h; return RRTMGP_B200_ERR_CUDA; }
+        if (cfg->dtype == 0 && cfg->ncol < kSplitMaxCols) {      // small Float32 shards: scratch of the split columns
+            const size_t nscr = (size_t)cfg->ncol * 4 * (3 * (96 + 4) + 4);   // 4 shares, the larger accumulator stride (8-warp geometry)
+            if (cudaMalloc(&h->split_scratch, nscr * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&h->split_flags, (size_t)cfg->ncol * sizeof(unsigned int)) != cudaSuccess ||
+                cudaMemset(h->split_flags, 0, (size_t)cfg->ncol * sizeof(unsigned int)) != cudaSuccess) {
+                if (h->split_scratch) cudaFree(h->split_scratch);
+                if (h->split_flags) cudaFree(h->split_flags);
+                cudaFree(h->work_counters);
+                delete h;
+                return RRTMGP_B200_ERR_CUDA;
+            }
+        }
     }
     *out = h;
     return RRTMGP_B200_OK;
@@ -548,6 +575,8 @@ void rrtmgp_b200_destroy(rrtmgp_b200_handle_t* h) {
     DeviceGuard g(h->cfg.device);
     free_lut_store(h->luts);
     if (h->work_counters) cudaFree(h->work_counters);
+    if (h->split_scratch) cudaFree(h->split_scratch);
+    if (h->split_flags) cudaFree(h->split_flags);
     delete h;
 }
 

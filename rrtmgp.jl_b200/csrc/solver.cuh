@@ -58,6 +58,10 @@ struct SolveParams {
     long long col_offset;
     unsigned long long seed;
     unsigned int* work_counter;   // fast kernels: next column to hand out (zeroed before the launch)
+    // fast kernels, small shards: a column's g-point blocks split over `split` (1, 2 or 4) work items (solver_fast.cuh)
+    int split;
+    float* split_scratch;         // [ncol][split][3 * acc_stride + 4] partial sums, or null
+    unsigned int* split_flags;    // [ncol] arrival counters, zero between launches
     FT Ds[4], wts[4];
     // per-warp shared-memory layout, in bytes from the warp's base
     int off_colj, off_colp, off_recj, off_rec, off_plk, off_store, warp_bytes;

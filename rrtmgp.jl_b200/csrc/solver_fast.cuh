@@ -211,14 +211,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
         if (lane == 0) v = atomicAdd(P.work_counter, 1u);
         return (long long)__shfl_sync(0xffffffffu, v, 0);
     };
+    // SMALL SHARDS (P.split = 2 or 4, chosen by the launcher when a warp would get fewer than 16 columns): a work item is
+    // (column, contiguous share of its g-point blocks), so the last item of a warp costs a half / a quarter of a column.
+    // Every item leaves its broadband partial sums in global scratch; the LAST arriver of a column (atomic counter) adds
+    // the shares in the fixed order 0, 1, .. and writes the column -- results do not depend on who arrives last.
+    const int split_log2 = P.split == 4 ? 2 : (P.split == 2 ? 1 : 0);
+    const long long nitems = (long long)P.ncol << split_log2;
+    constexpr int kScr = 3 * kAccStride + 4;      // floats per (column, share) of the scratch: accumulators + cloudy count
     long long col_next = next_column();
-    while (col_next < P.ncol) {
-        const long long col = col_next;
+    while (col_next < nitems) {
+        const long long item = col_next;
+        const long long col = item >> split_log2;
+        const int share = (int)(item & ((1 << split_log2) - 1));
         col_next = next_column();
         Warp<FT, MODE, NOWN, true> W(P, wbase, lane, col, sblob, F.staged_bytes, svmr);
         {
-            const long long nc = col_next;
-            if (nc < P.ncol) {
+            const long long nc = col_next >> split_log2;
+            if (nc < P.ncol && nc != col) {
                 // one rolled loop over (row pointer, bytes) pairs: inlined per array this was 13 KB of code run once per
                 // column, which evicted the hot loops from the instruction cache
                 const char* rows[12];
@@ -270,7 +279,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
         int n_cloudy = 0;
         __syncwarp();
 
-        for (int g0 = 0; g0 < NGPT; g0 += 32) {   // NGPT is a multiple of 32: every lane owns a g-point
+        // this item's blocks of 32 g-points (NGPT is a multiple of 32: every lane owns a g-point)
+        const int blk0 = (share * (NGPT / 32)) >> split_log2, blk1 = ((share + 1) * (NGPT / 32)) >> split_log2;
+        for (int g0 = 32 * blk0; g0 < 32 * blk1; g0 += 32) {
             W.set_block(g0);
             __syncwarp();
             if (HAS_CLD) n_cloudy += W.mcica(col_key, cld_start, cld_finish);
@@ -828,6 +839,30 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
             if (spectral) flush_bands(false);
         }
         __syncwarp();
+
+        if (split_log2 > 0) {   // warp-uniform
+            float* scr = P.split_scratch + ((size_t)col << split_log2) * kScr;
+            float* mine = scr + share * kScr;
+            for (int i = lane; i < 3 * kAccStride; i += 32) __stcg(mine + i, accs[i]);
+            if (lane == 0) __stcg(mine + 3 * kAccStride, (float)n_cloudy);
+            __threadfence();
+            __syncwarp();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(P.split_flags + col, 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev != (1u << split_log2) - 1u) continue;          // another share of this column is still on its way
+            __threadfence();
+            if (lane == 0) P.split_flags[col] = 0u;                  // ready for the next launch
+            for (int i = lane; i < 3 * kAccStride; i += 32) {
+                float t = 0.f;
+                for (int sh = 0; sh < (1 << split_log2); ++sh) t += __ldcg(scr + sh * kScr + i);
+                accs[i] = t;
+            }
+            float nc_f = 0.f;
+            for (int sh = 0; sh < (1 << split_log2); ++sh) nc_f += __ldcg(scr + sh * kScr + 3 * kAccStride);
+            n_cloudy = (int)nc_f;
+            __syncwarp();
+        }
 
         // ---------------- epilogue: (nlev, ncol) presentation, net, scaling, diagnostics ----------------
 #pragma unroll

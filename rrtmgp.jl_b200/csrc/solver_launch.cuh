@@ -96,8 +96,11 @@ static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t
     if (P.work_counter == nullptr) return -1;
     e = cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return (int)e;
-    const int need = (P.ncol + kFastWarps - 1) / kFastWarps;
     const int sms = sm_count_of_current_device();
+    // small shards: P.split (1, 2 or 4 work items per column) comes from the handle (api.cu: split_of)
+    if (P.split_scratch == nullptr || P.split_flags == nullptr || (P.split != 2 && P.split != 4)) P.split = 1;
+    const long long items = (long long)P.ncol * P.split;
+    const int need = (int)((items + kFastWarps - 1) / kFastWarps);
     const int grid = need < sms ? need : sms;   // persistent: one CTA per SM
     kern<<<grid, kFastWarps * 32, smem, stream>>>(P, F);
     return (int)cudaGetLastError();
