@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -31,7 +32,7 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
 };
 constexpr int kMaxRanks = 16, kGatheredViews = 8;
-constexpr int kSplitMaxCols = 16 * 12 * 160;   // above 16 columns per warp (12 warps on up to 160 SMs) nothing is split
+constexpr int kSplitMaxCols = 4 * 12 * 160;    // from four columns per warp (12 warps on up to 160 SMs) nothing is split
 struct CommState {
     NcclApi nccl;
     ncclComm_t comm = nullptr;
@@ -326,7 +327,13 @@ void base_params(const rrtmgp_b200_handle* h, SolveParams<FT>& P, bool sw, bool 
     {
         const int warps = (c.nlay > 64 ? 8 : 12) * (h->sm_count > 0 ? h->sm_count : 148);
         const long long per_warp = (long long)c.ncol / warps;
-        P.split = h->split_scratch == nullptr ? 1 : (per_warp >= 16 ? 1 : (per_warp >= 8 ? 2 : 4));
+        // measured on B200 (tools/configs_sweep.py with RRTMGP_B200_SPLIT = 1 / 2 / 4): every halving of the work items
+        // costs ~9 % (phase 0, set-up and the combination run per item; L1 hit rate of the gathers drops), so it only
+        // pays below four columns per warp: 4096 columns 2.34e6 -> 2.52e6 col/s with two items per column, but 1e4
+        // columns 2.68e6 -> 2.47e6 and four items per column never
+        P.split = h->split_scratch == nullptr ? 1 : (per_warp >= 4 ? 1 : 2);
+        if (const char* e = std::getenv("RRTMGP_B200_SPLIT"))                  // A/B experiments: 1, 2 or 4
+            if (h->split_scratch != nullptr) P.split = std::atoi(e) == 4 ? 4 : (std::atoi(e) == 2 ? 2 : 1);
         const size_t scr = 3 * (size_t)((c.nlay > 64 ? 96 : 64) + 4) + 4;      // solver_fast.cuh: kScr of the geometry in use
         P.split_scratch = h->split_scratch ? h->split_scratch + (size_t)c0 * P.split * scr : nullptr;
         P.split_flags = h->split_flags ? h->split_flags + c0 : nullptr;

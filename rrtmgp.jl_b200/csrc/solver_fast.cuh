@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
         if (lane == 0) v = atomicAdd(P.work_counter, 1u);
         return (long long)__shfl_sync(0xffffffffu, v, 0);
     };
-    // SMALL SHARDS (P.split = 2 or 4, chosen by the launcher when a warp would get fewer than 16 columns): a work item is
+    // SMALL SHARDS (P.split = 2 or 4, chosen by the host when a warp would get fewer than four columns, api.cu): a work item is
     // (column, contiguous share of its g-point blocks), so the last item of a warp costs a half / a quarter of a column.
     // Every item leaves its broadband partial sums in global scratch; the LAST arriver of a column (atomic counter) adds
     // the shares in the fixed order 0, 1, .. and writes the column -- results do not depend on who arrives last.
@@ -845,13 +845,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
             float* mine = scr + share * kScr;
             for (int i = lane; i < 3 * kAccStride; i += 32) __stcg(mine + i, accs[i]);
             if (lane == 0) __stcg(mine + 3 * kAccStride, (float)n_cloudy);
-            __threadfence();
+            // Ordering without __threadfence(): that is MEMBAR.SC.GPU + CCTL.IVALL, and invalidating the SM's L1 twice per
+            // work item throws the k-distribution gathers of all 12 warps out of the cache.  The partial sums go around
+            // L1 (st.cg / ld.cg); the warp's stores are ordered before lane 0's RELEASE increment (MEMBAR.ALL.GPU, no
+            // invalidation) by the warp barrier; the last arriver's loads depend on the counter value through the branch.
             __syncwarp();
             unsigned prev = 0;
-            if (lane == 0) prev = atomicAdd(P.split_flags + col, 1u);
+            if (lane == 0)
+                asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(P.split_flags + col) : "memory");
             prev = __shfl_sync(0xffffffffu, prev, 0);
             if (prev != (1u << split_log2) - 1u) continue;          // another share of this column is still on its way
-            __threadfence();
             if (lane == 0) P.split_flags[col] = 0u;                  // ready for the next launch
             for (int i = lane; i < 3 * kAccStride; i += 32) {
                 float t = 0.f;
