@@ -53,8 +53,15 @@ static bool ws_enabled() {
     return e && !std::strcmp(e, "ws");
 }
 
-// Fast path: Float32, nlay <= 95, real-table shape. Returns -1 when not applicable.
+int launch_tm(int mode, SolveParams<double>& P, int max_smem_optin, cudaStream_t s);   // solver_tm.cu
+
+// Fast paths.  Float64: the tensor-memory kernels of solver_tm.cuh (two-stream, nlay <= 64, any table shape).
+// Float32: nlay <= 95, real-table shape.  Return -1 when not applicable.
 template <typename FT> static int try_fast(int, SolveParams<FT>&, int, cudaStream_t) { return -1; }
+template <> int try_fast<double>(int mode, SolveParams<double>& P, int max_smem_optin, cudaStream_t s) {
+    if (!fast_enabled()) return -1;
+    return launch_tm(mode, P, max_smem_optin, s);
+}
 template <> int try_fast<float>(int mode, SolveParams<float>& P, int max_smem_optin, cudaStream_t s) {
     const GasLut<float>& L = P.lut;
     if (!fast_enabled() || P.nlay >= FastGeom<8>::max_lay || P.nlay < 2) return -1;

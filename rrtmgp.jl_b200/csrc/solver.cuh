@@ -206,6 +206,7 @@ struct Warp {
     FT* rec;     // [nlay][maxb][RW]: fe1, fe2, s1, s2, minor scalings, cloud(3), aerosol(3)
     FT* plk;     // LW: [maxb][2*nlev] B(t_lev) | B(t_lay) (noscat) | B(t_sfc)
     const int RW, maxb;
+    bool rec_by_part = false;   // generic records built 32 layers at a time (solver_tm.cuh): row of layer k is k & 31
     // fast kernels: shared-memory copy of the small-table block (GasLut::blob) and of the global-mean vmr array
     const unsigned char* sblob;
     const int staged;   // bytes of the block that are staged (a prefix ending at a table boundary)
@@ -379,7 +380,7 @@ struct Warp {
         for (int jj = 0; jj < (FUSED ? 1 : NOWN); ++jj) {
             const int j = FUSED ? half : jj;
             const int k = lane + 32 * j;
-            if (k >= nlay) continue;
+            if (k >= nlay || (!FUSED && half >= 0 && j != half)) continue;
             const int kr = half >= 0 ? lane : k;   // record row
             const int cj = colj[k];
             const int jt = cj & 0xff, tropo = ((cj >> 16) & 1) + 1;
@@ -592,9 +593,10 @@ struct Warp {
         const int cj = colj[k];
         const int jt = cj & 0xff, jp = (cj >> 8) & 0xff, tr = (cj >> 16) & 1;
         const FT ft = colp[4 * k + 0], fp = colp[4 * k + 1], col_dry = colp[4 * k + 2];
-        const int rj = recj[k * maxb + bl];
+        const int kr = rec_by_part ? (k & 31) : k;   // record row
+        const int rj = recj[kr * maxb + bl];
         const int je1 = rj & 0xf, je2 = (rj >> 4) & 0xf, nmin = rj >> 8;
-        const FT* r = rec + k * P.rec_row + bl * RW;
+        const FT* r = rec + kr * P.rec_row + bl * RW;
         const FT fe1 = r[0], fe2 = r[1];
         const FT omfe1 = FT(1) - fe1, omfe2 = FT(1) - fe2, omft = FT(1) - ft, omfp = FT(1) - fp;
         // element offsets (all tables < 2^31 elements)

@@ -103,6 +103,7 @@ struct FastSmem {
     int off_blob, off_vmr;               // CTA-shared: staged small-table block, global-mean vmr array (from the smem base)
     int staged_bytes;                    // staged prefix of GasLut::blob
     int off_bacc;                        // per warp: per-band accumulators [2 bands][up, dn][kAccStride] (spectral fluxes), or -1
+    int active_warps;                    // warps per CTA that take work items (fewer than all when there are few columns)
 };
 
 // ---- TMA bulk copy global -> shared with mbarrier completion (the small-table block, once per CTA) ----
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
     const int split_log2 = P.split == 4 ? 2 : (P.split == 2 ? 1 : 0);
     const long long nitems = (long long)P.ncol << split_log2;
     constexpr int kScr = 3 * kAccStride + 4;      // floats per (column, share) of the scratch: accumulators + cloudy count
-    long long col_next = next_column();
+    // few work items: the launcher spreads them over the SMs (one CTA each) and lets only `active_warps` warps per CTA
+    // take any, so e.g. 128 columns run one warp per SM instead of twelve warps on eleven SMs
+    long long col_next = warp < F.active_warps ? next_column() : nitems;
     while (col_next < nitems) {
         const long long item = col_next;
         const long long col = item >> split_log2;

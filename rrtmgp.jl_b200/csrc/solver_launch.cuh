@@ -100,8 +100,9 @@ static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t
     // small shards: P.split (1, 2 or 4 work items per column) comes from the handle (api.cu: split_of)
     if (P.split_scratch == nullptr || P.split_flags == nullptr || (P.split != 2 && P.split != 4)) P.split = 1;
     const long long items = (long long)P.ncol * P.split;
-    const int need = (int)((items + kFastWarps - 1) / kFastWarps);
-    const int grid = need < sms ? need : sms;   // persistent: one CTA per SM
+    const int grid = items < sms ? (int)items : sms;   // persistent: one CTA per SM; fewer CTAs only for fewer items than SMs
+    const long long per_cta = (items + grid - 1) / grid;
+    F.active_warps = per_cta < kFastWarps ? (int)per_cta : kFastWarps;
     kern<<<grid, kFastWarps * 32, smem, stream>>>(P, F);
     return (int)cudaGetLastError();
 }
