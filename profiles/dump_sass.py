@@ -13,7 +13,8 @@ CSRC = os.path.join(ROOT, "rrtmgp.jl_b200", "csrc")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 KERNELS = [("fast_lw_ng1", "ILi0ELi256ELi1ELb1ELb1ELb0ELi12E", "lw_2stream_fused"),
            ("fast_sw_ng1", "ILi2ELi224ELi1ELb1ELb1ELb0ELi12E", "sw_2stream_fused"),
-           ("ws_lw_ng1", "solve_kernel_wsILi0ELi256ELi1ELb1ELb1ELb0E", "lw_2stream_warp_specialised")]
+           ("ws_lw_ng1", "solve_kernel_wsILi0ELi256ELi1ELb1ELb1ELb0E", "lw_2stream_warp_specialised"),
+           ("solver_tm", "solve_kernel_tmILi0E", "lw_2stream_float64_tensor_memory")]
 SPECIAL = ("LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "USETMAXREG", "UTCBAR", "UTCATOMSWS", "LDG", "LDS", "STS", "MUFU", "FFMA", "FMUL", "FADD")
 
 for obj, key, name in KERNELS:
@@ -40,7 +41,7 @@ for obj, key, name in KERNELS:
                 t = int(m.group(1), 16)
                 body = [(x, y) for x, y in ins if t <= x <= a]
                 n_ldg = sum(1 for _, y in body if y.startswith("LDG") or " LDG" in y)
-                if n_ldg >= 12 and (best is None or len(body) < len(best)):
+                if n_ldg >= (12 if "solver_tm" not in obj else 20) and (best is None or len(body) < len(best)):
                     best = body
     log = open(os.path.join(CSRC, obj + ".ptxas.log")).read()
     regs = re.findall(r"Used (\d+) registers", log)

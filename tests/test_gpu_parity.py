@@ -859,3 +859,58 @@ def test_comm_single_rank_gathered_equals_local(real_pack):
     R.comm_destroy(b)
     with pytest.raises(R.RRTMGPB200Error):
         R.update_fluxes_gathered(b, 5)             # not ready without a communicator
+
+
+# ---- Float64 two-stream kernels on tensor memory (csrc/solver_tm.cuh); taken from 2 x SM-count columns up ----
+@pytest.mark.parametrize("nlay", [2, 8, 31, 32, 33, 40, 63, 64])
+def test_f64_tensor_memory_kernels_runtime_nlay(real_pack, nlay):
+    """Every tile (8 / 16) and record-part (32) boundary: Float64 engine vs Float64 oracle at 1e-9 relative, partial
+    cloudiness and a day / night mix, cloud cover and AOD bit-equal / to 1e-12."""
+    st = R.synthetic.make_atmosphere(320, nlay, dtype=np.float64, cld_frac=None, cos_zenith=None)
+    kw = dict(method="all_sky", aerosols=True, seed=99)
+    e, o = run_engine(real_pack, st, np.float64, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f64(e, o)
+    np.testing.assert_array_equal(e["cld_cover_lw"], o["cld_cover_lw"])
+    np.testing.assert_array_equal(e["cld_cover_sw"], o["cld_cover_sw"])
+    np.testing.assert_allclose(e["aod_sw_ext"], o["aod_sw_ext"], rtol=1e-12)
+    night = st["cos_zenith"] <= 0
+    assert night.any() and np.abs(e["sw_dn"][night]).max() == 0.0
+
+
+def test_f64_tensor_memory_kernels_variants(real_pack):
+    """Clear sky, clear-sky diagnostics, full per-gas vmr storage, an incident longwave flux, metric scaling and
+    latitude-dependent gravity on the tensor-memory kernels."""
+    st = R.synthetic.make_atmosphere(300, 64, dtype=np.float64, cld_frac=None, vmr_kind="full", with_lat=True)
+    rng = np.random.default_rng(4)
+    st["inc_flux_lw"] = rng.uniform(0.0, 0.02, (256, 300))
+    st["metric_scaling"] = np.linspace(1.0, 1.2, 300 * 65).reshape(300, 65)
+    for method, aer in (("clear_sky", False), ("all_sky_with_clear", True)):
+        kw = dict(method=method, aerosols=aer, seed=5)
+        e, o = run_engine(real_pack, st, np.float64, **kw), run_oracle(real_pack, st, np.float64, **kw)
+        keys = FLUX_KEYS + (tuple("clear_" + k for k in FLUX_KEYS) if method == "all_sky_with_clear" else ())
+        _check_f64(e, o, keys)
+
+
+def test_f64_tensor_memory_kernels_irregular_tables():
+    """Tables with unequal bands, a g-point count that is not a multiple of 32 and more than two bands per block (the
+    optics of these kernels are the generic ones); 33 layers."""
+    dims = R.synthetic.LutDims(n_bnd_lw=5, n_bnd_sw=4, gpts_lw=[4, 12, 8, 16, 6], gpts_sw=[10, 3, 16, 9],
+                               nsize_liq=8, nsize_ice=7, nrh=9)
+    pack = R.synthetic.make_lut_pack(seed=3, dims=dims)
+    st = R.synthetic.make_atmosphere(310, 33, dtype=np.float64, n_bnd_lw=5, n_bnd_sw=4, cld_frac=None)
+    kw = dict(method="all_sky", aerosols=True, seed=21)
+    e, o = run_engine(pack, st, np.float64, **kw), run_oracle(pack, st, np.float64, **kw)
+    _check_f64(e, o)
+    np.testing.assert_array_equal(e["cld_cover_lw"], o["cld_cover_lw"])
+
+
+def test_f64_tensor_memory_and_generic_kernels_agree(real_pack, monkeypatch):
+    """Same inputs through the tensor-memory kernels and the generic shared-memory kernels (RRTMGP_B200_KERNEL=generic)."""
+    st = R.synthetic.make_atmosphere(400, 64, dtype=np.float64, cld_frac=None, cos_zenith=None)
+    kw = dict(method="all_sky", aerosols=True, seed=31)
+    monkeypatch.delenv("RRTMGP_B200_KERNEL", raising=False)
+    a = run_engine(real_pack, st, np.float64, **kw)
+    monkeypatch.setenv("RRTMGP_B200_KERNEL", "generic")
+    b = run_engine(real_pack, st, np.float64, **kw)
+    _check_f64(a, b, rel=1e-11)
+    assert a["solver"].last_launch_count == b["solver"].last_launch_count
