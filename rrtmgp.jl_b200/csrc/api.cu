@@ -846,6 +846,10 @@ int rrtmgp_b200_comm_destroy(rrtmgp_b200_handle_t* h) {
     cudaDeviceSynchronize();
     for (int p = 0; p < c->nranks; ++p)
         if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+    // exported memory must outlive every importer's mapping: all ranks close first, then everybody frees
+    if (c->comm && c->token && c->copy_stream && c->nranks > 1 &&
+        c->nccl.AllReduce(c->token, c->token, 1, kNcclFloat32, kNcclSum, c->comm, c->copy_stream) == 0)
+        cudaStreamSynchronize(c->copy_stream);
     if (c->comm) c->nccl.CommDestroy(c->comm);
     if (c->gathered) cudaFree(c->gathered);
     if (c->token) cudaFree(c->token);
