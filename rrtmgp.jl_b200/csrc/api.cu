@@ -43,6 +43,7 @@ struct CommState {
     size_t view_bytes = 0;                   // bytes of one gathered view
     unsigned char* peer[kMaxRanks] = {};     // every rank's `gathered` as mapped here (peer[rank] == gathered)
     float* token = nullptr;                  // 2 floats for the framing all-reduces
+    bool ready = false;                      // comm_init completed on this rank (and, by its collective steps, on every rank)
 };
 
 struct rrtmgp_b200_handle {
@@ -847,7 +848,7 @@ int rrtmgp_b200_comm_destroy(rrtmgp_b200_handle_t* h) {
     for (int p = 0; p < c->nranks; ++p)
         if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
     // exported memory must outlive every importer's mapping: all ranks close first, then everybody frees
-    if (c->comm && c->token && c->copy_stream && c->nranks > 1 &&
+    if (c->ready && c->comm && c->token && c->copy_stream && c->nranks > 1 &&
         c->nccl.AllReduce(c->token, c->token, 1, kNcclFloat32, kNcclSum, c->comm, c->copy_stream) == 0)
         cudaStreamSynchronize(c->copy_stream);
     if (c->comm) c->nccl.CommDestroy(c->comm);
@@ -915,6 +916,7 @@ int rrtmgp_b200_comm_init(rrtmgp_b200_handle_t* h, const void* unique_id, int32_
         if (e != cudaSuccess) { fail_cuda(h, e); return bail(RRTMGP_B200_ERR_CUDA); }
         c->peer[p] = (unsigned char*)mapped;
     }
+    c->ready = true;
     return RRTMGP_B200_OK;
 }
 
