@@ -228,20 +228,55 @@ def main():
     s.set_state(st)
     R.compute_relative_humidity(s)
 
+    gather_how = None
+
     def join(solver):
-        """Every rank joins the engine's own communicator (NCCL id created by rank 0, shipped through torch.distributed)."""
-        box = [R.comm_unique_id() if rank == 0 else None]
+        """Every rank joins the engine's own communicator (NCCL id created by rank 0, shipped through torch.distributed).
+        Returns False -- on EVERY rank -- if any rank could not (no libnccl to dlopen, CUDA IPC not permitted ...): the
+        step then falls back to torch.distributed's all-gather after the kernels, as in round 1."""
+        err = "RRTMGP_BENCH_TORCH_GATHER set" if os.environ.get("RRTMGP_BENCH_TORCH_GATHER") else None
+        try:
+            box = [R.comm_unique_id() if (rank == 0 and err is None) else None]
+        except Exception as e:   # noqa: BLE001
+            box, err = [None], repr(e)
         dist.broadcast_object_list(box, src=0)
-        R.comm_init(solver, box[0], rank, world)
-
-    if world > 1:
-        join(s)
-
-    def step(seed):
-        if world > 1:
-            R.update_fluxes_gathered(s, seed)   # compute + all-gather of the eight (nlev, ncol) views, overlapped
+        if box[0] is not None:
+            try:
+                R.comm_init(solver, box[0], rank, world)
+            except Exception as e:   # noqa: BLE001
+                err = repr(e)
         else:
-            R.update_fluxes(s, seed)
+            err = err or "rank 0 could not create the NCCL id"
+        bad = torch.tensor([0.0 if err is None else 1.0], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if bad.item() > 0:
+            if rank == 0:
+                print(f"bench.py: rrtmgp_b200_comm_init failed on some rank ({err}); using torch.distributed all-gather", file=sys.stderr)
+            return False
+        return True
+
+    fallback_keys = ("lw_flux_up", "lw_flux_dn", "lw_flux_net", "sw_flux_up", "sw_flux_dn", "sw_flux_net", "sw_flux_dn_dir", "net_flux")
+
+    def make_step(solver, engine_gather):
+        if world == 1:
+            return lambda seed: R.update_fluxes(solver, seed)
+        if engine_gather:   # compute + all-gather of the eight (nlev, ncol) views, overlapped, behind the C ABI
+            return lambda seed: R.update_fluxes_gathered(solver, seed)
+        n = solver.grid_params.ncol
+        solver.gathered = {k: torch.empty(world * n, nlev, dtype=torch.float32, device=dev) for k in fallback_keys}
+
+        def fb(seed):
+            R.update_fluxes(solver, seed)
+            works = [dist.all_gather_into_tensor(solver.gathered[k], solver.buffers[k], async_op=True) for k in fallback_keys]
+            for w in works:
+                w.wait()
+        return fb
+
+    engine_gather = join(s) if world > 1 else False
+    if world > 1:
+        gather_how = ("rrtmgp_b200_update_fluxes_gathered (copy-engine pushes over NVLink + NCCL fences)" if engine_gather
+                      else "torch.distributed all_gather_into_tensor after the kernels (comm_init unavailable)")
+    step = make_step(s, engine_gather)
 
     def barrier():
         if world > 1:
@@ -359,7 +394,11 @@ def main():
         def e2e_step(seed):
             pipe.update_fluxes(seed)            # H2D of every input, update_fluxes!, D2H of every flux (column chunks)
             if world > 1:
-                R.all_gather_fluxes(s)          # + the gather of the eight views (grouped ncclAllGather)
+                if engine_gather:
+                    R.all_gather_fluxes(s)      # + the gather of the eight views (grouped ncclAllGather)
+                else:
+                    for w in [dist.all_gather_into_tensor(s.gathered[k], s.buffers[k], async_op=True) for k in fallback_keys]:
+                        w.wait()
                 torch.cuda.synchronize()
         for i in range(2):
             e2e_step(i)
@@ -430,9 +469,9 @@ def main():
                     m = min(ncol, n_sw - a)
                     dst[a:a + m].copy_(v[:m])
             s2.buffers["vmr"].copy_(s.buffers["vmr"])
-            if world > 1:
-                join(s2)
-            fn = (lambda i: R.update_fluxes_gathered(s2, 400 + i)) if world > 1 else (lambda i: R.update_fluxes(s2, 400 + i))
+            eg2 = join(s2) if (world > 1 and engine_gather) else False
+            step2 = make_step(s2, eg2)
+            fn = lambda i: step2(400 + i)
             fn(0)
             barrier()
             ms_s = torch.tensor([time_call(fn, 3)], dtype=torch.float64, device=dev)
@@ -440,9 +479,9 @@ def main():
                 dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
             sweep.append({"ncol_per_gpu": n_sw, "value": world * n_sw / (float(ms_s.item()) * 1e-3), "unit": "columns/s",
                           "ms_per_step": float(ms_s.item())})
-            if world > 1:
+            if eg2:
                 R.comm_destroy(s2)
-            del s2
+            del s2, step2
             torch.cuda.empty_cache()
 
     cpu_baseline = None
@@ -467,7 +506,7 @@ def main():
                 "config": config_of(ncol, nlay, world),
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_fp32": roofline_fp32, "roofline_issue": roofline_issue, "cpu_baseline": cpu_baseline,
-                "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants, "sweep": sweep, "gather_check": gather_check}
+                "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants, "sweep": sweep, "gather_check": gather_check, "gather": gather_how}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
