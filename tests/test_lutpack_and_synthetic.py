@@ -73,3 +73,36 @@ def test_atmosphere_recipe():
     assert (st["cos_zenith"] <= 0).any() and (st["cos_zenith"] > 0).any()
     rh = R.synthetic.relative_humidity(st["layerdata"][:, :, 1], st["layerdata"][:, :, 2], st["vmr_h2o"])
     np.testing.assert_array_equal(rh, st["layerdata"][:, :, 3])
+
+
+def test_float32_parity_gate_rules():
+    """The per-column Float32 gate of the GPU suite (tests/helpers.py::gate_f32) on hand-made arrays: within the
+    threshold passes; above it passes only beside a comparably wrong Float32 oracle in the SAME column; the strict
+    variant also wants the Float32 oracle above the threshold there, or the engine within a tenth of the threshold of it."""
+    import numpy as np
+    import pytest
+    from helpers import LEDGER, gate_f32
+    ref = np.zeros((4, 5))
+    tol = 0.1
+    ok = ref + 0.05
+    n0 = len(LEDGER)
+    assert gate_f32("k", ok, ref, tol)["bar"] == "threshold"
+    eng = ref.copy(); eng[2, 1] = 0.14                       # one column above the threshold
+    with pytest.raises(AssertionError):
+        gate_f32("k", eng, ref, tol)                         # no Float32 oracle to excuse it
+    o32 = ref.copy(); o32[1, 1] = 0.2                        # the oracle is wrong in ANOTHER column: no excuse
+    with pytest.raises(AssertionError):
+        gate_f32("k", eng, ref, tol, o32)
+    o32 = ref.copy(); o32[2, 1] = 0.12                       # same column, engine <= 1.5 x oracle error, oracle above the threshold
+    row = gate_f32("k", eng, ref, tol, o32, strict=True)
+    assert row["passed"] and row["columns_excused_by_f32_oracle"] == 1 and row["engine_max_err_column"] == 2
+    o32[2, 1] = 0.099                                        # oracle just below the threshold, engine 0.14: |e - o32| = 0.041 > 0.01
+    gate_f32("k", eng, ref, tol, o32)                        # the plain rule excuses it (0.14 <= 1.5 * 0.099)
+    with pytest.raises(AssertionError):
+        gate_f32("k", eng, ref, tol, o32, strict=True)       # the strict rule does not
+    eng[2, 1] = 0.105                                        # engine tracks the oracle to within a tenth of the threshold
+    assert gate_f32("k", eng, ref, tol, o32, strict=True)["passed"]
+    eng[2, 1] = 0.31; o32[2, 1] = 0.2                        # more than 1.5 x the oracle's error: never
+    with pytest.raises(AssertionError):
+        gate_f32("k", eng, ref, tol, o32)
+    del LEDGER[n0:]                                          # these rows are not parity evidence
