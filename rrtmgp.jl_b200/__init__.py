@@ -4,7 +4,7 @@ Host-side mirror of the reference's Layer-2 interface (`RRTMGPSolver`, `update_f
 getters; `solver.py`) over a C-ABI CUDA library (`csrc/`, `include/rrtmgp_b200.h`)."""
 import importlib as _importlib
 
-from . import lutpack, synthetic, tables  # noqa: F401
+from . import hdf5min, lutpack, synthetic, tables  # noqa: F401
 from ._lib import RRTMGPB200Error, build_ext  # noqa: F401
 
 

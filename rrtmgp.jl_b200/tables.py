@@ -14,8 +14,9 @@ File access is kept apart from the table logic:
   checked against the Julia source it cites.
 * `open_dataset(path)` reads NetCDF classic / 64-bit-offset files with `scipy.io.netcdf_file`.  The
   artifact ships NetCDF-4 (HDF5) files; those are read through `netCDF4` or `h5py` when one of them is
-  importable, otherwise the error says how to convert (`nccopy -k nc6 in.nc out.nc`).  Nothing here falls
-  back to synthetic data.
+  importable, otherwise through the built-in minimal HDF5 reader `hdf5min.py` (pure Python; its docstring says
+  what it covers and that it was validated only against this repo's own test writer); if that refuses the file
+  the error says how to convert (`nccopy -k nc6 in.nc out.nc`).  Nothing here falls back to synthetic data.
 """
 from __future__ import annotations
 
@@ -85,13 +86,22 @@ def open_dataset(path: str) -> Dataset:
         try:
             import h5py  # type: ignore
         except ImportError:
+            h5py = None
+        if h5py is not None:
+            with h5py.File(path, "r") as h5:
+                variables = {k: np.array(v[...]) for k, v in h5.items() if isinstance(v, h5py.Dataset)}
+                dims = {k: int(v.shape[0]) for k, v in h5.items()
+                        if isinstance(v, h5py.Dataset) and v.attrs.get("CLASS", b"") == b"DIMENSION_SCALE"}
+            return Dataset(dims, variables)
+        # neither library: the built-in minimal reader (hdf5min.py states what it covers and how it was validated)
+        from . import hdf5min
+        try:
+            dims, variables = hdf5min.read_netcdf4(path)
+        except hdf5min.HDF5Error as e:
             raise TableError(
-                f"{path} is a NetCDF-4/HDF5 file and neither netCDF4 nor h5py is installed; convert it once "
-                f"with `nccopy -k nc6 {path} out.nc` (64-bit-offset classic format) and pass the copy") from None
-        with h5py.File(path, "r") as h5:
-            variables = {k: np.array(v[...]) for k, v in h5.items() if isinstance(v, h5py.Dataset)}
-            dims = {k: int(v.shape[0]) for k, v in h5.items()
-                    if isinstance(v, h5py.Dataset) and v.attrs.get("CLASS", b"") == b"DIMENSION_SCALE"}
+                f"{path} is a NetCDF-4/HDF5 file that the built-in reader cannot read ({e}); install netCDF4 or "
+                f"h5py, or convert it once with `nccopy -k nc6 {path} out.nc` (64-bit-offset classic format) and "
+                f"pass the copy") from None
         return Dataset(dims, variables)
     raise TableError(f"{path}: not a NetCDF file (magic {magic!r})")
 
