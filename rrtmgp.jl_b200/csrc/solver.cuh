@@ -224,6 +224,10 @@ struct Warp {
     int gpt, ibnd, bl, b_first, nb;
     bool lane_on;
     unsigned mask[NOWN];
+    // set once per column by kernels that scan cld_frac anyway: every cloud fraction of the column is exactly 0 or 1, so the
+    // McICA sample is the same for every g-point -- mask = (cld_frac > 0), no draws (see mcica)
+    bool cf_binary = false;
+    unsigned cf_words[NOWN];
 
     __device__ __forceinline__ Warp(const SolveParams<FT>& P_, unsigned char* wbase, int lane_, long long col_,
                                     const unsigned char* sblob_ = nullptr, int staged_ = 0, const FT* svmr_ = nullptr)
@@ -554,6 +558,14 @@ struct Warp {
 #pragma unroll
         for (int i = 0; i < NOWN; ++i) mask[i] = 0u;
         if (!(P.use_cloud != 0) || cld_finish <= 0) return 0;
+        if (cf_binary) {
+            // cloud_optics.jl:276-301 with every fraction 0 or 1: the threshold 1 - cf of a cloudy layer is exactly 0, so
+            // `r >= 1 - cf` holds for any draw r in [0, 1) (fresh, reused or rescaled) and a layer with cf = 0 is clear:
+            // bit-identical to the loop below, without the draws
+#pragma unroll
+            for (int i = 0; i < NOWN; ++i) mask[i] = cf_words[i];
+            return __popc(__ballot_sync(0xffffffffu, lane_on));
+        }
         const FT* cf = P.io.cld_frac + (size_t)col * nlay;
         const int swflag = LW ? 0 : 1;
         FT cf_p1 = __ldg(cf + cld_finish - 1);

@@ -270,11 +270,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
         if (HAS_CLD) {
             const FT* cf = P.io.cld_frac + (size_t)col * nlay;
             unsigned lo = 0xffffffffu, hi = 0;
-            for (int k = lane; k < nlay; k += 32)
-                if (__ldg(cf + k) > FT(0)) { lo = lo < (unsigned)(k + 1) ? lo : (unsigned)(k + 1); hi = hi > (unsigned)(k + 1) ? hi : (unsigned)(k + 1); }
+            bool frac = false;   // a fraction strictly between 0 and 1 (or above 1): the sample needs its draws
+#pragma unroll
+            for (int j = 0; j < NOWN; ++j) {
+                const int k = lane + 32 * j;
+                const FT c = k < nlay ? __ldg(cf + k) : FT(0);
+                if (c > FT(0)) { lo = lo < (unsigned)(k + 1) ? lo : (unsigned)(k + 1); hi = hi > (unsigned)(k + 1) ? hi : (unsigned)(k + 1); }
+                frac = frac || (c > FT(0) && c != FT(1));
+                W.cf_words[j] = __ballot_sync(0xffffffffu, c > FT(0));
+            }
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
             if (hi > 0) { cld_start = (int)lo; cld_finish = (int)hi; }
+            W.cf_binary = !__any_sync(0xffffffffu, frac);
         }
         const FT mu0 = LWG ? FT(1) : __ldg(P.io.cos_zenith + col);
         const bool day = LWG || mu0 > FT(0);

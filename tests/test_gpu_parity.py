@@ -60,6 +60,27 @@ def test_cloudy_sky_mcica_f32(real_pack, cld_frac):
     assert (e["cld_cover_lw"] >= 0).all() and (e["cld_cover_lw"] <= 1).all()
 
 
+def test_binary_cloud_fraction_shortcut_f32(real_pack):
+    """Columns whose cloud fractions are all exactly 0 or 1 take the draw-free McICA path of the fast kernels
+    (`Warp::mcica`, cloud_optics.jl:276-301 with thresholds 1 - cf = 0): same masks as the oracle's loop, also with
+    clear layers inside the cloudy span, next to columns that do need their draws."""
+    st = R.synthetic.make_atmosphere(384, 64, aerosols=False, cld_frac=1.0)
+    cf = st["cld_frac"]                                        # [ncol][nlay]
+    cloudy = cf > 0
+    rng = np.random.default_rng(5)
+    col = np.arange(cf.shape[0])[:, None]
+    cf[cloudy & (rng.random(cf.shape) < 0.3) & (col % 3 == 1)] = 0.0      # every third column: holes in the deck
+    frac_cols = np.arange(cf.shape[0]) % 3 == 0                           # every third column: fractional cover
+    cf[frac_cols] = np.where(cloudy[frac_cols], rng.random((int(frac_cols.sum()), cf.shape[1])), 0.0).astype(cf.dtype)
+    binary = ((cf == 0) | (cf == 1)).all(axis=1)
+    assert (~binary).sum() >= 100 and ((cf[binary] > 0).any(axis=1)).sum() >= 100   # (a third of the columns is cloud free)
+    kw = dict(method="all_sky", aerosols=False, seed=31)
+    e, o = run_engine(real_pack, st, np.float32, **kw), run_oracle(real_pack, st, np.float64, **kw)
+    _check_f32(e, o, F32_LW, F32_SW_CLOUDY, run_oracle(real_pack, st, np.float32, **kw))
+    np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(np.float32))
+    np.testing.assert_array_equal(e["cld_cover_sw"].astype(np.float64), o["cld_cover_sw"].astype(np.float32))
+
+
 def test_all_sky_with_aerosols_f32(real_pack):
     """BASELINE config 4 on a subsample: all-sky with aerosols, Float32 vs Float64 oracle."""
     st = R.synthetic.make_atmosphere(1024, 64)
