@@ -37,6 +37,15 @@
 #pragma once
 #include "solver.cuh"
 
+// ABLATION BUILDS (tools/ablation.sh, DESIGN.md section 7 "where the time goes"): -DRB_WHATIF=n removes one part of the kernels
+// so that its cost in elapsed time can be measured (the results of such a build are wrong by construction; the
+// shipped library is built with RB_WHATIF = 0 and contains none of this).  1: band records (phase 1) only for the
+// first g-point block of a column; 2: no McICA sampling; 3: no second sweeps; 8: 1 + 2 + 3; 4: no table gathers;
+// 9: table gathers always from the same few rows (all L1 hits); 5: trivial two-stream coefficients; 6: no level-store writes.
+#ifndef RB_WHATIF
+#define RB_WHATIF 0
+#endif
+
 namespace rb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -295,12 +304,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
         for (int g0 = 32 * blk0; g0 < 32 * blk1; g0 += 32) {
             W.set_block(g0);
             __syncwarp();
+#if RB_WHATIF == 2 || RB_WHATIF == 8
+            W.mask[0] = W.mask[NOWN - 1] = 0xffffffffu;
+#else
             if (HAS_CLD) n_cloudy += W.mcica(col_key, cld_start, cld_finish);
+#endif
             // band records are built half a column (32 layers) at a time, just before the sweep needs them
             FT aod_e = 0.f, aod_s = 0.f;
             const bool aod_here = !LWG && HAS_AER && P.io.aod_ext != nullptr && P.aero.iband_550nm >= W.b_first + 1 &&
                                   P.aero.iband_550nm <= W.b_first + W.nb;
             auto build_records = [&](int half) {
+#if RB_WHATIF == 1 || RB_WHATIF == 8
+                if (g0 != 32 * blk0) return;
+#endif
                 __syncwarp();
                 FT e, sc;
                 W.phase1(e, sc, half);
@@ -348,8 +364,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 G.v1 = *reinterpret_cast<const float4*>(r + 4);
 #pragma unroll
                 for (int gi = 0; gi < NG; ++gi) G.sc[gi] = *reinterpret_cast<const float4*>(r + 12 + 4 * gi);
+#if RB_WHATIF == 9
+                const int ia = __float_as_int(G.s.z) & 1, ib = (__float_as_int(G.s.w) & 1) + KT;
+                const int ma = __float_as_int(G.x.w) & 1, mb = ma + (ib - ia);
+#else
                 const int ia = __float_as_int(G.s.z), ib = __float_as_int(G.s.w);   // (jp-1, jt, je1), (jp-1, jt+1, je2)
                 const int ma = __float_as_int(G.x.w), mb = ma + (ib - ia);          // (jt, je1), (jt+1, je2): MT == KT
+#endif
+#if RB_WHATIF == 4
+                {
+                    const float f = __int_as_float((ia & 0xff) | 0x3f000000), h = __int_as_float((ib & 0xff) | 0x3e000000);
+#pragma unroll
+                    for (int i = 0; i < (LWG ? 8 : 1); ++i) G.c2[i] = make_float2(f * 1e-3f, h);
+#pragma unroll
+                    for (int i = 0; i < (LWG ? 1 : 8); ++i) G.c1[i] = f * 1e-3f;
+#pragma unroll
+                    for (int i = 0; i < 4 * NG; ++i) G.m[i] = make_float4(f * 1e-4f, h * 1e-4f, f * 1e-5f, h * 1e-5f);
+                    (void)ma; (void)mb;
+                    return;
+                }
+#endif
                 if (LWG) {   // {kmajor, planck_fraction} pairs
                     const float2* pa = reinterpret_cast<const float2*>(major_lane) + ia;
                     const float2* pb = reinterpret_cast<const float2*>(major_lane) + ib;
@@ -470,8 +504,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     const FT su = Num<FT>::pi() * (lev_top * C.emis_fac - C.q * dB);
                     const FT sd = Num<FT>::pi() * (lev_bot * C.emis_fac + C.q * dB);
                     // level kl: F_dn(kl) = A F_dn(kl+1) + B ; F_up(kl) = albedo F_dn(kl) + src
+#if RB_WHATIF != 6
                     tmem_st2(tA + 2 * kl, C.Tdif * denom, (C.Rdif * src + sd) * denom);
                     st_alpha(kl, albedo);
+#endif
                     const FT src_lev = src;
                     src = su + C.Tdif * denom * (src + albedo * sd);
                     albedo = C.Rdif + C.Tdif * C.Tdif * albedo * denom;
@@ -494,7 +530,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     FT* sk = stage + lane;
                     for (int k = ks; k < ke; ++k) {                       // single basic block
                         gather_r(rk, mw & 1u, G);
+#if RB_WHATIF == 5
+                        LwCoef C; C.Rdif = ssa * 0.5f; C.Tdif = 0.5f + tau * 1e-3f; C.emis_fac = 0.3f + g; C.q = tau * 1e-2f;
+#else
                         const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
+#endif
                         const FT denom = hrcp(1.f - C.Rdif * albedo);
                         const FT bk = *pk;
                         const FT inc_k = bk * pf;
@@ -533,7 +573,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 // reads its (A, B) pairs with ONE tcgen05.ld.x16 (and the albedos with one .x8 or eight LDS) and has no
                 // per-level TMEM round trip; the top tile of a column whose layer count is not a multiple of 8 and the
                 // tile that straddles the TMEM / shared-memory albedo split take the level-by-level path.
-                for (int kc = (nlay - 1) & ~7; kc >= 0; kc -= 8) {     // 8 levels x (dn, albedo * dn) per tile
+                for (int kc = (nlay - 1) & ~7; kc >= ((RB_WHATIF == 3 || RB_WHATIF == 8) ? 1 << 20 : 0); kc -= 8) {     // 8 levels x (dn, albedo * dn) per tile
                     const int ktop = kc + 7 < nlay - 1 ? kc + 7 : nlay - 1;
                     const bool al_tmem = kc + 8 <= kAlphaTmemLevels, al_smem = kc >= kAlphaTmemLevels;
                     if (ktop == kc + 7 && (al_tmem || al_smem)) {
@@ -722,12 +762,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 // layer k: coefficients, TMEM store, marching update; returns d_{k+1} (before the update)
                 auto march = [&](int k) -> FT {
                     FT Rdir, Tdir, Rdif, Tdif;
+#if RB_WHATIF == 5
+                    Rdir = ssa * 0.3f; Tdir = 0.2f + tau * 1e-3f; Rdif = g * 0.1f + 0.1f; Tdif = 0.5f + tau * 1e-3f;
+#else
                     sw_2stream_coeffs(tau, ssa, g, mu0, inv_mu0, Rdir, Tdir, Rdif, Tdif);
+#endif
                     const FT su = Rdir * dir, sd = Tdir * dir;       // dir = direct flux at level k+1
                     const FT denom = hrcp(1.f - Rdif * beta);
                     // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
+#if RB_WHATIF != 6
                     tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
                     st_alpha(k, beta);
+#endif
                     const FT d_above = d;
                     d = sd + Tdif * denom * (d + beta * su);
                     beta = Rdif + Tdif * Tdif * beta * denom;
@@ -800,7 +846,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     if (spectral && (lane & 15) == 0) { band_add(UP, 0, hu); band_add(DN, 0, hdd); }
                 }
                 tmem_wait_st();
-                for (int kc = 0; kc < nlay; kc += 8) {                // 8 levels x (F_up, beta * F_up) per tile
+                for (int kc = ((RB_WHATIF == 3 || RB_WHATIF == 8) ? 1 << 20 : 0); kc < nlay; kc += 8) {                // 8 levels x (F_up, beta * F_up) per tile
                     const int kend = kc + 8 < nlay ? kc + 8 : nlay;
                     const bool be_tmem = kc + 8 <= kAlphaTmemLevels, be_smem = kc >= kAlphaTmemLevels;
                     if (kend == kc + 8 && (be_tmem || be_smem)) {       // one tcgen05.ld.x16 (+ .x8) per tile, as in the LW sweep
