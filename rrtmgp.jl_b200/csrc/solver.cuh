@@ -186,6 +186,42 @@ __device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, const FT* s
     }
 }
 
+// Small tables a fast kernel reads in phases 0 / 1: where each one lives (its copy inside the staged part of the
+// small-table block, or the global array) is resolved ONCE per CTA into a shared-memory pointer table, so a use is
+// one 64-bit shared load instead of the offset / range-check / select sequence (profiles/r2p: 50 of the 620
+// instructions of a band pass).
+enum SmallTable { TB_T_REF = 0, TB_LN_P_REF, TB_T_PLANCK, TB_TOT_PLANCK, TB_GPT2BND, TB_KEY_SPECIES, TB_VMR_REF,
+                  TB_MINOR_BND_ST, TB_MINOR_BND_ST_UPPER, TB_MINOR_GASDATA, TB_MINOR_GASDATA_UPPER, TB_LIQDATA, TB_ICEDATA,
+                  TB_AERO_DUST, TB_AERO_BIN_LIMS, TB_AERO_RH, TB_COUNT };
+
+template <typename FT>
+__device__ __forceinline__ void fill_small_table_pointers(const void** tp, const SolveParams<FT>& P, const unsigned char* sblob,
+                                                          int staged, int tid) {
+    if (tid >= TB_COUNT) return;
+    const GasLut<FT>& L = P.lut;
+    const void* g = nullptr;
+    switch (tid) {
+        case TB_T_REF: g = L.t_ref; break;
+        case TB_LN_P_REF: g = L.ln_p_ref; break;
+        case TB_T_PLANCK: g = L.t_planck; break;
+        case TB_TOT_PLANCK: g = L.tot_planck; break;
+        case TB_GPT2BND: g = L.gpt2bnd; break;
+        case TB_KEY_SPECIES: g = L.key_species; break;
+        case TB_VMR_REF: g = L.vmr_ref; break;
+        case TB_MINOR_BND_ST: g = L.minor_bnd_st[0]; break;
+        case TB_MINOR_BND_ST_UPPER: g = L.minor_bnd_st[1]; break;
+        case TB_MINOR_GASDATA: g = L.minor_gasdata[0]; break;
+        case TB_MINOR_GASDATA_UPPER: g = L.minor_gasdata[1]; break;
+        case TB_LIQDATA: g = P.cld.liqdata; break;
+        case TB_ICEDATA: g = P.cld.icedata; break;
+        case TB_AERO_DUST: g = P.aero.dust; break;
+        case TB_AERO_BIN_LIMS: g = P.aero.size_bin_limits; break;
+        default: g = P.aero.rh_levels; break;
+    }
+    const long long off = reinterpret_cast<const unsigned char*>(g) - L.blob;
+    tp[tid] = (g != nullptr && off >= 0 && off < staged) ? static_cast<const void*>(sblob + off) : g;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-warp context shared by the kernels below
 // ---------------------------------------------------------------------------------------------
@@ -210,7 +246,8 @@ struct Warp {
     // fast kernels: shared-memory copy of the small-table block (GasLut::blob) and of the global-mean vmr array
     const unsigned char* sblob;
     const int staged;   // bytes of the block that are staged (a prefix ending at a table boundary)
-    const FT* svmr;
+    const FT* svmr;     // element -1 holds 1 (dry air, gas index 0): svmr[ig - 1] serves every ig >= 0
+    const void* const* tptr = nullptr;   // fast kernels: the CTA's small-table pointer table (fill_small_table_pointers)
     // per-lane registers for the layers this lane owns in phase 0/1: lane, lane+32, lane+64
     FT own_h2o[NOWN], own_g3[NOWN], own_dens[NOWN], own_cdry[NOWN];   // own_g3: vmr of gas 3 (ozone in VmrGM)
     AeroLayer own_aero[NOWN];
@@ -239,12 +276,10 @@ struct Warp {
     // words per band of the Planck buffer
     __device__ __forceinline__ int plk_stride() const { return FUSED ? (NOSCAT ? 2 * nlev : nlev + 1) : 2 * nlev; }
 
-    // A small table: the global array, or (fast kernels) its copy inside the staged part of the block
-    template <class T> __device__ __forceinline__ const T* tb(const T* g) const {
-        if (FUSED) {
-            const long long off = reinterpret_cast<const unsigned char*>(g) - L.blob;
-            if (off >= 0 && off < staged) return reinterpret_cast<const T*>(sblob + off);
-        }
+    // A small table: the global array, or (fast kernels) wherever the CTA's pointer table says it lives -- its copy
+    // inside the staged part of the block, or the global array.  `sel` (0 / 1) picks the upper-atmosphere twin.
+    template <class T> __device__ __forceinline__ const T* tb(const T* g, int idx, int sel = 0) const {
+        if (FUSED) return reinterpret_cast<const T*>(tptr[idx + sel]);
         return g;
     }
     // vmr of gas ig at layer k = lane + 32 j.  Fast kernels: the two gases that vary per layer in VmrGM (1 = h2o,
@@ -271,9 +306,9 @@ struct Warp {
         const FT* ld = P.io.layerdata + (size_t)col * nlay * 4;
         const bool use_cloud = P.use_cloud != 0, use_aero = P.use_aero != 0;
         const int n_t = L.n_t;
-        const FT* t_ref = tb(L.t_ref);
-        const FT* ln_p_ref = tb(L.ln_p_ref);
-        const FT* t_planck = tb(L.t_planck);
+        const FT* t_ref = tb(L.t_ref, TB_T_REF);
+        const FT* ln_p_ref = tb(L.ln_p_ref, TB_LN_P_REF);
+        const FT* t_planck = tb(L.t_planck, TB_T_PLANCK);
 #pragma unroll
         for (int j = 0; j < NOWN; ++j) {
             const int k = lane + 32 * j;
@@ -310,10 +345,10 @@ struct Warp {
                         const int pos = __ffs((int)sized) - 1;
                         sized &= sized - 1u;
                         const int i = pos < 5 ? (pos == 0 ? 0 : 6 + pos) : (pos == 5 ? 1 : 5 + pos);
-                        bins |= (unsigned)merra_size_bin<FUSED>(tb(P.aero.size_bin_limits), P.aero.nbin, __ldg(as + i)) << (3 * pos);
+                        bins |= (unsigned)merra_size_bin<FUSED>(tb(P.aero.size_bin_limits, TB_AERO_BIN_LIMS), P.aero.nbin, __ldg(as + i)) << (3 * pos);
                     }
                     int loc; FT f;
-                    interp1d_loc_factor<FUSED>(__ldg(ld + 4 * k + 3), tb(P.aero.rh_levels), P.aero.nrh, loc, f);
+                    interp1d_loc_factor<FUSED>(__ldg(ld + 4 * k + 3), tb(P.aero.rh_levels, TB_AERO_RH), P.aero.nrh, loc, f);
                     int off0, bs0;
                     aero_entry(P.aero, __ffs((int)act) - 1, bins, loc, off0, bs0);
                     own_aero[j] = AeroLayer{act, bins, loc, off0, bs0};
@@ -361,7 +396,7 @@ struct Warp {
         const int n_gpt = L.n_gpt;
         lane_on = g0 + lane < n_gpt;
         gpt = lane_on ? g0 + lane : n_gpt - 1;
-        const int* gpt2bnd = tb(L.gpt2bnd);
+        const int* gpt2bnd = tb(L.gpt2bnd, TB_GPT2BND);
         b_first = ldt<FUSED>(gpt2bnd + g0);
         const int b_last = ldt<FUSED>(gpt2bnd + (g0 + 31 < n_gpt ? g0 + 31 : n_gpt - 1));
         nb = b_last - b_first + 1;
@@ -404,10 +439,10 @@ struct Warp {
             const FT g3_j = pick(own_g3, j);
             auto vmrq = [&](int ig) -> FT {
                 if (gm_fast) {
-                    FT v = svmr[ig > 0 ? ig - 1 : 0];
+                    FT v = svmr[ig - 1];              // svmr[-1] = 1: dry air
                     v = ig == 1 ? vmr_h2o : v;
                     v = ig == 3 ? g3_j : v;
-                    return ig == 0 ? FT(1) : v;
+                    return v;
                 }
                 return vmr_of(ig, k, j);
             };
@@ -415,7 +450,7 @@ struct Warp {
                 const int ib = b_first + b;
                 FT* r = rec + (size_t)kr * P.rec_row + b * RW;
                 // gas_optics.jl:129-170
-                const int* ksp = tb(L.key_species) + 2 * ((tropo - 1) + 2 * ib);
+                const int* ksp = tb(L.key_species, TB_KEY_SPECIES) + 2 * ((tropo - 1) + 2 * ib);
                 const int ig1 = ldt<FUSED>(ksp), ig2 = ldt<FUSED>(ksp + 1);
                 const FT vmr1 = vmrq(ig1), vmr2 = vmrq(ig2);
                 int je[2];
@@ -425,7 +460,7 @@ struct Warp {
                 const int sc0 = FUSED ? 12 : 4;
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                    const FT* vr = tb(L.vmr_ref) + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
+                    const FT* vr = tb(L.vmr_ref, TB_VMR_REF) + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
                     FT eta_half = hdiv(ldt<FUSED>(vr + 2 * ig1), ldt<FUSED>(vr + 2 * ig2));
                     FT col_mix = vmr1 + eta_half * vmr2;
                     FT eta = vmr1 * hdiv(FT(1), col_mix);
@@ -442,8 +477,8 @@ struct Warp {
                 // (gas_optics.jl:430-444: (vmr_h2o + 1) * col_dry).
                 const int soff = (FUSED && !LW) ? 1 : 0;
                 const int nslots = FUSED ? 4 * L.n_minor_groups : L.nminor_max;
-                const int* bst = tb(L.minor_bnd_st[tropo - 1]);
-                const int4* gdt = reinterpret_cast<const int4*>(tb(L.minor_gasdata[tropo - 1]));
+                const int* bst = tb(L.minor_bnd_st[tropo - 1], TB_MINOR_BND_ST, tropo - 1);
+                const int4* gdt = reinterpret_cast<const int4*>(tb(L.minor_gasdata[tropo - 1], TB_MINOR_GASDATA, tropo - 1));
                 const int m0 = ldt<FUSED>(bst + ib), nmin = ldt<FUSED>(bst + ib + 1) - m0;
                 auto minor_scaling = [&](int i) -> FT {      // gas_optics.jl:344-412, absorber i of this (band, tropo)
                     const int4 gd = ldt<FUSED>(gdt + (m0 + i));
@@ -461,10 +496,11 @@ struct Warp {
                     }
                     return scaling;
                 };
-                if (FUSED && !LW) r[sc0] = (vmr_h2o + FT(1)) * col_dry;
+                if constexpr (FUSED) {   // unused slots are zero: clear the groups first (128-bit stores), then fill
+                    for (int gi = 0; gi < L.n_minor_groups; ++gi) reinterpret_cast<float4*>(r + sc0)[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!LW) r[sc0] = (vmr_h2o + FT(1)) * col_dry;
+                }
                 for (int i = 0; i < nmin; ++i) r[sc0 + soff + i] = minor_scaling(i);
-                if (FUSED)
-                    for (int i = soff + nmin; i < nslots; ++i) r[sc0 + i] = FT(0);
                 FT* rc = r + sc0 + nslots;   // cloud (3) then aerosol (3)  [FUSED: aerosol-only / cloud+aerosol products]
                 FT tc = FT(0), sc = FT(0), gc = FT(0);
                 // cloud_optics.jl:70-138 (2-stream) / :1-50 (1-scalar), for layers that can be cloudy
@@ -472,8 +508,8 @@ struct Warp {
                     if ((cld_j >> 16) & 1) {
                         const CldLut<FT>& C = P.cld;
                         size_t kk = (size_t)col * nlay + k;
-                        const FT* liq = tb(C.liqdata) + (size_t)3 * C.nsize_liq * ib;
-                        const FT* ice = tb(C.icedata) + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
+                        const FT* liq = tb(C.liqdata, TB_LIQDATA) + (size_t)3 * C.nsize_liq * ib;
+                        const FT* ice = tb(C.icedata, TB_ICEDATA) + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
                         FT tl, tls, tlsg, ti, tis, tisg;
                         cld_eval<FUSED>(C.nsize_liq, liq, cld_j & 0xff, cld_fl_j, __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
                         cld_eval<FUSED>(C.nsize_ice, ice, (cld_j >> 8) & 0xff, cld_fi_j, __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
@@ -494,7 +530,7 @@ struct Warp {
                     if ((cj >> 17) & 1) {
                         size_t kk = ((size_t)col * nlay + k) * 15;
                         FT tsa, tsga;
-                        lookup_aerosol<FUSED>(P.aero, tb(P.aero.dust), ib, P.io.aero_mass + kk, aero_j, rh_f_j, ta, tsa, tsga);
+                        lookup_aerosol<FUSED>(P.aero, tb(P.aero.dust, TB_AERO_DUST), ib, P.io.aero_mass + kk, aero_j, rh_f_j, ta, tsa, tsga);
                         if (!LW && ib + 1 == P.aero.iband_550nm) { aod_e += ta; aod_s += tsa; }   // :96-116
                         if (NOSCAT) {
                             ta = ta - tsa;
@@ -535,7 +571,7 @@ struct Warp {
                 }
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {
-                    const FT* totplnk = tb(L.tot_planck) + (size_t)L.n_t_plnk * ib;
+                    const FT* totplnk = tb(L.tot_planck, TB_TOT_PLANCK) + (size_t)L.n_t_plnk * ib;
                     // per band: B(t_lev[0..nlay]), then B(t_lay) (no-scattering only), B(t_sfc) last;
                     // the fast kernels keep just the nlev + 1 values they use
                     // (fast no-scattering kernel: B(t_lev) [nlev], B(t_sfc), then B(t_lay) [nlay])

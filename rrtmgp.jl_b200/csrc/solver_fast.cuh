@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(8) uint64_t blob_bar;
+    __shared__ const void* small_tables[TB_COUNT];   // where each small table lives (solver.cuh)
     constexpr bool LW = MODE == MODE_LW_2STREAM;
     constexpr bool NOSCAT = MODE == MODE_LW_NOSCAT;
     constexpr bool LWG = LW || NOSCAT;      // longwave gas optics: {kmajor, Planck fraction} pairs, no Rayleigh, always "day"
@@ -179,14 +180,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
     // table, cloud and aerosol tables) into shared memory with one TMA bulk copy: the persistent CTA reads them
     // ~10^5 times per column and they would otherwise fight the k-distribution gathers for L1.
     unsigned char* sblob = smem_raw + F.off_blob;
-    float* svmr = P.vmr_kind == 0 ? reinterpret_cast<float*>(smem_raw + F.off_vmr) : nullptr;
+    float* svmr = P.vmr_kind == 0 ? reinterpret_cast<float*>(smem_raw + F.off_vmr) + 1 : nullptr;
     if (threadIdx.x == 0) {
         mbar_init(&blob_bar, 1);
         mbar_expect_tx(&blob_bar, (uint32_t)F.staged_bytes);
         if (F.staged_bytes > 0) tma_bulk_g2s(sblob, P.lut.blob, (uint32_t)F.staged_bytes, &blob_bar);
     }
-    if (svmr != nullptr)
-        for (int i = threadIdx.x; i < P.ngas; i += blockDim.x) svmr[i] = __ldg(P.io.vmr + i);
+    if (svmr != nullptr)   // svmr[-1] = 1 (dry air), svmr[ig - 1] = global-mean vmr of gas ig
+        for (int i = threadIdx.x; i <= P.ngas; i += blockDim.x) svmr[i - 1] = i == 0 ? 1.f : __ldg(P.io.vmr + i - 1);
+    fill_small_table_pointers(small_tables, P, sblob, F.staged_bytes, (int)threadIdx.x);
     if (warp == 0) tmem_alloc(&tmem_base_smem, 512u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
         const int share = (int)(item & ((1 << split_log2) - 1));
         col_next = next_column();
         Warp<FT, MODE, NOWN, true> W(P, wbase, lane, col, sblob, F.staged_bytes, svmr);
+        W.tptr = small_tables;
         {
             const long long nc = col_next >> split_log2;
             if (nc < P.ncol && nc != col) {

@@ -60,15 +60,15 @@ static int plan_smem_fast(SolveParams<float>& P, FastSmem& F, int max_smem_optin
     P.warp_bytes = off;
     // CTA-shared tail: the staged small-table block and the global-mean vmr array
     int tail = kFastWarps * off;
-    F.off_vmr = tail;  tail = align_up(tail + (P.ngas > 0 ? P.ngas : 1) * (int)sizeof(float), 128);
+    F.off_vmr = tail;  tail = align_up(tail + ((P.ngas > 0 ? P.ngas : 1) + 1) * (int)sizeof(float), 128);
     F.off_blob = tail;
-    int room = max_smem_optin - 64 - tail;   // 64: static shared memory of the kernel
+    int room = max_smem_optin - 256 - tail;   // 256: static shared memory of the kernel (barrier, pointer table)
     // Shared memory is carved out of the L1 cache, which serves the k-distribution gathers: staging the most-read
     // ~20 KB of the block (key species, reference vmr, minor-absorber lists, the Planck table; not the aerosol and cloud tables) and
     // leaving the rest of the space to L1 measured best on B200 at ncol = 1e5 (LW 17.9 ms against 18.4 with
     // everything staged and 18.7 with nothing; SW 16.8 / 17.0 / 17.1).  RRTMGP_B200_STAGE_BYTES overrides the cap.
     room = std::min(room, 20480);
-    if (const char* e = std::getenv("RRTMGP_B200_STAGE_BYTES")) room = std::min(max_smem_optin - 64 - tail, std::atoi(e));
+    if (const char* e = std::getenv("RRTMGP_B200_STAGE_BYTES")) room = std::min(max_smem_optin - 256 - tail, std::atoi(e));
     F.staged_bytes = 0;
     for (int i = 0; i < P.lut.n_blob_cut; ++i)
         if (P.lut.blob_cut[i] <= room) F.staged_bytes = P.lut.blob_cut[i];
@@ -89,7 +89,7 @@ static int launch_fast_t(SolveParams<float>& P, int max_smem_optin, cudaStream_t
     FastSmem F;
     constexpr int kFastWarps = WARPS;
     const size_t smem = (size_t)plan_smem_fast<WARPS>(P, F, max_smem_optin, MODE == MODE_LW_NOSCAT);
-    if ((int)smem > max_smem_optin) return -1;   // does not fit: generic kernel
+    if ((int)smem > max_smem_optin - 256) return -1;   // does not fit (256: static shared memory): generic kernel
     auto kern = solve_kernel_fast<MODE, NGPT, NG, HAS_CLD, HAS_AER, SPECTRAL, WARPS, NMU>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -155,7 +155,7 @@ static int plan_smem_ws(SolveParams<float>& P, WsSmem& F, int max_smem_optin) {
     if (P.io.band_up != nullptr) { F.off_bacc = off; off = align_up(off + 4 * kWsAccStride * (int)sizeof(float), 128); }
     P.warp_bytes = off;                                        // bytes per pair
     int tail = kWsPairs * off;
-    F.off_vmr = tail;  tail = align_up(tail + (P.ngas > 0 ? P.ngas : 1) * (int)sizeof(float), 128);
+    F.off_vmr = tail;  tail = align_up(tail + ((P.ngas > 0 ? P.ngas : 1) + 1) * (int)sizeof(float), 128);
     F.off_blob = tail;
     int room = max_smem_optin - 1024 - tail;                   // 1024: static shared memory (mbarriers, mailboxes)
     if (const char* e = std::getenv("RRTMGP_B200_STAGE_BYTES")) room = std::min(room, std::atoi(e));

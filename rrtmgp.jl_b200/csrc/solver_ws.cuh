@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(8) uint64_t blob_bar;
+    __shared__ const void* small_tables[TB_COUNT];   // where each small table lives (solver.cuh)
     // per pair: full[kWsStages], empty[kWsStages], column mailbox full[2], empty[2]
     __shared__ __align__(8) uint64_t bars[kWsPairs][2 * kWsStages + 4];
     __shared__ long long colslot[kWsPairs][2];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
     const bool is_rt = warp < kWsPairs;
 
     unsigned char* sblob = smem_raw + F.off_blob;
-    float* svmr = P.vmr_kind == 0 ? reinterpret_cast<float*>(smem_raw + F.off_vmr) : nullptr;
+    float* svmr = P.vmr_kind == 0 ? reinterpret_cast<float*>(smem_raw + F.off_vmr) + 1 : nullptr;
     if (threadIdx.x == 0) {
         mbar_init(&blob_bar, 1);
         mbar_expect_tx(&blob_bar, (uint32_t)F.staged_bytes);
@@ -114,8 +115,9 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
         const int b = threadIdx.x % (2 * kWsStages + 4);
         mbar_init(&bars[threadIdx.x / (2 * kWsStages + 4)][b], b < 2 * kWsStages ? 32u : 1u);
     }
-    if (svmr != nullptr)
-        for (int i = threadIdx.x; i < P.ngas; i += blockDim.x) svmr[i] = __ldg(P.io.vmr + i);
+    if (svmr != nullptr)   // svmr[-1] = 1 (dry air), svmr[ig - 1] = global-mean vmr of gas ig
+        for (int i = threadIdx.x; i <= P.ngas; i += blockDim.x) svmr[i - 1] = i == 0 ? 1.f : __ldg(P.io.vmr + i - 1);
+    fill_small_table_pointers(small_tables, P, sblob, F.staged_bytes, (int)threadIdx.x);
     if (warp == 0) tmem_alloc(&tmem_base_smem, 512u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -470,6 +472,7 @@ __global__ void __launch_bounds__(kWsPairs * 64, 1) solve_kernel_ws(const SolveP
             if (col >= P.ncol) break;
             col_next = next_column();
             Warp<FT, MODE, 2, true> W(P, pbase, lane, col, sblob, F.staged_bytes, svmr);
+            W.tptr = small_tables;
             {
                 const long long nc = col_next;
                 if (nc < P.ncol) {   // the next column's inputs (read once, cold in DRAM) into L2
