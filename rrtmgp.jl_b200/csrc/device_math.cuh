@@ -147,9 +147,9 @@ __device__ __forceinline__ void interp1d_eq_locate(FT xi, const FT* __restrict__
 }
 template <bool S = false, typename FT>
 __device__ __forceinline__ FT interp1d_eq_eval(int loc, FT factor, const FT* __restrict__ y, int n) {
-    if (loc == 0) return ldt<S>(y);
-    if (loc == n) return ldt<S>(y + n - 1);
-    return ldt<S>(y + loc - 1) * (FT(1) - factor) + ldt<S>(y + loc) * factor;
+    // branch-free: the two clamped cases read the end value twice with factor 0 (exactly y[0] / y[n-1])
+    const int i0 = loc > 0 ? loc - 1 : 0, i1 = loc < n ? loc : n - 1;
+    return ldt<S>(y + i0) * (FT(1) - factor) + ldt<S>(y + i1) * factor;
 }
 // ---- optics_utils.jl:51-62 + :21-27 (non-uniform x) ----
 template <bool S = false, typename FT>

@@ -165,7 +165,7 @@ __device__ __forceinline__ void lookup_aerosol(const AeroLut<FT>& A, const FT* s
                                                const AeroLayer& al, FT f, FT& tc, FT& tsc, FT& tsgc) {
     tc = tsc = tsgc = FT(0);
     auto species = [&](int off, int bs) {
-        const FT* p = (((bs >> 23) & 1) ? A.dust : small) + off + (size_t)(bs & 0x7fffff) * ibnd;
+        const FT* p = (((bs >> 23) & 1) ? A.dust : small) + (off + (bs & 0x7fffff) * ibnd);
         const bool rh = (bs >> 24) & 1;
         const int d = rh ? 3 : 0;
         const FT fe = rh ? f : FT(0);
@@ -448,7 +448,7 @@ struct Warp {
             };
             for (int b = 0; b < nb; ++b) {
                 const int ib = b_first + b;
-                FT* r = rec + (size_t)kr * P.rec_row + b * RW;
+                FT* r = rec + (kr * P.rec_row + b * RW);
                 // gas_optics.jl:129-170
                 const int* ksp = tb(L.key_species, TB_KEY_SPECIES) + 2 * ((tropo - 1) + 2 * ib);
                 const int ig1 = ldt<FUSED>(ksp), ig2 = ldt<FUSED>(ksp + 1);
@@ -460,7 +460,7 @@ struct Warp {
                 const int sc0 = FUSED ? 12 : 4;
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                    const FT* vr = tb(L.vmr_ref, TB_VMR_REF) + (size_t)2 * L.ngas1 * (jt - 1 + it) + (tropo - 1);
+                    const FT* vr = tb(L.vmr_ref, TB_VMR_REF) + (2 * L.ngas1 * (jt - 1 + it) + (tropo - 1));
                     FT eta_half = hdiv(ldt<FUSED>(vr + 2 * ig1), ldt<FUSED>(vr + 2 * ig2));
                     FT col_mix = vmr1 + eta_half * vmr2;
                     FT eta = vmr1 * hdiv(FT(1), col_mix);
@@ -508,8 +508,8 @@ struct Warp {
                     if ((cld_j >> 16) & 1) {
                         const CldLut<FT>& C = P.cld;
                         size_t kk = (size_t)col * nlay + k;
-                        const FT* liq = tb(C.liqdata, TB_LIQDATA) + (size_t)3 * C.nsize_liq * ib;
-                        const FT* ice = tb(C.icedata, TB_ICEDATA) + (size_t)3 * C.nsize_ice * (ib + (size_t)C.nband * (P.ice_rgh - 1));
+                        const FT* liq = tb(C.liqdata, TB_LIQDATA) + 3 * C.nsize_liq * ib;
+                        const FT* ice = tb(C.icedata, TB_ICEDATA) + 3 * C.nsize_ice * (ib + C.nband * (P.ice_rgh - 1));
                         FT tl, tls, tlsg, ti, tis, tisg;
                         cld_eval<FUSED>(C.nsize_liq, liq, cld_j & 0xff, cld_fl_j, __ldg(P.io.cld_path_liq + kk), tl, tls, tlsg);
                         cld_eval<FUSED>(C.nsize_ice, ice, (cld_j >> 8) & 0xff, cld_fi_j, __ldg(P.io.cld_path_ice + kk), ti, tis, tisg);
@@ -571,11 +571,11 @@ struct Warp {
                 }
                 // Planck functions of this band (compute_optical_props.jl:157-195 / :43-82)
                 if (LW) {
-                    const FT* totplnk = tb(L.tot_planck, TB_TOT_PLANCK) + (size_t)L.n_t_plnk * ib;
+                    const FT* totplnk = tb(L.tot_planck, TB_TOT_PLANCK) + L.n_t_plnk * ib;
                     // per band: B(t_lev[0..nlay]), then B(t_lay) (no-scattering only), B(t_sfc) last;
                     // the fast kernels keep just the nlev + 1 values they use
                     // (fast no-scattering kernel: B(t_lev) [nlev], B(t_sfc), then B(t_lay) [nlay])
-                    FT* pb = plk + (size_t)b * plk_stride();
+                    FT* pb = plk + b * plk_stride();
                     pb[k + 1] = interp1d_eq_eval<FUSED>(pl_loc_j, pl_f_j, totplnk, L.n_t_plnk);
                     if (k == 0) {
                         pb[0] = interp1d_eq_eval<FUSED>(p0_loc, p0_f, totplnk, L.n_t_plnk);
