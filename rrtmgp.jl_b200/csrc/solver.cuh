@@ -497,7 +497,8 @@ struct Warp {
                     return scaling;
                 };
                 if constexpr (FUSED) {   // unused slots are zero: clear the groups first (128-bit stores), then fill
-                    for (int gi = 0; gi < L.n_minor_groups; ++gi) reinterpret_cast<float4*>(r + sc0)[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    reinterpret_cast<float4*>(r + sc0)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (L.n_minor_groups > 1) reinterpret_cast<float4*>(r + sc0)[1] = make_float4(0.f, 0.f, 0.f, 0.f);   // (fast kernels: one or two groups)
                     if (!LW) r[sc0] = (vmr_h2o + FT(1)) * col_dry;
                 }
                 for (int i = 0; i < nmin; ++i) r[sc0 + soff + i] = minor_scaling(i);
