@@ -29,6 +29,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own log lines (its version banner at communicator creation, anything
+# NCCL_DEBUG asks for) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "columns/sec for all-sky update_fluxes! (ncol=1e5, nlay=64) at 1/2/4/8 B200"
 PARAMS = dict(grav=9.80665, molmass_dryair=0.028964, molmass_water=0.018016)
