@@ -29,9 +29,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own log lines (its version banner at communicator creation, anything
-# NCCL_DEBUG asks for) go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its version
+# banner there at communicator creation on the GPU boxes), so descriptor 1 is pointed at stderr for the whole run and
+# the JSON line goes to a private duplicate of the original stdout.
+sys.stdout.flush()
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
 
 METRIC = "columns/sec for all-sky update_fluxes! (ncol=1e5, nlay=64) at 1/2/4/8 B200"
 PARAMS = dict(grav=9.80665, molmass_dryair=0.028964, molmass_water=0.018016)
@@ -185,7 +192,7 @@ def run_reference(args, rank, world):
                              "sample": f"{ncol_s} of {args.ncol} columns per step (cost is linear in ncol); "
                                        "C++ restatement of the Julia reference, OpenMP over columns"},
             "e2e": {"value": v, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -510,7 +517,7 @@ def main():
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_fp32": roofline_fp32, "roofline_issue": roofline_issue, "cpu_baseline": cpu_baseline,
                 "kernel_ms": {"prepare": ms_prep, "lw": ms_lw, "sw": ms_sw}, "variants": variants, "sweep": sweep, "gather_check": gather_check, "gather": gather_how}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

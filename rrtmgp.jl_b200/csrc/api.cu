@@ -33,12 +33,15 @@ struct NcclApi {
 };
 constexpr int kMaxRanks = 16, kGatheredViews = 8;
 constexpr int kSplitMaxCols = 4 * 12 * 160;    // from four columns per warp (12 warps on up to 160 SMs) nothing is split
+constexpr int kCopyStreams = 4;
 struct CommState {
+    cudaStream_t push_stream(int j) const { return j == 0 ? copy_stream : copy_extra[j - 1]; }
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 0;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr}, ev_copied = nullptr;
+    cudaStream_t copy_stream = nullptr;      // bootstrap collectives and pushes to every kCopyStreams-th peer
+    cudaStream_t copy_extra[kCopyStreams - 1] = {};   // the other peers' pushes: several copy engines / NVLink ports at once
+    cudaEvent_t ev_kernel[6] = {}, ev_copied[kCopyStreams] = {};
     unsigned char* gathered = nullptr;       // this rank's 8 arrays, [view][nranks * ncol][nlev]
     size_t view_bytes = 0;                   // bytes of one gathered view
     unsigned char* peer[kMaxRanks] = {};     // every rank's `gathered` as mapped here (peer[rank] == gathered)
@@ -855,7 +858,8 @@ int rrtmgp_b200_comm_destroy(rrtmgp_b200_handle_t* h) {
     if (c->gathered) cudaFree(c->gathered);
     if (c->token) cudaFree(c->token);
     for (auto& e : c->ev_kernel) if (e) cudaEventDestroy(e);
-    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    for (auto& e : c->ev_copied) if (e) cudaEventDestroy(e);
+    for (auto& x : c->copy_extra) if (x) cudaStreamDestroy(x);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
     h->comm = nullptr;
@@ -878,7 +882,8 @@ int rrtmgp_b200_comm_init(rrtmgp_b200_handle_t* h, const void* unique_id, int32_
     if (rc != 0) { fail_nccl(h, c->nccl, rc); return bail(RRTMGP_B200_ERR_CUDA); }
     cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev_kernel) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming);
+    for (auto& ev : c->ev_copied) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto& x : c->copy_extra) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking);
     const size_t esz = h->cfg.dtype == 1 ? 8 : 4;
     c->view_bytes = (size_t)nranks * h->cfg.ncol * (h->cfg.nlay + 1) * esz;
     // an allocation of its own (cudaMalloc, not a pool): CUDA IPC exports whole allocations
@@ -947,7 +952,7 @@ static cudaError_t push_views(rrtmgp_b200_handle* h, int first, int last, long l
             if (!v[i]) continue;
             unsigned char* dst = c->peer[peer] + i * c->view_bytes + ((size_t)c->rank * h->cfg.ncol + c0) * row;
             const unsigned char* src = (const unsigned char*)v[i] + (size_t)c0 * row;
-            cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)count * row, cudaMemcpyDeviceToDevice, c->copy_stream);
+            cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)count * row, cudaMemcpyDeviceToDevice, c->push_stream(p % kCopyStreams));
             if (e != cudaSuccess) return e;
         }
     }
@@ -972,26 +977,32 @@ int rrtmgp_b200_update_fluxes_gathered(rrtmgp_b200_handle_t* h, uint64_t seed, i
     if (!st) st = f64 ? solve_lw_t<double>(h, sd, 0, ncol, s) : solve_lw_t<float>(h, sd, 0, ncol, s);
     if (st) return st;
     cudaError_t e = cudaEventRecord(c->ev_kernel[0], s);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_kernel[0], 0);
+    for (int j = 0; j < kCopyStreams && e == cudaSuccess; ++j) e = cudaStreamWaitEvent(c->push_stream(j), c->ev_kernel[0], 0);
     if (e == cudaSuccess) e = push_views(h, 0, 3, 0, ncol);                 // longwave views travel under the shortwave kernel
     if (e != cudaSuccess) return fail_cuda(h, e);
-    // shortwave (+ net) in column chunks of whole waves of the persistent kernel; a chunk travels while the next one runs
+    // shortwave (+ net) in column chunks of whole waves of the persistent kernel; a chunk travels while the next one runs,
+    // and the chunks shrink (45 / 30 / 17 / 8 %) because only the last one's pushes are exposed
     const int wave = 12 * (h->sm_count > 0 ? h->sm_count : 148);
-    int nchunk = (h->cfg.spectral_fluxes || ncol < 4 * wave) ? 1 : 3;
+    int nchunk = 1;
+    if (!h->cfg.spectral_fluxes && ncol >= 4 * wave) nchunk = ncol >= 16 * wave ? 4 : 3;
+    static const double kEnd4[4] = {0.45, 0.75, 0.92, 1.0};
     long long c0 = 0;
     for (int i = 0; i < nchunk; ++i) {
-        long long c1 = i + 1 == nchunk ? ncol : (long long)((ncol * (long long)(i + 1) / nchunk) / wave) * wave;
+        const double end = nchunk == 4 ? kEnd4[i] : (double)(i + 1) / nchunk;
+        long long c1 = i + 1 == nchunk ? ncol : ((long long)(ncol * end) / wave) * wave;
         if (c1 <= c0) continue;
         st = f64 ? solve_sw_t<double>(h, sd, true, c0, (int)(c1 - c0), s) : solve_sw_t<float>(h, sd, true, c0, (int)(c1 - c0), s);
         if (st) return st;
         e = cudaEventRecord(c->ev_kernel[1 + i], s);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_kernel[1 + i], 0);
+        for (int j = 0; j < kCopyStreams && e == cudaSuccess; ++j) e = cudaStreamWaitEvent(c->push_stream(j), c->ev_kernel[1 + i], 0);
         if (e == cudaSuccess) e = push_views(h, 3, kGatheredViews, c0, (int)(c1 - c0));
         if (e != cudaSuccess) return fail_cuda(h, e);
         c0 = c1;
     }
-    e = cudaEventRecord(c->ev_copied, c->copy_stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_copied, 0);
+    for (int j = 0; j < kCopyStreams && e == cudaSuccess; ++j) {
+        e = cudaEventRecord(c->ev_copied[j], c->push_stream(j));
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_copied[j], 0);
+    }
     if (e != cudaSuccess) return fail_cuda(h, e);
     return comm_fence(h, 1, s);                                             // everybody's pushes have landed
 }
