@@ -985,6 +985,10 @@ int rrtmgp_b200_update_fluxes_gathered(rrtmgp_b200_handle_t* h, uint64_t seed, i
     const int wave = 12 * (h->sm_count > 0 ? h->sm_count : 148);
     int nchunk = 1;
     if (!h->cfg.spectral_fluxes && ncol >= 4 * wave) nchunk = ncol >= 16 * wave ? 4 : 3;
+    if (const char* env = std::getenv("RRTMGP_B200_GATHER_CHUNKS")) {   // experiments: 1, 3 (equal) or 4 (shrinking)
+        const int n = std::atoi(env);
+        if ((n == 1 || n == 3 || n == 4) && !h->cfg.spectral_fluxes && ncol >= 4 * wave) nchunk = n;
+    }
     static const double kEnd4[4] = {0.45, 0.75, 0.92, 1.0};
     long long c0 = 0;
     for (int i = 0; i < nchunk; ++i) {
