@@ -376,6 +376,13 @@ def main():
                      "peak_source": "measured in this run: scalar FFMA stream, 16 warps/SM (rrtmgp_b200_measure_fp32_peak)",
                      "peak_ffma2": ffma2.value, "frac_of_ffma2_peak": fp32_achieved / ffma2.value,
                      "peak_nominal": FP32_NOMINAL_TFLOPS, "algorithmic_flops_per_column": ALGO_FLOPS_PER_COL}
+    try:   # what the kernels actually execute (FADD + FMUL + 2 FFMA per thread, counted by ncu for this workload)
+        ex = (tj["lw_fp32_flops_executed"] + tj["sw_fp32_flops_executed"]) / tj["ncol"]
+        roofline_fp32.update({"executed_flops_per_column": ex, "achieved_executed": cols_per_s_gpu * ex / 1e12,
+                              "frac_executed": cols_per_s_gpu * ex / 1e12 / ffma.value,
+                              "executed_source": "profiles/traffic.json (" + tj.get("fp32_flops_note", "") + ")"})
+    except Exception:
+        pass
 
     # The two limits that actually bind: warp-instruction issue (4 schedulers x 1 instr/clk per SM) and
     # the L1 data pipe (one 128-byte wavefront/clk per SM, shared + global).  Counts per launch are properties of
