@@ -935,3 +935,58 @@ def test_f64_tensor_memory_and_generic_kernels_agree(real_pack, monkeypatch):
     b = run_engine(real_pack, st, np.float64, **kw)
     _check_f64(a, b, rel=1e-11)
     assert a["solver"].last_launch_count == b["solver"].last_launch_count
+
+
+def _random_case(i):
+    """Deterministic pseudo-random configuration i of the engine (every option the C ABI takes that changes the
+    kernels or their geometry), for `test_randomized_configurations`."""
+    rng = np.random.default_rng(7000 + i)
+    f64 = bool(rng.integers(0, 4) == 0)
+    nlay = int(rng.choice([8, 17, 31, 32, 33, 40, 47, 48, 63, 64, 65, 72, 80, 95]))
+    ncol = int(rng.choice([1, 2, 5, 31, 64, 150, 333]))
+    method = str(rng.choice(["clear_sky", "all_sky", "all_sky"]))
+    aerosols = bool(rng.integers(0, 2))
+    noscat = bool(rng.integers(0, 3) == 0)
+    kw = dict(method=method, aerosols=aerosols, seed=int(rng.integers(0, 2 ** 31)), lw_noscat=noscat,
+              n_gauss_angles=int(rng.integers(1, 5)) if noscat else 1, ice_rgh=int(rng.integers(1, 4)))
+    spectral = (not noscat) and bool(rng.integers(0, 4) == 0)     # spectral_fluxes needs two-stream optics (solver.jl:255-262)
+    st_kw = dict(dtype=np.float64 if f64 else np.float32, seed=int(rng.integers(0, 2 ** 31)),
+                 cld_frac=[1.0, None, None][int(rng.integers(0, 3))], clouds=method != "clear_sky", aerosols=aerosols,
+                 cos_zenith=[0.86, None][int(rng.integers(0, 2))], vmr_kind=str(rng.choice(["gm", "gm", "full"])),
+                 with_lat=bool(rng.integers(0, 2)), z_top=float(rng.choice([30.0e3, 45.0e3, 60.0e3])))
+    extras = (bool(rng.integers(0, 4) == 0), bool(rng.integers(0, 4) == 0), float(rng.uniform(0.5, 40.0)))
+    return f64, ncol, nlay, kw, spectral, st_kw, extras
+
+
+@pytest.mark.parametrize("i", range(96))
+def test_randomized_configurations(real_pack, i):
+    """96 fixed pseudo-random combinations of precision, column / layer count (every kernel geometry and tile
+    boundary), radiation method, aerosols, LW solver and angle count, ice roughness, per-band output, cloud-fraction
+    and sun-angle mode, vmr storage, latitude-dependent gravity, model top, incident LW flux and metric scaling -- each
+    against the oracle at the usual bars (Float64: 1e-9 relative; Float32: the reference's CI thresholds per column,
+    helpers.gate_f32)."""
+    f64, ncol, nlay, kw, spectral, st_kw, (with_inc, with_scaling, inc_total) = _random_case(i)
+    st = R.synthetic.make_atmosphere(ncol, nlay, **st_kw)
+    dt = np.float64 if f64 else np.float32
+    if with_inc:
+        st["inc_flux_lw"] = np.full((256, ncol), inc_total / 256, dtype=dt)
+    if with_scaling:
+        st["metric_scaling"] = np.linspace(0.9, 1.2, ncol * (nlay + 1)).reshape(ncol, nlay + 1).astype(dt)
+    e = run_engine(real_pack, st, dt, spectral=spectral, **kw)
+    o = run_oracle(real_pack, st, np.float64, spectral=spectral, **kw)
+    o32 = None if f64 else run_oracle(real_pack, st, np.float32, spectral=spectral, **kw)
+    cloudy = kw["method"] != "clear_sky" or kw["aerosols"]
+    sw_tol = F32_SW_CLOUDY if cloudy else F32_SW_CLEAR
+    if f64:
+        _check_f64(e, o)
+    else:
+        _check_f32(e, o, F32_LW, sw_tol, o32)
+    if kw["method"] != "clear_sky":
+        np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(dt).astype(np.float64))
+        np.testing.assert_array_equal(e["cld_cover_sw"].astype(np.float64), o["cld_cover_sw"].astype(dt).astype(np.float64))
+    if spectral:
+        for k in ("lw_band_up", "lw_band_dn", "sw_band_up", "sw_band_dn"):
+            if f64:
+                gate_f64(k, e[k], o[k])
+            else:
+                gate_f32(k, e[k], o[k], sw_tol if k.startswith("sw") else F32_LW, o32[k], col_axis=1)
