@@ -37,6 +37,8 @@
 #pragma once
 #include "solver.cuh"
 
+#include <type_traits>
+
 // ABLATION BUILDS (tools/ablation.sh, DESIGN.md section 7 "where the time goes"): -DRB_WHATIF=n removes one part of the kernels
 // so that its cost in elapsed time can be measured (the results of such a build are wrong by construction; the
 // shipped library is built with RB_WHATIF = 0 and contains none of this).  1: band records (phase 1) only for the
@@ -472,6 +474,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 tmem_st1(tAl + (k < kAlphaTmemLevels ? k : kAlphaTmemLevels), v);
                 alpha_hi[(k < kAlphaTmemLevels ? 0 : k - kAlphaTmemLevels + 1) * 32 + lane] = v;
             };
+            // the same store when the caller knows on which side of the split level k lies (the level loops of the
+            // two-stream sweeps run as two single-block loops, below and above the split: one store and its address
+            // instead of two stores and four selects per cell)
+            struct InTmem {}; struct InSmem {}; struct Either {};
+            auto st_alpha_at = [&](auto where, int k, FT v) {
+                using W_ = decltype(where);
+                if constexpr (std::is_same<W_, InTmem>::value) tmem_st1(tAl + k, v);
+                else if constexpr (std::is_same<W_, InSmem>::value) alpha_hi[(k - kAlphaTmemLevels + 1) * 32 + lane] = v;
+                else st_alpha(k, v);
+            };
             auto ld_alpha_t = [&](int k, FT& v) { tmem_ld1(tAl + (k < kAlphaTmemLevels ? k : kAlphaTmemLevels), v); };
             auto ld_alpha_s = [&](int k) -> FT { return alpha_hi[(k < kAlphaTmemLevels ? 0 : k - kAlphaTmemLevels + 1) * 32 + lane]; };
             // g-point sum of the staging tile, read transposed: lane r and lane r + 16 each add half of row r
@@ -502,14 +514,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 FT tau = 0.f, ssa = 0.f, g = 0.f, pf = 0.f;
                 FT lev_bot = 0.f, albedo = 1.f - emis, src = 0.f;
                 // finishes layer kl = k - 1 given the Planck source at its top
-                auto close_layer = [&](int kl, const LwCoef& C, FT denom, FT lev_top) {
+                auto close_layer = [&](auto where, int kl, const LwCoef& C, FT denom, FT lev_top) {
                     const FT dB = lev_bot - lev_top;
                     const FT su = Num<FT>::pi() * (lev_top * C.emis_fac - C.q * dB);
                     const FT sd = Num<FT>::pi() * (lev_bot * C.emis_fac + C.q * dB);
                     // level kl: F_dn(kl) = A F_dn(kl+1) + B ; F_up(kl) = albedo F_dn(kl) + src
 #if RB_WHATIF != 6
                     tmem_st2(tA + 2 * kl, C.Tdif * denom, (C.Rdif * src + sd) * denom);
-                    st_alpha(kl, albedo);
+                    st_alpha_at(where, kl, albedo);
 #endif
                     const FT src_lev = src;
                     src = su + C.Tdif * denom * (src + albedo * sd);
@@ -531,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     unsigned mw = HAS_CLD ? mask_word(ks) >> (ks & 31) : 0u;
                     const FT* pk = pbk + ks;
                     FT* sk = stage + lane;
-                    for (int k = ks; k < ke; ++k) {                       // single basic block
+                    auto level = [&](auto where, int k) {                 // single basic block
                         gather_r(rk, mw & 1u, G);
 #if RB_WHATIF == 5
                         LwCoef C; C.Rdif = ssa * 0.5f; C.Tdif = 0.5f + tau * 1e-3f; C.emis_fac = 0.3f + g; C.q = tau * 1e-2f;
@@ -543,9 +555,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                         const FT inc_k = bk * pf;
                         finish(G, tau, ssa, g, pf);
                         const FT lev_top = hsqrt(inc_k * (bk * pf));
-                        *sk = close_layer(k - 1, C, denom, lev_top);
+                        *sk = close_layer(where, k - 1, C, denom, lev_top);
                         rk += RR; mw >>= 1; ++pk; sk += kStageStride;
-                    }
+                    };
+                    // iteration k closes level k - 1: below the split its albedo goes to tensor memory, above to shared memory
+                    const int ksplit = ke < kAlphaTmemLevels + 1 ? ke : (ks > kAlphaTmemLevels + 1 ? ks : kAlphaTmemLevels + 1);
+                    for (int k = ks; k < ksplit; ++k) level(InTmem{}, k);
+                    for (int k = ksplit; k < ke; ++k) level(InSmem{}, k);
                     __syncwarp();
                     {                                                     // sum_g src of levels ks-1 .. ke-2
                         FT hs;
@@ -558,7 +574,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 {   // top layer: its upper source is its own increment (compute_optical_props.jl:193-195)
                     const LwCoef C = lw_2stream_coeffs_nosrc(tau, ssa, g);
                     const FT denom = hrcp(1.f - C.Rdif * albedo);
-                    const FT s_top = close_layer(nlay - 1, C, denom, pbk[nlay] * pf);
+                    const FT s_top = close_layer(Either{}, nlay - 1, C, denom, pbk[nlay] * pf);
                     FT hs;
                     const FT ssum = warp_sum2(s_top, hs);
                     if (lane == 0) accs[UP * kAccStride + nlay - 1] += ssum;
@@ -763,7 +779,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 }
                 FT tau = 0.f, ssa = 0.f, g = 0.f, pf = 0.f;
                 // layer k: coefficients, TMEM store, marching update; returns d_{k+1} (before the update)
-                auto march = [&](int k) -> FT {
+                auto march = [&](auto where, int k) -> FT {
                     FT Rdir, Tdir, Rdif, Tdif;
 #if RB_WHATIF == 5
                     Rdir = ssa * 0.3f; Tdir = 0.2f + tau * 1e-3f; Rdif = g * 0.1f + 0.1f; Tdif = 0.5f + tau * 1e-3f;
@@ -775,7 +791,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     // F_up(k+1) = A'_k F_up(k) + B'_k ; F_dn_dif(k+1) = beta_{k+1} F_up(k+1) + d_{k+1}
 #if RB_WHATIF != 6
                     tmem_st2(tA + 2 * k, Tdif * denom, (Rdif * d + su) * denom);
-                    st_alpha(k, beta);
+                    st_alpha_at(where, k, beta);
 #endif
                     const FT d_above = d;
                     d = sd + Tdif * denom * (d + beta * su);
@@ -802,13 +818,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     const FT* rk = rec_lane + (jtop & 31) * RR;
                     unsigned mw = HAS_CLD ? mask_word(jtop) << (31 - (jtop & 31)) : 0u;   // bit 31 = layer j
                     FT* sk = stage + ((jtop - jc) * 2) * kStageStride + lane;
-                    for (int j = jtop; j >= jc; --j) {                  // single basic block
+                    auto level = [&](auto where, int j) {               // single basic block
                         gather_r(rk, (mw >> 31) & 1u, G);
-                        sk[0] = march(j + 1);
+                        sk[0] = march(where, j + 1);
                         sk[kStageStride] = dir;
                         finish(G, tau, ssa, g, pf);
                         rk -= RR; mw <<= 1; sk -= 2 * kStageStride;
-                    }
+                    };
+                    // iteration j stores level j + 1: shared memory at and above the split, tensor memory below
+                    const int jsplit = jc > kAlphaTmemLevels - 1 ? jc : (jtop + 1 < kAlphaTmemLevels - 1 ? jtop + 1 : kAlphaTmemLevels - 1);
+                    for (int j = jtop; j >= jsplit; --j) level(InSmem{}, j);
+                    for (int j = (jsplit - 1 < jtop ? jsplit - 1 : jtop); j >= jc; --j) level(InTmem{}, j);
                     __syncwarp();
                     {
                         const int kk = jc + 1 + ((lane & 15) >> 1);
@@ -832,7 +852,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                 }
                 {   // lowest layer
                     FT hd1, hdir0;
-                    const FT d1 = warp_sum2(march(0), hd1), dir0 = warp_sum2(dir, hdir0);
+                    const FT d1 = warp_sum2(march(Either{}, 0), hd1), dir0 = warp_sum2(dir, hdir0);
                     if (lane == 0) { accs[DN * kAccStride + 1] += d1; accs[DN * kAccStride] += dir0; accs[DIR * kAccStride] += dir0; }
                     if (spectral && (lane & 15) == 0) { band_add(DN, 1, hd1); band_add(DN, 0, hdir0); }
                 }
