@@ -40,7 +40,26 @@ mutable struct B200Engine
     handle::Ptr{Cvoid}
 end
 
+const ABI_VERSION = 1
+function __init__()
+    v = ccall((:rrtmgp_b200_abi_version, LIB), Cint, ())
+    v == ABI_VERSION || error("librrtmgp_b200.so has ABI version $v, this binding was written for $ABI_VERSION")
+end
+
 check(st::Cint) = st == 0 || error(unsafe_string(ccall((:rrtmgp_b200_strerror, LIB), Cstring, (Cint,), st)))
+# with the handle at hand a CUDA failure carries the runtime's own message (rrtmgp_b200_last_cuda_error)
+function check(st::Cint, handle::Ptr{Cvoid})
+    st == 0 && return true
+    msg = unsafe_string(ccall((:rrtmgp_b200_strerror, LIB), Cstring, (Cint,), st))
+    st == 4 && (msg *= ": " * unsafe_string(ccall((:rrtmgp_b200_last_cuda_error, LIB), Cstring, (Ptr{Cvoid},), handle)))
+    error(msg)
+end
+
+# rrtmgp_b200_lut_info_t: what `load_luts` found (the host sizes its boundary-condition arrays by these)
+struct LutInfo
+    n_gpt_lw::Int32; n_bnd_lw::Int32; n_gpt_sw::Int32; n_bnd_sw::Int32; ngas::Int32; iband_550nm::Int32
+    p_ref_min::Float64; t_ref_min::Float64; t_ref_max::Float64; solar_src_tot::Float64
+end
 
 devptr(::Nothing) = CuPtr{Cvoid}(0)
 devptr(a) = reinterpret(CuPtr{Cvoid}, pointer(parent(a)))   # parent(): getters hand out SubArray views
@@ -127,6 +146,23 @@ function update_fluxes!(e::B200Engine, seedval = nothing)
                 e.handle, isnothing(seedval) ? UInt64(0) : UInt64(seedval), isnothing(seedval) ? 0 : 1, st))
     return nothing
 end
+# update_lw_fluxes!(s) / update_sw_fluxes!(s) / update_net_fluxes!(s) (src/api/update_fluxes.jl:12-16, 74-78, 165-194): the
+# per-band-type steps of update_fluxes! for a host that calls them one by one (after prepare_atmosphere!)
+seed_args(seedval) = (isnothing(seedval) ? UInt64(0) : UInt64(seedval), Cint(isnothing(seedval) ? 0 : 1))
+update_lw_fluxes!(e::B200Engine, seedval = nothing) =
+    (check(ccall((:rrtmgp_b200_update_lw_fluxes, LIB), Cint, (Ptr{Cvoid}, UInt64, Cint, Ptr{Cvoid}), e.handle, seed_args(seedval)..., CUDA.stream().handle), e.handle); nothing)
+update_sw_fluxes!(e::B200Engine, seedval = nothing) =
+    (check(ccall((:rrtmgp_b200_update_sw_fluxes, LIB), Cint, (Ptr{Cvoid}, UInt64, Cint, Ptr{Cvoid}), e.handle, seed_args(seedval)..., CUDA.stream().handle), e.handle); nothing)
+update_net_fluxes!(e::B200Engine) =
+    (check(ccall((:rrtmgp_b200_update_net_fluxes, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, CUDA.stream().handle), e.handle); nothing)
+# a column range of the bound arrays on a caller-chosen stream (host pipelines that overlap copies with compute)
+update_fluxes_range!(e::B200Engine, seedval, col0::Integer, count::Integer, stream = CUDA.stream()) =
+    (check(ccall((:rrtmgp_b200_update_fluxes_range, LIB), Cint, (Ptr{Cvoid}, UInt64, Cint, Int64, Int32, Ptr{Cvoid}), e.handle,
+                 seed_args(seedval)..., col0, count, stream.handle), e.handle); nothing)
+lut_info(e::B200Engine) = (r = Ref{LutInfo}(); check(ccall((:rrtmgp_b200_lut_info, LIB), Cint, (Ptr{Cvoid}, Ref{LutInfo}), e.handle, r)); r[])
+# kernels launched by the last update call (3 for an all-sky update_fluxes!: prepare, LW, SW)
+last_launch_count(e::B200Engine) = ccall((:rrtmgp_b200_last_launch_count, LIB), Cint, (Ptr{Cvoid},), e.handle)
+
 prepare_atmosphere!(e::B200Engine) =
     (check(ccall((:rrtmgp_b200_prepare_atmosphere, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.handle, CUDA.stream().handle)); nothing)
 

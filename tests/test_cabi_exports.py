@@ -118,3 +118,16 @@ def test_comm_entry_points_validate_arguments(lib):
     assert lib.rrtmgp_b200_update_fluxes_gathered(None, 0, 1, None) == _lib.ERR_INVALID_ARG
     assert lib.rrtmgp_b200_all_gather_fluxes(None, None) == _lib.ERR_INVALID_ARG
     assert C.sizeof(_lib.Gathered) == 8 * C.sizeof(C.c_void_p) and _lib.UNIQUE_ID_BYTES == 128
+
+
+def test_julia_shim_binds_every_entry_point():
+    """INTEGRATION.md's reference-side binding (`julia/RRTMGPB200Ext.jl`, untested here: no Julia) names every function
+    `include/rrtmgp_b200.h` declares, except the one that only the benchmark uses."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "rrtmgp_b200.h")).read()
+    shim = open(os.path.join(root, "julia", "RRTMGPB200Ext.jl")).read()
+    declared = set(re.findall(r"\b(rrtmgp_b200_[a-z0-9_]+)\s*\(", header))
+    bound = set(re.findall(r":(rrtmgp_b200_[a-z0-9_]+)", shim))
+    assert declared - bound <= {"rrtmgp_b200_measure_fp32_peak"}, sorted(declared - bound)
+    assert bound <= declared, sorted(bound - declared)
