@@ -944,7 +944,7 @@ def _random_case(i):
     f64 = bool(rng.integers(0, 4) == 0)
     nlay = int(rng.choice([8, 17, 31, 32, 33, 40, 47, 48, 63, 64, 65, 72, 80, 95]))
     ncol = int(rng.choice([1, 2, 5, 31, 64, 150, 333]))
-    method = str(rng.choice(["clear_sky", "all_sky", "all_sky"]))
+    method = str(rng.choice(["clear_sky", "all_sky", "all_sky", "all_sky_with_clear"]))
     aerosols = bool(rng.integers(0, 2))
     noscat = bool(rng.integers(0, 3) == 0)
     kw = dict(method=method, aerosols=aerosols, seed=int(rng.integers(0, 2 ** 31)), lw_noscat=noscat,
@@ -981,6 +981,14 @@ def test_randomized_configurations(real_pack, i):
         _check_f64(e, o)
     else:
         _check_f32(e, o, F32_LW, sw_tol, o32)
+    if kw["method"] == "all_sky_with_clear":     # the clear-sky snapshot (update_fluxes.jl:39-65, 101-128; aerosols included)
+        clear_sw_tol = F32_SW_CLOUDY if kw["aerosols"] else F32_SW_CLEAR
+        for k in FLUX_KEYS:
+            if f64:
+                gate_f64("clear_" + k, e["clear_" + k], o["clear_" + k])
+            else:
+                tol = F32_LW if k.startswith("lw") else (F32_LW + clear_sw_tol if k == "net" else clear_sw_tol)
+                gate_f32("clear_" + k, e["clear_" + k], o["clear_" + k], tol, o32["clear_" + k])
     if kw["method"] != "clear_sky":
         np.testing.assert_array_equal(e["cld_cover_lw"].astype(np.float64), o["cld_cover_lw"].astype(dt).astype(np.float64))
         np.testing.assert_array_equal(e["cld_cover_sw"].astype(np.float64), o["cld_cover_sw"].astype(dt).astype(np.float64))
