@@ -245,15 +245,16 @@ __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, 
     FT k_mu2 = k_mu * k_mu;
     FT diff = FT(1) - k_mu2;
     const FT win = Num<FT>::k_min();                    // resonance_window = sqrt(eps) (Numerics.jl:49)
-    {   // nudge k mu0 off the removable singularity (branch-free select; the two possible roots are constants)
+    {   // nudge k mu0 off the removable singularity (branch-free select; the two possible roots are constants):
+        // k_mu2 = 1 -+ window, so the denominator 1 - k_mu2 below is +- window itself
         const bool res = rabs(diff) < win;
         const bool below = diff >= FT(0);
         const FT root_lo = rsqrt_(FT(1) - win), root_hi = rsqrt_(FT(1) + win);
-        k_mu2 = res ? (below ? FT(1) - win : FT(1) + win) : k_mu2;
+        diff = res ? (below ? FT(1) - (FT(1) - win) : FT(1) - (FT(1) + win)) : diff;
         k_mu = res ? (below ? root_lo : root_hi) : k_mu;
     }
     FT k_g3 = k * g3, k_g4 = k * g4;
-    RT_term = hdiv(ssa * RT_term, FT(1) - k_mu2);
+    RT_term = hdiv(ssa * RT_term, diff);
     FT Rdir_u = RT_term * ((FT(1) - k_mu) * (a2 + k_g3) - (FT(1) + k_mu) * (a2 - k_g3) * e2 -
                            FT(2) * (k_g3 - a2 * k_mu) * e * T0);
     FT Tdir_u = -RT_term * ((FT(1) + k_mu) * (a1 + k_g4) * T0 - (FT(1) - k_mu) * (a1 - k_g4) * e2 * T0 -

@@ -452,7 +452,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     ssa = 0.f; g = 0.f;
                 } else {
                     tau = rmax(tau + tau_ray, 0.f);
-                    ssa = tau > 0.f ? hdiv(tau_ray, tau) : 0.f;
+                    // gas ssa = tau_ray / tau (0 if tau <= 0, gas_optics.jl:313-318).  With an increment to follow only the
+                    // product tau ssa is used, and that is tau_ray itself: no division
+                    if (INCR) tau_ray = tau > 0.f ? tau_ray : 0.f;
+                    else ssa = tau > 0.f ? hdiv(tau_ray, tau) : 0.f;
                     g = 0.f;
                 }
                 // one fused, unconditional increment (optics_utils.jl:189-202 is additive in tau, tau ssa, tau ssa g;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) solve_kernel_fast(const SolvePa
                     tau += G.x.x;   // absorption optical depth of cloud + aerosol (cloud_optics.jl:1-50, aerosol_optics.jl:18-61)
                 } else if (INCR) {
                     const FT tn = tau + G.x.x;
-                    const FT w = LW ? G.x.y : tau * ssa + G.x.y;       // LW gas: ssa = 0
+                    const FT w = LW ? G.x.y : tau_ray + G.x.y;         // LW gas: ssa = 0; SW gas: tau ssa = tau_ray
                     const FT h = G.x.z;                                  // gas: g = 0 in both
                     g = hdiv(h, rmax(FLT_EPSILON, w));
                     ssa = hdiv(w, rmax(FLT_EPSILON, tn));
