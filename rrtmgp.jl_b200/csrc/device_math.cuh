@@ -225,13 +225,16 @@ __device__ __forceinline__ LwCoef lw_2stream_coeffs_nosrc(float tau, float ssa, 
 template <typename FT>
 __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, FT inv_mu0, FT& Rdir, FT& Tdir,
                                                   FT& Rdif, FT& Tdif) {
-    FT g1 = (FT(8) - ssa * (FT(5) + FT(3) * g)) * FT(0.25);
-    FT g2 = FT(3) * (ssa * (FT(1) - g)) * FT(0.25);
-    FT g3 = (FT(2) - (FT(3) * mu0) * g) * FT(0.25);
-    FT g4 = FT(1) - g3;
+    // PIFM coefficients (shortwave_2stream.jl:193-196) with the constant factors folded in: (8 - ssa (5 + 3 g)) / 4 =
+    // 2 - ssa (1.25 + 0.75 g), 3 ssa (1 - g) / 4 = u - u g with u = 0.75 ssa, (2 - 3 mu0 g) / 4 = 0.5 - (0.75 mu0) g
+    const FT u = FT(0.75) * ssa, c3 = FT(0.75) * mu0;
+    FT g1 = FT(2) - ssa * (FT(1.25) + FT(0.75) * g);
+    FT g2 = u - u * g;
+    FT g3 = FT(0.5) - c3 * g;
+    FT g4 = FT(0.5) + c3 * g;
     FT a1 = g1 * g4 + g2 * g3;
     FT a2 = g1 * g3 + g2 * g4;
-    FT k = hsqrt(rmax(FT(2) * (FT(1) - ssa) * (g1 + g2), Num<FT>::k_min()));
+    FT k = hsqrt(rmax((FT(2) - FT(2) * ssa) * (g1 + g2), Num<FT>::k_min()));
     FT tk = tau * k;
     FT e = hexp(-tk);
     FT e2 = e * e;
