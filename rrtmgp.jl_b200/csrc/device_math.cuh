@@ -53,7 +53,12 @@ __device__ __forceinline__ float rcos(float x) { return cosf(x); }
 __device__ __forceinline__ double rcos(double x) { return cos(x); }
 template <typename FT> __device__ __forceinline__ FT rmax(FT a, FT b) { return a > b ? a : b; }
 template <typename FT> __device__ __forceinline__ FT rmin(FT a, FT b) { return a < b ? a : b; }
-template <typename FT> __device__ __forceinline__ FT rabs(FT a) { return a < FT(0) ? -a : a; }
+__device__ __forceinline__ float rabs(float a) { return fabsf(a); }
+__device__ __forceinline__ double rabs(double a) { return fabs(a); }
+// max(x, 0) as ONE instruction (FMNMX / DMNMX).  `rmax(0, x)` keeps the sign of a zero result and compiles to a compare
+// and a select; where only the value matters (clamps of the two-stream coefficients) this form is used
+__device__ __forceinline__ float rmax0(float x) { return fmaxf(x, 0.f); }
+__device__ __forceinline__ double rmax0(double x) { return fmax(x, 0.0); }
 
 // IEEE division (phase 0: table indices and everything else computed once per (column, layer))
 __device__ __forceinline__ float pdiv(float a, float b) { return __fdiv_rn(a, b); }
@@ -270,9 +275,9 @@ __device__ __forceinline__ void sw_2stream_coeffs(FT tau, FT ssa, FT g, FT mu0, 
     const FT V = a1 + k_mu * k_g4, F = k_g4 + a1 * k_mu;
     FT Rdir_u = RT_term * (U * one_minus_e2kt + S * (one_plus_e2kt - FT(2) * (e * T0)));
     FT Tdir_u = -RT_term * (V * (T0 * one_minus_e2kt) + F * (T0 * one_plus_e2kt - FT(2) * e));
-    Rdir = rmax(FT(0), Rdir_u);
-    Tdir = rmax(FT(0), Tdir_u);
-    FT av_energy = rmax(FT(0), FT(1) - T0);
+    Rdir = rmax0(Rdir_u);
+    Tdir = rmax0(Tdir_u);
+    FT av_energy = rmax0(FT(1) - T0);
     FT tot_dir = Rdir + Tdir;
     {
         FT scale = hdiv(av_energy, rmax(Num<FT>::eps(), tot_dir));
