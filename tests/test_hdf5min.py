@@ -187,3 +187,49 @@ def test_artifact_layout_through_the_hdf5_container(tmp_path, classic_dir, style
     pack_w, _ = T.lut_pack_from_artifact(classic_dir)
     pack_g, _ = T.lut_pack_from_artifact(str(tmp_path))
     assert pack_w == pack_g
+
+
+# ---- property test: random shapes / chunkings / filters / container styles -------------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st_
+
+
+@st_.composite
+def _random_file(draw):
+    rank = draw(st_.integers(0, 4))
+    shape = tuple(draw(st_.integers(1, 7)) for _ in range(rank))
+    dtype = draw(st_.sampled_from(["<f8", "<f4", ">f8", "<i4", "<i2", "<u1", ">i4", "S1", "S5"]))
+    style = draw(st_.sampled_from(["v0", "v2"]))
+    layout = draw(st_.sampled_from(["compact", "contiguous", "chunked", "chunked", "implicit"]))
+    if style == "v0" and layout == "implicit":
+        layout = "chunked"
+    chunk = tuple(draw(st_.integers(1, s)) for s in shape)
+    filters = draw(st_.sampled_from([[], [DEFLATE], [(2, []), DEFLATE], [(2, []), DEFLATE, FLETCHER]])) if layout == "chunked" else []
+    extra = draw(st_.integers(0, 12))
+    seed = draw(st_.integers(0, 2 ** 16))
+    return shape, dtype, style, layout, chunk, filters, extra, seed, draw(st_.booleans()), draw(st_.sampled_from([1, 2, 10]))
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(_random_file())
+def test_random_files_round_trip(tmp_path, case):
+    shape, dtype, style, layout, chunk, filters, extra, seed, dense, page_bits = case
+    rng = np.random.default_rng(seed)
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64))
+    if dt.kind == "S":
+        a = np.array([bytes(rng.integers(65, 91, dt.itemsize).astype(np.uint8)) for _ in range(n)], dtype=dt).reshape(shape)
+    elif dt.kind == "f":
+        a = rng.standard_normal(shape).astype(dt)
+    else:
+        a = rng.integers(0, 100, shape).astype(dt)
+    v = {"x": a}
+    for i in range(extra):
+        v[f"v{i}"] = rng.standard_normal((2,)).astype("<f4")
+    p = str(tmp_path / "r.nc")
+    write_hdf5(p, v, {"d0": 3}, style=style, layout=layout, chunk={"x": chunk}, filters=filters, dense=dense and style == "v2",
+               page_bits=page_bits, split_headers=bool(seed & 1))
+    dims, got = H.read_netcdf4(p)
+    assert dims == {"d0": 3} and set(got) == set(v)
+    for k in v:
+        assert got[k].shape == v[k].shape and got[k].dtype.itemsize == v[k].dtype.itemsize
+        np.testing.assert_array_equal(got[k], v[k])
