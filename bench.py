@@ -376,6 +376,11 @@ def main():
                      "peak_source": "measured in this run: scalar FFMA stream, 16 warps/SM (rrtmgp_b200_measure_fp32_peak)",
                      "peak_ffma2": ffma2.value, "frac_of_ffma2_peak": fp32_achieved / ffma2.value,
                      "peak_nominal": FP32_NOMINAL_TFLOPS, "algorithmic_flops_per_column": ALGO_FLOPS_PER_COL}
+    try:   # the restated reference algorithm's own count (tools/opcount.py: every +, -, *, / of the oracle, per column)
+        with open(os.path.join(ROOT, "profiles", "oracle_opcount.json")) as f:
+            roofline_fp32["reference_algorithm_ops_per_column"] = json.load(f)["per_column"]["total"]["flops_add_mul_div"]
+    except Exception:
+        pass
     try:   # what the kernels actually execute (FADD + FMUL + 2 FFMA per thread, counted by ncu for this workload)
         ex = (tj["lw_fp32_flops_executed"] + tj["sw_fp32_flops_executed"]) / tj["ncol"]
         roofline_fp32.update({"executed_flops_per_column": ex, "achieved_executed": cols_per_s_gpu * ex / 1e12,

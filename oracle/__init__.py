@@ -17,6 +17,8 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
+    if os.environ.get("RRTMGP_ORACLE_LIB"):      # tools/opcount.py: the operation-counting build of the same source
+        return os.environ["RRTMGP_ORACLE_LIB"]
     src = os.path.join(_HERE, "rrtmgp_oracle.cpp")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)

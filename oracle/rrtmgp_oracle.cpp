@@ -1265,6 +1265,12 @@ template <class FT> inline FT gray_tau_sw(int kind, const double* prm, FT p0, FT
 // =====================================================================================
 // C entry points
 // =====================================================================================
+// The Float64 instantiation of the spectral path: `double`, or -- in the operation-count build (oracle/opcount.cpp, which
+// includes this file) -- a counting wrapper of `double` with the same size and layout
+#ifndef ORACLE_F64_T
+#define ORACLE_F64_T double
+#endif
+
 extern "C" {
 
 void* oracle_create(const unsigned char* pack, size_t nbytes, int is_f64) {
@@ -1272,7 +1278,7 @@ void* oracle_create(const unsigned char* pack, size_t nbytes, int is_f64) {
     if (!parse_pack(pack, nbytes, p)) return nullptr;
     try {
         if (is_f64) {
-            auto* h = new OracleHandle<double>();
+            auto* h = new OracleHandle<ORACLE_F64_T>();
             load_gas(p, "lw", false, h->L.lw); load_gas(p, "sw", true, h->L.sw);
             if (p.count("cld_lw/dims")) { load_cld(p, "cld_lw", h->L.cld_lw); load_cld(p, "cld_sw", h->L.cld_sw); }
             if (p.count("aero_lw/dims")) { load_aero(p, "aero_lw", h->L.aero_lw); load_aero(p, "aero_sw", h->L.aero_sw); }
@@ -1286,14 +1292,14 @@ void* oracle_create(const unsigned char* pack, size_t nbytes, int is_f64) {
     } catch (...) { return nullptr; }
 }
 void oracle_destroy(void* h, int is_f64) {
-    if (is_f64) delete (OracleHandle<double>*)h; else delete (OracleHandle<float>*)h;
+    if (is_f64) delete (OracleHandle<ORACLE_F64_T>*)h; else delete (OracleHandle<float>*)h;
 }
 int oracle_update_fluxes(void* h, int is_f64, const OracleState* st, OracleOut* out, const OracleOpts* o) {
-    return is_f64 ? update_fluxes<double>((OracleHandle<double>*)h, st, out, o)
+    return is_f64 ? update_fluxes<ORACLE_F64_T>((OracleHandle<ORACLE_F64_T>*)h, st, out, o)
                   : update_fluxes<float>((OracleHandle<float>*)h, st, out, o);
 }
 int oracle_dims(void* h, int is_f64, int* d) {  // n_gpt_lw, n_bnd_lw, n_gpt_sw, n_bnd_sw, ngas
-    if (is_f64) { auto* H = (OracleHandle<double>*)h; d[0] = H->L.lw.n_gpt; d[1] = H->L.lw.n_bnd; d[2] = H->L.sw.n_gpt; d[3] = H->L.sw.n_bnd; d[4] = H->L.lw.ngas1 - 1; }
+    if (is_f64) { auto* H = (OracleHandle<ORACLE_F64_T>*)h; d[0] = H->L.lw.n_gpt; d[1] = H->L.lw.n_bnd; d[2] = H->L.sw.n_gpt; d[3] = H->L.sw.n_bnd; d[4] = H->L.lw.ngas1 - 1; }
     else { auto* H = (OracleHandle<float>*)h; d[0] = H->L.lw.n_gpt; d[1] = H->L.lw.n_bnd; d[2] = H->L.sw.n_gpt; d[3] = H->L.sw.n_bnd; d[4] = H->L.lw.ngas1 - 1; }
     return 0;
 }

@@ -202,3 +202,23 @@ def test_gray_float32_consistency():
     d = lambda a, b: np.abs(a.astype(np.float64) - b).max()
     assert max(d(o32["lw"]["net"], o64["lw"]["net"]), d(o32["sw"]["net"], o64["sw"]["net"])) <= 1e-3
     assert d(o32["heating_rate"], o64["heating_rate"]) <= 1e-8
+
+
+def test_operation_count_build_of_the_oracle(tmp_path):
+    """tools/opcount.py (SURVEY.md §8d "pin by op-counting the oracle"): the counting build runs the same source, and
+    its counters show the structure of the reference algorithm -- one `log` per (layer, g-point) cell (the pressure
+    interpolation is redone for every g-point, gas_optics.jl:100-115), the longwave two-stream coefficients evaluated
+    twice per cell (longwave_2stream.jl:279,313: two `exp`, two `expm1`)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "ops.json"
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "opcount.py"), "--ncol", "2", "--nlay", "8", "--out", str(out)],
+                          stdout=subprocess.DEVNULL)
+    per = json.load(open(out))["per_column"]
+    cells_lw, cells_sw = 8 * 256, 8 * 224
+    assert per["lw"]["log"] == cells_lw and per["sw"]["log"] == cells_sw
+    assert per["lw"]["exp"] == 2 * cells_lw and per["lw"]["expm1"] == 2 * cells_lw
+    assert per["lw"]["flops_add_mul_div"] > 100 * cells_lw and per["sw"]["flops_add_mul_div"] > 100 * cells_sw
