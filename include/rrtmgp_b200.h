@@ -226,9 +226,9 @@ int rrtmgp_b200_validate_inputs(rrtmgp_b200_handle_t* h, uint32_t* failed, void*
  *                    and opens every peer's copy through CUDA IPC so results can be pushed over NVLink by the copy
  *                    engines.  Every rank must use the same ncol, nlay and dtype.
  *   update_fluxes_gathered   update_fluxes! + the gather, overlapped: the three longwave views travel while the
- *                    shortwave kernel runs, the shortwave / net views per column chunk as it finishes; copies are
- *                    cudaMemcpyAsync on a side stream (DMA engines -- the persistent kernels leave no SM for a
- *                    collective kernel), framed by two one-element NCCL all-reduces (nobody still reads the previous
+ *                    shortwave kernel runs, the shortwave / net views per column chunk as it finishes (chunks shrink so
+ *                    that only a short last push is exposed); copies are cudaMemcpyAsync on four side streams (DMA
+ *                    engines -- the persistent kernels leave no SM for a collective kernel), framed by two one-element NCCL all-reduces (nobody still reads the previous
  *                    step's arrays / everybody's pushes have landed).  On return (stream order) every rank holds all
  *                    columns.
  *   all_gather_fluxes   the plain alternative: one grouped ncclAllGather of the eight views as they are now. */
